@@ -1,0 +1,145 @@
+/*
+ * scico_b200_xray.h -- C ABI of the B200-native X-ray projector pair.
+ *
+ * This is the drop-in boundary for the hot path of lanl/scico's native CT projectors.  Each
+ * entry point replaces one method of the reference (paths relative to the reference checkout):
+ *
+ *   xct2d_plan_create  <- XRayTransform2D.__init__          scico/linop/xray/_xray2d.py:52-136
+ *                         + per-view part of _calc_weights   scico/linop/xray/_xray2d.py:326-347
+ *   xct3d_plan_create  <- XRayTransform3D.__init__          scico/linop/xray/_xray3d.py:54-93
+ *   xct_forward        <- XRayTransform2D._project           scico/linop/xray/_xray2d.py:223-265
+ *                         XRayTransform3D._project           scico/linop/xray/_xray3d.py:110-159
+ *   xct_adjoint        <- XRayTransform2D._back_project      scico/linop/xray/_xray2d.py:267-306
+ *                         XRayTransform3D._back_project      scico/linop/xray/_xray3d.py:161-204
+ *   xct_forward_host / xct_adjoint_host : the same two calls for HOST buffers (what a
+ *                         jax.pure_callback / NumPy caller binds; precedent for an external
+ *                         projector behind LinearOperator: scico/linop/xray/astra/_astra_3d.py:498-511)
+ *   xct3d_debug_weights / xct2d_debug_weights <- XRayTransform3D._calc_weights _xray3d.py:206-266
+ *                         / XRayTransform2D._calc_weights _xray2d.py:308-351 (test hook: dumps the
+ *                         index/weight arrays the reference materialises, for bit-level diffing)
+ *
+ * Conventions
+ *   - plain C, no torch/JAX types; all arrays are C-contiguous float32, indices int32.
+ *   - device entry points take DEVICE pointers, enqueue on `stream` (a cudaStream_t passed as
+ *     void*), never synchronise the host and never allocate: they are CUDA-graph capturable and
+ *     can be called from an XLA FFI handler (XLA owns the buffers; results are fully overwritten).
+ *   - geometry is runtime data (a host table handed to plan_create), never baked at compile time.
+ *   - every function returns 0 on success or a negative xct_status; xct_last_error() returns a
+ *     thread-local message.  Nothing aborts.
+ *   - plans are immutable after creation and may be used concurrently from several threads /
+ *     streams of the device they were created on.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SCICO_B200_XRAY_H
+#define SCICO_B200_XRAY_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define XCT_API
+#else
+#define XCT_API __attribute__((visibility("default")))
+#endif
+
+#define XCT_VERSION 100 /* 0.1.0 */
+
+typedef enum xct_status {
+  XCT_OK = 0,
+  XCT_ERR_INVALID = -1,     /* bad argument (shape, null pointer, ...) */
+  XCT_ERR_CUDA = -2,        /* CUDA runtime error (message in xct_last_error) */
+  XCT_ERR_UNSUPPORTED = -3, /* geometry outside every kernel's envelope */
+  XCT_ERR_NO_DEVICE = -4    /* no CUDA device: there is no CPU fallback */
+} xct_status;
+
+/* plan_create flags */
+#define XCT_FLAG_FORCE_GENERAL 0x1u /* skip the separable fast path (testing / comparison) */
+
+/* kernel families a plan can resolve to (xct_plan_info.path) */
+#define XCT_PATH_2D_PLANE 1   /* 2D, warp-autonomous plane kernels */
+#define XCT_PATH_2D_GENERAL 2 /* 2D, thread-per-pixel fallback */
+#define XCT_PATH_3D_SEP 3     /* 3D, separable geometry: rows <- axis 0 only, cols <- axes 1,2 only */
+#define XCT_PATH_3D_GENERAL 4 /* 3D, arbitrary 2x4 matrices */
+
+typedef struct xct_plan xct_plan; /* opaque */
+
+/* 2D geometry: mirrors the constructor of XRayTransform2D after defaults are resolved. */
+typedef struct xct2d_geom {
+  int32_t n0, n1;          /* image shape (input_shape) */
+  int32_t num_views;       /* len(angles) held by this plan (a view block when view-sharded) */
+  int32_t det_count;       /* ny */
+  const float *view_table; /* HOST (num_views,4) f32: Pxmin, Pdx0, Pdx1, width per view */
+  int32_t device;          /* CUDA device ordinal */
+  uint32_t flags;
+} xct2d_geom;
+
+/* 3D geometry: mirrors XRayTransform3D(input_shape, matrices, det_shape) plus the slab hooks. */
+typedef struct xct3d_geom {
+  int32_t n0, n1, n2;     /* LOCAL volume shape held in memory */
+  int32_t d0, d1;         /* LOCAL detector rows x cols held in memory */
+  int32_t num_views;      /* views held by this plan */
+  const float *matrices;  /* HOST (num_views,2,4) f32 */
+  int32_t slice_offset;   /* added to the axis-0 voxel coordinate (_xray3d.py:212) */
+  int32_t det_row_offset; /* global detector row of local row 0 (z-slab sharding), else 0 */
+  int32_t det_rows_total; /* global D0 used for the in-bounds test; 0 means d0 */
+  int32_t device;
+  uint32_t flags;
+} xct3d_geom;
+
+typedef struct xct_plan_info {
+  int32_t ndim;           /* 2 or 3 */
+  int32_t path;           /* XCT_PATH_* */
+  int32_t num_views;
+  int32_t fwd_lane_stride; /* conflict-free lane stride of the forward kernel (0 = atomics) */
+  int32_t row_aligned;    /* 3D sep: every voxel row lands in exactly one detector row */
+  int32_t device;
+  int64_t in_elems;       /* elements of one forward input (per batch item) */
+  int64_t out_elems;      /* elements of one forward output (per batch item) */
+  int64_t updates;        /* voxel-view updates per application = in_elems * num_views */
+} xct_plan_info;
+
+XCT_API int xct_version(void);
+XCT_API const char *xct_last_error(void);
+XCT_API int xct_device_count(void);
+
+XCT_API int xct2d_plan_create(xct_plan **plan, const xct2d_geom *geom);
+XCT_API int xct3d_plan_create(xct_plan **plan, const xct3d_geom *geom);
+XCT_API void xct_plan_destroy(xct_plan *plan);
+XCT_API int xct_plan_get_info(const xct_plan *plan, xct_plan_info *info);
+
+/* Forward projection.  in: (batch, *input_shape)  out: (batch, *output_shape), DEVICE pointers.
+ * `batch` must be 1 for 3D plans.  `out` is fully overwritten (it may be uninitialised). */
+XCT_API int xct_forward(const xct_plan *plan, const float *in_dev, float *out_dev, int32_t batch,
+                        void *stream);
+/* Back projection (exact adjoint).  in: (batch, *output_shape)  out: (batch, *input_shape). */
+XCT_API int xct_adjoint(const xct_plan *plan, const float *in_dev, float *out_dev, int32_t batch,
+                        void *stream);
+
+/* Same two operators for HOST buffers: H2D copy, kernel(s), D2H copy, synchronous on return.
+ * Device staging buffers are cached inside the plan (these two calls are therefore NOT
+ * re-entrant on one plan). */
+XCT_API int xct_forward_host(xct_plan *plan, const float *in_host, float *out_host, int32_t batch);
+XCT_API int xct_adjoint_host(xct_plan *plan, const float *in_host, float *out_host, int32_t batch);
+
+/* Test hooks: dump what the reference's _calc_weights materialises, as computed by the code path
+ * the plan resolved to.  DEVICE outputs.
+ *   3D: ul (2, n0,n1,n2) int32 [row, col], w (4, n0,n1,n2) f32 [ul, ur, ll, lr], masked.
+ *   2D: inds (n0,n1) int32, w (n0,n1) f32 (tap-0 weight, unmasked, as the reference returns it). */
+XCT_API int xct3d_debug_weights(const xct_plan *plan, int32_t view, int32_t *ul_dev, float *w_dev,
+                                void *stream);
+XCT_API int xct2d_debug_weights(const xct_plan *plan, int32_t view, int32_t *inds_dev, float *w_dev,
+                                void *stream);
+
+/* Number of this library's kernels launched by the calling thread since the last reset
+ * (bench.py's gpu_launches claim). */
+XCT_API int64_t xct_launch_count(void);
+XCT_API void xct_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCICO_B200_XRAY_H */

@@ -1,0 +1,142 @@
+"""ctypes binding of ``libscico_b200_xray.so`` (the C ABI in ``include/scico_b200_xray.h``).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is present when a
+compute entry point is called, an exception is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint32, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libscico_b200_xray.so"
+LIB_PATH = os.path.join(_HERE, LIB_NAME)
+
+XCT_OK = 0
+XCT_ERR_INVALID = -1
+XCT_ERR_CUDA = -2
+XCT_ERR_UNSUPPORTED = -3
+XCT_ERR_NO_DEVICE = -4
+
+FLAG_FORCE_GENERAL = 0x1
+
+PATH_NAMES = {1: "2d_plane", 2: "2d_general", 3: "3d_sep", 4: "3d_general"}
+
+# Every symbol include/scico_b200_xray.h declares (checked by tests/test_abi.py).
+EXPORTED_SYMBOLS = (
+    "xct_version",
+    "xct_last_error",
+    "xct_device_count",
+    "xct2d_plan_create",
+    "xct3d_plan_create",
+    "xct_plan_destroy",
+    "xct_plan_get_info",
+    "xct_forward",
+    "xct_adjoint",
+    "xct_forward_host",
+    "xct_adjoint_host",
+    "xct3d_debug_weights",
+    "xct2d_debug_weights",
+    "xct_launch_count",
+    "xct_launch_count_reset",
+)
+
+
+class Geom2D(ctypes.Structure):
+    _fields_ = [
+        ("n0", c_int32),
+        ("n1", c_int32),
+        ("num_views", c_int32),
+        ("det_count", c_int32),
+        ("view_table", POINTER(c_float)),
+        ("device", c_int32),
+        ("flags", c_uint32),
+    ]
+
+
+class Geom3D(ctypes.Structure):
+    _fields_ = [
+        ("n0", c_int32),
+        ("n1", c_int32),
+        ("n2", c_int32),
+        ("d0", c_int32),
+        ("d1", c_int32),
+        ("num_views", c_int32),
+        ("matrices", POINTER(c_float)),
+        ("slice_offset", c_int32),
+        ("det_row_offset", c_int32),
+        ("det_rows_total", c_int32),
+        ("device", c_int32),
+        ("flags", c_uint32),
+    ]
+
+
+class PlanInfo(ctypes.Structure):
+    _fields_ = [
+        ("ndim", c_int32),
+        ("path", c_int32),
+        ("num_views", c_int32),
+        ("fwd_lane_stride", c_int32),
+        ("row_aligned", c_int32),
+        ("device", c_int32),
+        ("in_elems", c_int64),
+        ("out_elems", c_int64),
+        ("updates", c_int64),
+    ]
+
+
+class XctError(RuntimeError):
+    """Raised when a C-ABI call returns a negative status."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"scico_b200 native call failed ({code}): {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the native library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or scico_b200/build.py).  scico_b200 has no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    L.xct_version.restype = ctypes.c_int
+    L.xct_last_error.restype = c_char_p
+    L.xct_device_count.restype = ctypes.c_int
+    L.xct2d_plan_create.argtypes = [POINTER(c_void_p), POINTER(Geom2D)]
+    L.xct3d_plan_create.argtypes = [POINTER(c_void_p), POINTER(Geom3D)]
+    L.xct_plan_destroy.argtypes = [c_void_p]
+    L.xct_plan_destroy.restype = None
+    L.xct_plan_get_info.argtypes = [c_void_p, POINTER(PlanInfo)]
+    for name in ("xct_forward", "xct_adjoint"):
+        getattr(L, name).argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+    for name in ("xct_forward_host", "xct_adjoint_host"):
+        getattr(L, name).argtypes = [c_void_p, c_void_p, c_void_p, c_int32]
+    L.xct3d_debug_weights.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
+    L.xct2d_debug_weights.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
+    L.xct_launch_count.restype = c_int64
+    L.xct_launch_count_reset.restype = None
+    _lib = L
+    return L
+
+
+def check(code: int) -> None:
+    if code != XCT_OK:
+        raise XctError(code, lib().xct_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(lib().xct_launch_count())
+
+
+def launch_count_reset() -> None:
+    lib().xct_launch_count_reset()

@@ -1,0 +1,540 @@
+// C ABI of the B200-native X-ray projector pair: plan creation (host geometry analysis), kernel
+// dispatch, host-buffer entry points.  See include/scico_b200_xray.h for the contract.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/scico_b200_xray.h"
+#include "xct_general.cuh"
+#include "xct_plane.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int64_t g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define XCT_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(XCT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+// ---- compile-time tile configuration of the plane kernels (see xct_plane.cuh) ----
+constexpr int kWarps = 8;
+// adjoint
+constexpr int kAdjWin = 64;
+constexpr int kAdj3S = 4, kAdj3TA = 16;
+constexpr int kAdj2S = 1, kAdj2TA = 32;
+// forward
+constexpr int kFwdWin = 96;
+constexpr int kFwd3S = 2, kFwd3TN = 16;
+constexpr int kFwd2S = 1, kFwd2TN = 16;
+
+}  // namespace
+
+struct xct_plan {
+  int ndim = 0;
+  int path = 0;          // XCT_PATH_*
+  bool fwd_plane = false;  // forward uses the plane kernel (else general)
+  bool adj_plane = false;
+  int gs = 0;            // forward lane stride (2 or 3)
+  int device = 0;
+  int V = 0;
+  // 2D: n0,n1 image, d1 = ny.  3D: n0,n1,n2 volume, d0,d1 detector
+  int n0 = 0, n1 = 0, n2 = 1, d0 = 1, d1 = 0;
+  int slice_offset = 0, row_off = 0, rows_total = 0;
+  bool row_aligned = false;
+  xct::ViewRec* d_views = nullptr;
+  xct::RowRec* d_rows = nullptr;
+  float* d_mats = nullptr;
+  int* d_list[2] = {nullptr, nullptr};  // [0]: views whose major axis is A, [1]: major axis B
+  int n_list[2] = {0, 0};
+  // host-buffer staging (xct_*_host)
+  float* stage_in = nullptr;
+  float* stage_out = nullptr;
+  size_t cap_in = 0, cap_out = 0;
+  cudaStream_t hstream = nullptr;
+};
+
+namespace {
+
+int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(XCT_ERR_NO_DEVICE,
+                "no CUDA device available: scico_b200 has no CPU fallback (" +
+                    std::string(e == cudaSuccess ? "device count 0" : cudaGetErrorString(e)) + ")");
+  }
+  if (device < 0 || device >= n) return fail(XCT_ERR_INVALID, "device ordinal out of range");
+  return XCT_OK;
+}
+
+// Split the views into the two classes of the forward kernel and pick its lane stride.
+// Returns false when some view is outside the plane kernels' envelope.
+struct Envelope {
+  bool adj_ok = true, fwd_ok = true;
+  int gs = 2;
+  std::vector<int> list[2];
+};
+
+Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fwdTN) {
+  Envelope env;
+  float min_major = 1e30f;
+  for (size_t v = 0; v < views.size(); ++v) {
+    const float a = std::fabs(views[v].ca), b = std::fabs(views[v].cb);
+    if (!std::isfinite(a) || !std::isfinite(b)) {
+      env.adj_ok = env.fwd_ok = false;
+      continue;
+    }
+    // adjoint window: tile adjTA x 32, needs floor(max u) - floor(min u) + 2 <= WIN
+    if (a * (adjTA - 1) + b * 31.f + 3.f > (float)kAdjWin) env.adj_ok = false;
+    const bool major_b = b >= a;
+    env.list[major_b ? 1 : 0].push_back((int)v);
+    min_major = std::min(min_major, std::max(a, b));
+  }
+  // lanes GS voxels apart along the major axis must land >= 1 bin apart
+  if (2.f * min_major >= 1.01f) env.gs = 2;
+  else if (3.f * min_major >= 1.01f) env.gs = 3;
+  else env.fwd_ok = false;
+  if (env.fwd_ok) {
+    for (const auto& vr : views) {
+      const float a = std::fabs(vr.ca), b = std::fabs(vr.cb);
+      const float mj = std::max(a, b), mn = std::min(a, b);
+      if (mj * (32 * env.gs - 1) + mn * (fwdTN - 1) + 3.f > (float)kFwdWin) env.fwd_ok = false;
+    }
+  }
+  return env;
+}
+
+int upload_lists(xct_plan* pl, const Envelope& env) {
+  for (int c = 0; c < 2; ++c) {
+    pl->n_list[c] = (int)env.list[c].size();
+    if (pl->n_list[c] == 0) continue;
+    XCT_CUDA(cudaMalloc(&pl->d_list[c], sizeof(int) * env.list[c].size()));
+    XCT_CUDA(cudaMemcpy(pl->d_list[c], env.list[c].data(), sizeof(int) * env.list[c].size(),
+                        cudaMemcpyHostToDevice));
+  }
+  return XCT_OK;
+}
+
+template <class K>
+int launch_check(const char* name) {
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(XCT_ERR_CUDA, std::string(name) + " launch: " + cudaGetErrorString(e));
+  return XCT_OK;
+}
+int launch_ok(const char* name) { return launch_check<void>(name); }
+
+int general_grid(size_t n) {
+  size_t blocks = (n + 255) / 256;
+  return (int)std::min<size_t>(blocks, 148u * 64u);
+}
+
+xct::PlaneParams plane_params(const xct_plan* pl, int batch) {
+  xct::PlaneParams p{};
+  p.views = pl->d_views;
+  p.rows = pl->d_rows;
+  p.view_list = nullptr;
+  p.n_list = pl->V;
+  p.V = pl->V;
+  if (pl->ndim == 3) {
+    p.NA = pl->n1; p.NB = pl->n2; p.NS = pl->n0; p.D0 = pl->d0; p.D1 = pl->d1;
+  } else {
+    p.NA = pl->n0; p.NB = pl->n1; p.NS = batch; p.D0 = 1; p.D1 = pl->d1;
+  }
+  p.views_per_chunk = pl->V;
+  return p;
+}
+
+// ------------------------------------------------------------------ plane launches
+template <class G, bool IS3D, int S, int TA>
+int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+  xct::PlaneParams p = plane_params(pl, batch);
+  p.tilesA = ceil_div(p.NA, TA);
+  p.tilesB = ceil_div(p.NB, 32);
+  const long long tasks = (long long)ceil_div(p.NS, S) * p.tilesA * p.tilesB;
+  const int blocks = ceil_div(tasks, kWarps);
+  const size_t smem = (size_t)kWarps * 2 * S * kAdjWin * sizeof(float);
+  xct::plane_adjoint_kernel<G, IS3D, S, TA, kAdjWin, kWarps><<<blocks, kWarps * 32, smem, st>>>(p, in, out);
+  return launch_ok("plane_adjoint_kernel");
+}
+
+template <class G, bool IS3D, int S, int TN, int GS, bool MAJOR_B>
+int launch_plane_forward_class(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+  const int cls = MAJOR_B ? 1 : 0;
+  if (pl->n_list[cls] == 0) return XCT_OK;
+  xct::PlaneParams p = plane_params(pl, batch);
+  p.view_list = pl->d_list[cls];
+  p.n_list = pl->n_list[cls];
+  constexpr int TM = 32 * GS;
+  p.tilesA = ceil_div(p.NA, MAJOR_B ? TN : TM);
+  p.tilesB = ceil_div(p.NB, MAJOR_B ? TM : TN);
+  const long long tasks = (long long)ceil_div(p.NS, S) * p.tilesA * p.tilesB;
+  const int blocks = ceil_div(tasks, kWarps);
+  // small problems: split the view list over blockIdx.y so the grid fills the 148 SMs
+  const long long target_warps = 148LL * 32;
+  int chunks = 1;
+  if (tasks < target_warps) chunks = (int)std::min<long long>((target_warps + tasks - 1) / tasks, std::max(1, p.n_list / 4));
+  p.views_per_chunk = ceil_div(p.n_list, chunks);
+  chunks = ceil_div(p.n_list, p.views_per_chunk);
+  const size_t smem = (size_t)kWarps * S * kFwdWin * sizeof(float2);
+  dim3 grid(blocks, chunks);
+  xct::plane_forward_kernel<G, IS3D, S, TN, GS, kFwdWin, MAJOR_B, kWarps><<<grid, kWarps * 32, smem, st>>>(p, in, out);
+  return launch_ok("plane_forward_kernel");
+}
+
+template <class G, bool IS3D, int S, int TN>
+int launch_plane_forward(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+  int rc;
+  if (pl->gs == 2) {
+    if ((rc = launch_plane_forward_class<G, IS3D, S, TN, 2, true>(pl, batch, in, out, st))) return rc;
+    return launch_plane_forward_class<G, IS3D, S, TN, 2, false>(pl, batch, in, out, st);
+  }
+  if ((rc = launch_plane_forward_class<G, IS3D, S, TN, 3, true>(pl, batch, in, out, st))) return rc;
+  return launch_plane_forward_class<G, IS3D, S, TN, 3, false>(pl, batch, in, out, st);
+}
+
+xct::Gen3Params gen3_params(const xct_plan* pl) {
+  xct::Gen3Params g{};
+  g.mats = pl->d_mats;
+  g.V = pl->V; g.N0 = pl->n0; g.N1 = pl->n1; g.N2 = pl->n2; g.D0 = pl->d0; g.D1 = pl->d1;
+  g.slice_offset = pl->slice_offset; g.row_off = pl->row_off; g.rows_total = pl->rows_total;
+  return g;
+}
+xct::Gen2Params gen2_params(const xct_plan* pl, int batch) {
+  xct::Gen2Params g{};
+  g.views = pl->d_views;
+  g.V = pl->V; g.N0 = pl->n0; g.N1 = pl->n1; g.ny = pl->d1; g.batch = batch;
+  return g;
+}
+
+size_t in_elems(const xct_plan* pl) { return (size_t)pl->n0 * pl->n1 * pl->n2; }
+size_t out_elems(const xct_plan* pl) { return (size_t)pl->V * pl->d0 * pl->d1; }
+
+int check_call(const xct_plan* pl, const void* a, const void* b, int batch) {
+  if (!pl) return fail(XCT_ERR_INVALID, "null plan");
+  if (!a || !b) return fail(XCT_ERR_INVALID, "null buffer");
+  if (batch < 1) return fail(XCT_ERR_INVALID, "batch must be >= 1");
+  if (pl->ndim == 3 && batch != 1) return fail(XCT_ERR_INVALID, "3D plans take batch == 1");
+  return XCT_OK;
+}
+
+int ensure_stage(xct_plan* pl, size_t n_in, size_t n_out) {
+  if (!pl->hstream) XCT_CUDA(cudaStreamCreateWithFlags(&pl->hstream, cudaStreamNonBlocking));
+  if (n_in > pl->cap_in) {
+    if (pl->stage_in) cudaFree(pl->stage_in);
+    pl->stage_in = nullptr; pl->cap_in = 0;
+    XCT_CUDA(cudaMalloc(&pl->stage_in, n_in * sizeof(float)));
+    pl->cap_in = n_in;
+  }
+  if (n_out > pl->cap_out) {
+    if (pl->stage_out) cudaFree(pl->stage_out);
+    pl->stage_out = nullptr; pl->cap_out = 0;
+    XCT_CUDA(cudaMalloc(&pl->stage_out, n_out * sizeof(float)));
+    pl->cap_out = n_out;
+  }
+  return XCT_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int xct_version(void) { return XCT_VERSION; }
+const char* xct_last_error(void) { return g_err.c_str(); }
+int64_t xct_launch_count(void) { return g_launches; }
+void xct_launch_count_reset(void) { g_launches = 0; }
+
+int xct_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int xct2d_plan_create(xct_plan** out, const xct2d_geom* g) {
+  if (!out || !g) return fail(XCT_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (g->n0 < 1 || g->n1 < 1 || g->num_views < 1 || g->det_count < 1 || !g->view_table)
+    return fail(XCT_ERR_INVALID, "xct2d_plan_create: bad shape or null view_table");
+  if ((long long)g->n0 * g->n1 > (1LL << 40)) return fail(XCT_ERR_INVALID, "image too large");
+  int rc = check_device(g->device);
+  if (rc) return rc;
+  DeviceGuard guard(g->device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
+
+  xct_plan* pl = new (std::nothrow) xct_plan();
+  if (!pl) return fail(XCT_ERR_INVALID, "out of host memory");
+  pl->ndim = 2; pl->device = g->device; pl->V = g->num_views;
+  pl->n0 = g->n0; pl->n1 = g->n1; pl->n2 = 1; pl->d0 = 1; pl->d1 = g->det_count;
+
+  std::vector<xct::ViewRec> views(g->num_views);
+  bool finite = true;
+  for (int v = 0; v < g->num_views; ++v) {
+    const float* t = g->view_table + 4 * (size_t)v;
+    xct::ViewRec r{};
+    r.off = t[0]; r.ca = t[1]; r.cb = t[2]; r.width = t[3];
+    r.rwidth = 1.0f / t[3];
+    if (!(std::isfinite(t[0]) && std::isfinite(t[1]) && std::isfinite(t[2]) && t[3] > 0.f)) finite = false;
+    views[v] = r;
+  }
+  if (!finite) {
+    delete pl;
+    return fail(XCT_ERR_INVALID, "xct2d_plan_create: non-finite view table or width <= 0");
+  }
+  Envelope env = analyse_views(views, kAdj2TA, kFwd2TN);
+  const bool force_general = (g->flags & XCT_FLAG_FORCE_GENERAL) != 0;
+  pl->adj_plane = env.adj_ok && !force_general;
+  pl->fwd_plane = env.fwd_ok && !force_general;
+  pl->gs = pl->fwd_plane ? env.gs : 0;
+  pl->path = (pl->adj_plane && pl->fwd_plane) ? XCT_PATH_2D_PLANE : XCT_PATH_2D_GENERAL;
+
+  auto cleanup = [&](int code) { xct_plan_destroy(pl); return code; };
+  cudaError_t e = cudaMalloc(&pl->d_views, sizeof(xct::ViewRec) * views.size());
+  if (e == cudaSuccess)
+    e = cudaMemcpy(pl->d_views, views.data(), sizeof(xct::ViewRec) * views.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return cleanup(fail(XCT_ERR_CUDA, std::string("view table upload: ") + cudaGetErrorString(e)));
+  if ((rc = upload_lists(pl, env))) return cleanup(rc);
+  *out = pl;
+  return XCT_OK;
+}
+
+int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
+  if (!out || !g) return fail(XCT_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (g->n0 < 1 || g->n1 < 1 || g->n2 < 1 || g->d0 < 1 || g->d1 < 1 || g->num_views < 1 || !g->matrices)
+    return fail(XCT_ERR_INVALID, "xct3d_plan_create: bad shape or null matrices");
+  if ((long long)g->d0 * g->d1 >= (1LL << 31))
+    return fail(XCT_ERR_INVALID, "detector too large for int32 row*col offsets");
+  int rc = check_device(g->device);
+  if (rc) return rc;
+  DeviceGuard guard(g->device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
+
+  xct_plan* pl = new (std::nothrow) xct_plan();
+  if (!pl) return fail(XCT_ERR_INVALID, "out of host memory");
+  pl->ndim = 3; pl->device = g->device; pl->V = g->num_views;
+  pl->n0 = g->n0; pl->n1 = g->n1; pl->n2 = g->n2; pl->d0 = g->d0; pl->d1 = g->d1;
+  pl->slice_offset = g->slice_offset; pl->row_off = g->det_row_offset;
+  pl->rows_total = g->det_rows_total > 0 ? g->det_rows_total : g->d0;
+  auto cleanup = [&](int code) { xct_plan_destroy(pl); return code; };
+
+  const int V = g->num_views;
+  bool sep = true, finite = true;
+  for (int v = 0; v < V; ++v) {
+    const float* M = g->matrices + 8 * (size_t)v;
+    for (int q = 0; q < 8; ++q) finite = finite && std::isfinite(M[q]);
+    // rows depend on voxel axis 0 only, columns on axes 1, 2 only
+    if (!(M[1] == 0.f && M[2] == 0.f && M[4] == 0.f)) sep = false;
+  }
+  if (!finite) return cleanup(fail(XCT_ERR_INVALID, "xct3d_plan_create: non-finite matrix entry"));
+
+  cudaError_t e = cudaMalloc(&pl->d_mats, sizeof(float) * 8 * (size_t)V);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_mats, g->matrices, sizeof(float) * 8 * (size_t)V, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return cleanup(fail(XCT_ERR_CUDA, std::string("matrix upload: ") + cudaGetErrorString(e)));
+
+  pl->path = XCT_PATH_3D_GENERAL;
+  if (sep && !(g->flags & XCT_FLAG_FORCE_GENERAL)) {
+    std::vector<xct::ViewRec> views(V);
+    for (int v = 0; v < V; ++v) {
+      const float* M = g->matrices + 8 * (size_t)v;
+      xct::ViewRec r{};
+      r.ca = M[5]; r.cb = M[6]; r.off = M[7]; r.width = 1.f; r.rwidth = 1.f;
+      views[v] = r;
+    }
+    Envelope env = analyse_views(views, kAdj3TA, kFwd3TN);
+    if (env.gs != 2) env.fwd_ok = false;  // only the stride-2 forward is instantiated for 3D
+    if (env.adj_ok || env.fwd_ok) {
+      // Row records: voxel slice i of view v -> detector row(s) and axis-0 weights.
+      // Same expression tree as _xray3d.py:216 with the two zero coefficients kept, so that the
+      // result (including signed zeros) is what the general formula gives.  This translation unit
+      // is compiled with -ffp-contract=off for host code: every product and sum rounds to fp32.
+      std::vector<xct::RowRec> rows((size_t)V * g->n0);
+      bool aligned = true;
+      for (int v = 0; v < V; ++v) {
+        const float* M = g->matrices + 8 * (size_t)v;
+        for (int i = 0; i < g->n0; ++i) {
+          volatile float xi = ((float)i + 0.5f) + (float)g->slice_offset;
+          volatile float t0 = M[0] * xi;
+          volatile float t1 = M[1] * 0.5f;
+          volatile float t2 = M[2] * 0.5f;
+          volatile float s = t0 + t1;
+          s = s + t2;
+          s = s + M[3];
+          volatile float left = s - 0.25f;
+          volatile float d = std::ceil(left) - left;
+          const float tn = std::fmin(d, 0.5f);
+          const long long rg = (long long)std::floor(left);
+          xct::RowRec rr{};
+          long long rl = rg - g->det_row_offset;
+          rl = std::max<long long>(-2, std::min<long long>(rl, (long long)g->d0 + 1));
+          rr.r0 = (int)rl;
+          volatile float un = 0.5f - tn;
+          rr.w0 = tn * 4.0f;
+          rr.w1 = un * 4.0f;
+          const bool in0 = rg >= 0 && rg < pl->rows_total && rl >= 0 && rl < g->d0;
+          const bool in1 = rg + 1 >= 0 && rg + 1 < pl->rows_total && rl + 1 >= 0 && rl + 1 < g->d0;
+          if (!in0) rr.w0 = 0.f;
+          if (!in1) rr.w1 = 0.f;
+          if (rr.w0 != 0.f && rr.w1 != 0.f) aligned = false;
+          rows[(size_t)v * g->n0 + i] = rr;
+        }
+      }
+      pl->row_aligned = aligned;
+      e = cudaMalloc(&pl->d_views, sizeof(xct::ViewRec) * views.size());
+      if (e == cudaSuccess) e = cudaMemcpy(pl->d_views, views.data(), sizeof(xct::ViewRec) * views.size(), cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMalloc(&pl->d_rows, sizeof(xct::RowRec) * rows.size());
+      if (e == cudaSuccess) e = cudaMemcpy(pl->d_rows, rows.data(), sizeof(xct::RowRec) * rows.size(), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return cleanup(fail(XCT_ERR_CUDA, std::string("table upload: ") + cudaGetErrorString(e)));
+      if ((rc = upload_lists(pl, env))) return cleanup(rc);
+      pl->adj_plane = env.adj_ok;
+      pl->fwd_plane = env.fwd_ok;
+      pl->gs = env.fwd_ok ? env.gs : 0;
+      if (pl->adj_plane && pl->fwd_plane) pl->path = XCT_PATH_3D_SEP;
+    }
+  }
+  *out = pl;
+  return XCT_OK;
+}
+
+void xct_plan_destroy(xct_plan* pl) {
+  if (!pl) return;
+  DeviceGuard guard(pl->device);
+  cudaFree(pl->d_views);
+  cudaFree(pl->d_rows);
+  cudaFree(pl->d_mats);
+  cudaFree(pl->d_list[0]);
+  cudaFree(pl->d_list[1]);
+  cudaFree(pl->stage_in);
+  cudaFree(pl->stage_out);
+  if (pl->hstream) cudaStreamDestroy(pl->hstream);
+  delete pl;
+}
+
+int xct_plan_get_info(const xct_plan* pl, xct_plan_info* info) {
+  if (!pl || !info) return fail(XCT_ERR_INVALID, "null argument");
+  info->ndim = pl->ndim;
+  info->path = pl->path;
+  info->num_views = pl->V;
+  info->fwd_lane_stride = pl->gs;
+  info->row_aligned = pl->row_aligned ? 1 : 0;
+  info->device = pl->device;
+  info->in_elems = (int64_t)in_elems(pl);
+  info->out_elems = (int64_t)out_elems(pl);
+  info->updates = info->in_elems * pl->V;
+  return XCT_OK;
+}
+
+int xct_forward(const xct_plan* pl, const float* in, float* out, int32_t batch, void* stream) {
+  int rc = check_call(pl, in, out, batch);
+  if (rc) return rc;
+  DeviceGuard guard(pl->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  // every forward kernel accumulates with RED: the (possibly uninitialised) output is zeroed first
+  XCT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * out_elems(pl) * batch, st));
+  if (pl->ndim == 3) {
+    if (pl->fwd_plane) return launch_plane_forward<xct::Geom3, true, kFwd3S, kFwd3TN>(pl, 1, in, out, st);
+    xct::gen3d_forward_kernel<<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, out);
+    return launch_ok("gen3d_forward_kernel");
+  }
+  if (pl->fwd_plane) return launch_plane_forward<xct::Geom2, false, kFwd2S, kFwd2TN>(pl, batch, in, out, st);
+  xct::gen2d_forward_kernel<<<general_grid(in_elems(pl) * batch), 256, 0, st>>>(gen2_params(pl, batch), in, out);
+  return launch_ok("gen2d_forward_kernel");
+}
+
+int xct_adjoint(const xct_plan* pl, const float* in, float* out, int32_t batch, void* stream) {
+  int rc = check_call(pl, in, out, batch);
+  if (rc) return rc;
+  DeviceGuard guard(pl->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pl->ndim == 3) {
+    if (pl->adj_plane) return launch_plane_adjoint<xct::Geom3, true, kAdj3S, kAdj3TA>(pl, 1, in, out, st);
+    xct::gen3d_adjoint_kernel<<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, out);
+    return launch_ok("gen3d_adjoint_kernel");
+  }
+  if (pl->adj_plane) return launch_plane_adjoint<xct::Geom2, false, kAdj2S, kAdj2TA>(pl, batch, in, out, st);
+  xct::gen2d_adjoint_kernel<<<general_grid(in_elems(pl) * batch), 256, 0, st>>>(gen2_params(pl, batch), in, out);
+  return launch_ok("gen2d_adjoint_kernel");
+}
+
+static int run_host(xct_plan* pl, const float* in_host, float* out_host, int32_t batch, bool forward) {
+  int rc = check_call(pl, in_host, out_host, batch);
+  if (rc) return rc;
+  DeviceGuard guard(pl->device);
+  const size_t n_in = (forward ? in_elems(pl) : out_elems(pl)) * batch;
+  const size_t n_out = (forward ? out_elems(pl) : in_elems(pl)) * batch;
+  if ((rc = ensure_stage(pl, n_in, n_out))) return rc;
+  XCT_CUDA(cudaMemcpyAsync(pl->stage_in, in_host, n_in * sizeof(float), cudaMemcpyHostToDevice, pl->hstream));
+  rc = forward ? xct_forward(pl, pl->stage_in, pl->stage_out, batch, pl->hstream)
+               : xct_adjoint(pl, pl->stage_in, pl->stage_out, batch, pl->hstream);
+  if (rc) return rc;
+  XCT_CUDA(cudaMemcpyAsync(out_host, pl->stage_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, pl->hstream));
+  XCT_CUDA(cudaStreamSynchronize(pl->hstream));
+  return XCT_OK;
+}
+
+int xct_forward_host(xct_plan* pl, const float* in_host, float* out_host, int32_t batch) {
+  return run_host(pl, in_host, out_host, batch, true);
+}
+int xct_adjoint_host(xct_plan* pl, const float* in_host, float* out_host, int32_t batch) {
+  return run_host(pl, in_host, out_host, batch, false);
+}
+
+int xct3d_debug_weights(const xct_plan* pl, int32_t view, int32_t* ul, float* w, void* stream) {
+  if (!pl || !ul || !w) return fail(XCT_ERR_INVALID, "null argument");
+  if (pl->ndim != 3) return fail(XCT_ERR_INVALID, "not a 3D plan");
+  if (view < 0 || view >= pl->V) return fail(XCT_ERR_INVALID, "view out of range");
+  DeviceGuard guard(pl->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pl->adj_plane || pl->fwd_plane) {
+    xct::sep3d_weights_kernel<<<general_grid(in_elems(pl)), 256, 0, st>>>(
+        pl->d_views, pl->d_rows, view, pl->n0, pl->n1, pl->n2, pl->d1, pl->row_off, ul, w);
+    return launch_ok("sep3d_weights_kernel");
+  }
+  xct::gen3d_weights_kernel<<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), view, ul, w);
+  return launch_ok("gen3d_weights_kernel");
+}
+
+int xct2d_debug_weights(const xct_plan* pl, int32_t view, int32_t* inds, float* w, void* stream) {
+  if (!pl || !inds || !w) return fail(XCT_ERR_INVALID, "null argument");
+  if (pl->ndim != 2) return fail(XCT_ERR_INVALID, "not a 2D plan");
+  if (view < 0 || view >= pl->V) return fail(XCT_ERR_INVALID, "view out of range");
+  DeviceGuard guard(pl->device);
+  xct::gen2d_weights_kernel<<<general_grid(in_elems(pl)), 256, 0, (cudaStream_t)stream>>>(
+      gen2_params(pl, 1), view, inds, w);
+  return launch_ok("gen2d_weights_kernel");
+}
+
+}  // extern "C"

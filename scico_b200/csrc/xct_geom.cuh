@@ -1,0 +1,78 @@
+// Geometry policies shared by every kernel: the fp32 expression trees of the reference's
+// _calc_weights, written with explicit round-to-nearest intrinsics so that ptxas can never
+// contract a product and a sum into an FMA.  Bin indices (and, in 3D, the "left edge is an exact
+// integer" case of _xray3d.py:224) are discontinuous in the coordinate, so the coordinate must be
+// bit-identical to the oracle's; weights only need to agree to an ulp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xct {
+
+// One record per view, built on the host (see xct_api.cu) and read through the constant/L1 path.
+struct __align__(16) ViewRec {
+  float ca;      // coefficient of plane axis A   3D: M[1,1] (voxel axis 1)   2D: Pdx0 (image axis 0)
+  float cb;      // coefficient of plane axis B   3D: M[1,2] (voxel axis 2)   2D: Pdx1 (image axis 1)
+  float off;     // 3D: M[1,3]                                           2D: Pxmin
+  float width;   // 2D: projected pixel width                             3D: unused
+  float rwidth;  // 2D: 1/width (correctly rounded)                       3D: unused
+  float pad0, pad1, pad2;
+};
+
+// 3D separable geometry, plane = (voxel axis 1, voxel axis 2) -> detector column.
+//   Px = ((M10*x0 + M11*x1) + M12*x2) + M13 with M10 == 0   (_xray3d.py:217)
+//   left = Px - w/2, w = 0.5                                 (_xray3d.py:223)
+struct Geom3 {
+  static __device__ __forceinline__ float hoistA(const ViewRec& v, int a) {
+    return __fmul_rn(v.ca, (float)a + 0.5f);
+  }
+  static __device__ __forceinline__ float hoistB(const ViewRec& v, int b) {
+    return __fmul_rn(v.cb, (float)b + 0.5f);
+  }
+  static __device__ __forceinline__ float combine(const ViewRec& v, float hA, float hB) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(hA, hB), v.off), -0.25f);
+  }
+  // c = floor(left); w0 = to_next = min(ceil(left)-left, 0.5) (0 when left is an integer,
+  // _xray3d.py:224); w1 = 0.5 - to_next.  The common factor 1/w^2 = 4 lives in the row weights.
+  static __device__ __forceinline__ void bins(const ViewRec&, float u, int& c, float& w0, float& w1) {
+    c = __float2int_rd(u);
+    w0 = fminf(__fadd_rn(ceilf(u), -u), 0.5f);
+    w1 = __fadd_rn(0.5f, -w0);
+  }
+};
+
+// 2D geometry, plane = (image axis 0, image axis 1) -> detector bin.
+//   Px = (Pxmin + Pdx0*i) + Pdx1*j                            (_xray2d.py:331-335)
+struct Geom2 {
+  static __device__ __forceinline__ float hoistA(const ViewRec& v, int a) {
+    return __fadd_rn(v.off, __fmul_rn(v.ca, (float)a));
+  }
+  static __device__ __forceinline__ float hoistB(const ViewRec& v, int b) {
+    return __fmul_rn(v.cb, (float)b);
+  }
+  static __device__ __forceinline__ float combine(const ViewRec&, float hA, float hB) {
+    return __fadd_rn(hA, hB);
+  }
+  // inds = floor(Px); weights = min(1 - (Px - inds), width) / width   (_xray2d.py:338,348-349)
+  static __device__ __forceinline__ void bins(const ViewRec& v, float u, int& c, float& w0, float& w1) {
+    float fl = floorf(u);
+    c = __float2int_rd(u);
+    float m = fminf(__fadd_rn(1.0f, -__fadd_rn(u, -fl)), v.width);
+    // correctly rounded m/width from the host-rounded reciprocal plus one Markstein step
+    float q = __fmul_rn(m, v.rwidth);
+    float e = __fmaf_rn(-q, v.width, m);
+    w0 = __fmaf_rn(e, v.rwidth, q);
+    w1 = __fadd_rn(1.0f, -w0);
+  }
+};
+
+// Row record of the 3D separable path: where voxel slice i of view v lands on the detector's
+// axis 0 and with which weights (already multiplied by 1/w^2 = 4 and masked to 0 out of bounds).
+struct __align__(16) RowRec {
+  int32_t r0;  // LOCAL detector row of the first tap (may be -1 or d0-1 with a zero weight beside it)
+  float w0;    // weight of row r0      = 4*to_next0          (0 if row r0 is out of bounds)
+  float w1;    // weight of row r0 + 1  = 4*(0.5 - to_next0)  (0 if row r0+1 is out of bounds)
+  int32_t pad;
+};
+
+}  // namespace xct
