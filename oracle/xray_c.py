@@ -96,3 +96,14 @@ def weights_3d(matrix, input_shape, det_shape, slice_offset=0):
     lib().xo_weights_3d(pm, *n, int(det_shape[0]), int(det_shape[1]), int(slice_offset),
                         ul.ctypes.data_as(_ip), w.ctypes.data_as(_fp))
     return ul, w
+
+
+def back_project_3d_points(proj, matrices, points, slice_offset=0):
+    """Back projection at selected voxels ``points`` (npts, 3) int32 -> (npts,) float32."""
+    proj, pp = _f(proj)
+    M, pm = _f(matrices)
+    pts = np.ascontiguousarray(points, dtype=np.int32)
+    out = np.empty(len(pts), dtype=np.float32)
+    lib().xo_back_project_3d_points(pp, pm, M.shape[0], proj.shape[1], proj.shape[2], int(slice_offset),
+                                    pts.ctypes.data_as(_ip), len(pts), out.ctypes.data_as(_fp))
+    return out

@@ -399,7 +399,7 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
           const long long rg = (long long)std::floor(left);
           xct::RowRec rr{};
           long long rl = rg - g->det_row_offset;
-          rl = std::max<long long>(-2, std::min<long long>(rl, (long long)g->d0 + 1));
+          rl = std::max<long long>(-(1LL << 30), std::min<long long>(rl, 1LL << 30));  // int range only
           rr.r0 = (int)rl;
           volatile float un = 0.5f - tn;
           rr.w0 = tn * 4.0f;

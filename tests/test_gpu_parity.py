@@ -1,0 +1,295 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, on the B200.
+
+Tolerances are BASELINE.json's: relative L2 <= 1e-5 in fp32 for both directions and
+|<Ax,y> - <x,A^T y>| / (|Ax| |y|) < 1e-5.  Bin indices (int32) and the zero pattern of the
+weights must be bit-exact; weights themselves agree to an ulp (asserted <= 2.4e-7 absolute).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import scico_b200 as sb
+from scico_b200 import _lib
+from scico_b200.xray import debug_weights_2d, debug_weights_3d
+from oracle import xray_c as C
+from oracle import xray_np as O
+
+TOL = 1e-5
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+
+
+@pytest.fixture(scope="module")
+def torch_dev(cuda_device):
+    import torch
+
+    return torch, cuda_device
+
+
+def _gpu(torch, dev, op, x, adj=False):
+    t = torch.as_tensor(np.ascontiguousarray(x), device=dev)
+    return (op.adj(t) if adj else op(t)).cpu().numpy()
+
+
+def _x_mats(N, D, V, **kw):
+    return sb.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, V, endpoint=False)[:, None], **kw)
+
+
+CASES_3D = {
+    "x16_det11": ((16, 16, 16), (11, 11), lambda: _x_mats((16,) * 3, (11, 11), 3)),
+    "x_ragged": ((17, 18, 19), (20, 21), lambda: _x_mats((17, 18, 19), (20, 21), 5)),
+    "x_wide": ((5, 70, 150), (5, 170), lambda: _x_mats((5, 70, 150), (5, 170), 11)),
+    "x_tall": ((9, 150, 33), (12, 100), lambda: _x_mats((9, 150, 33), (12, 100), 8)),
+    "x_single_view": ((4, 40, 40), (4, 57), lambda: _x_mats((4, 40, 40), (4, 57), 1)),
+    "x_tiny": ((1, 1, 1), (1, 1), lambda: _x_mats((1, 1, 1), (1, 1), 2)),
+    "x_unaligned_rows": ((32, 48, 40), (40, 70), lambda: _x_mats((32, 48, 40), (40, 70), 6, voxel_spacing=[0.8, 1, 1])),
+    "x_det_offcentre": ((12, 30, 30), (20, 30), lambda: _x_mats((12, 30, 30), (20, 30), 4)),
+    "xy_tilt": ((17, 18, 19), (20, 21), lambda: sb.matrices_from_euler_angles(
+        (17, 18, 19), (20, 21), "XY", np.stack([np.linspace(0, np.pi, 5, endpoint=False), np.full(5, np.deg2rad(74.0))], 1))),
+    "y_rot": ((20, 12, 24), (30, 14), lambda: sb.matrices_from_euler_angles(
+        (20, 12, 24), (30, 14), "Y", np.linspace(0, np.pi, 5, endpoint=False)[:, None])),
+    "along_axis0": ((3, 6, 5), (4, 4), lambda: np.array([[[0, 1, 0, -2], [0, 0, 1, -1]]], dtype=np.float64)),
+    "magnified": ((8, 20, 20), (20, 50), lambda: _x_mats((8, 20, 20), (20, 50), 4, voxel_spacing=[2.0, 2.0, 2.0])),
+}
+
+
+def _quirk_mats():
+    M = _x_mats((8, 12, 10), (9, 16), 3)
+    M[:, :, 3] += 0.25
+    return M
+
+
+CASES_3D["quirk_integer_edges"] = ((8, 12, 10), (9, 16), _quirk_mats)
+
+
+@pytest.mark.parametrize("force_general", [False, True], ids=["auto", "general"])
+@pytest.mark.parametrize("name", list(CASES_3D))
+def test_3d_parity(torch_dev, name, force_general):
+    torch, dev = torch_dev
+    N, D, mk = CASES_3D[name]
+    M = mk()
+    A = sb.XRayTransform3D(N, M, D, _flags=_lib.FLAG_FORCE_GENERAL if force_general else 0)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(N).astype(np.float32)
+    y = rng.standard_normal(A.output_shape).astype(np.float32)
+    Ax, ATy = _gpu(torch, dev, A, x), _gpu(torch, dev, A, y, adj=True)
+    assert O.rel_l2(Ax, C.project_3d(x, A.matrices, D)) <= TOL
+    assert O.rel_l2(ATy, C.back_project_3d(y, A.matrices, N)) <= TOL
+    ns, ref = O.adjoint_gap(Ax, y, x, ATy)
+    assert ns < TOL
+    # index / weight arrays of _calc_weights, every view
+    for v in range(len(M)):
+        ul, w = debug_weights_3d(A, v)
+        rul, rw = C.weights_3d(A.matrices[v], N, D)
+        np.testing.assert_array_equal(w == 0, rw == 0)
+        live = (rw != 0).any(axis=0)
+        np.testing.assert_array_equal(ul[:, live], rul[:, live])
+        assert np.abs(w - rw).max() <= 2.4e-7
+
+
+def test_3d_paths_selected(torch_dev):
+    A = sb.XRayTransform3D((16,) * 3, _x_mats((16,) * 3, (16, 16), 4), (16, 16))
+    assert A.plan_info()["path_name"] == "3d_sep" and A.plan_info()["row_aligned"] == 1
+    N, D, mk = CASES_3D["xy_tilt"]
+    assert sb.XRayTransform3D(N, mk(), D).plan_info()["path_name"] == "3d_general"
+
+
+CASES_2D = {
+    "12x13": dict(nx=(12, 13), V=10),
+    "16x16_det11": dict(nx=(16, 16), V=3, dx=1.0 / np.sqrt(2), det_count=11),
+    "64x64": dict(nx=(64, 64), V=90),
+    "ragged": dict(nx=(101, 67), V=37, span=2 * np.pi),
+    "dx_half": dict(nx=(300, 200), V=50, dx=0.5),
+    "aniso": dict(nx=(90, 120), V=40, dx=(0.5, 0.7)),
+    "single_pixel": dict(nx=(1, 1), V=4),
+    "small_det": dict(nx=(80, 80), V=24, det_count=40),
+    "big_det": dict(nx=(40, 40), V=24, det_count=200),
+    "c2_512": dict(nx=(512, 512), V=360),
+}
+
+
+@pytest.mark.parametrize("force_general", [False, True], ids=["auto", "general"])
+@pytest.mark.parametrize("name", list(CASES_2D))
+def test_2d_parity(torch_dev, name, force_general):
+    torch, dev = torch_dev
+    kw = dict(CASES_2D[name])
+    nx, V, span = kw.pop("nx"), kw.pop("V"), kw.pop("span", np.pi)
+    angles = np.linspace(0, span, V, endpoint=False)
+    A = sb.XRayTransform2D(nx, angles, _flags=_lib.FLAG_FORCE_GENERAL if force_general else 0, **kw)
+    if name == "c2_512":
+        assert A.ny == 725  # BASELINE.json configs[1]
+    T = O.view_table_2d(angles, A.x0, A.dx, A.y0)
+    np.testing.assert_array_equal(T, A.view_table)
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal(nx).astype(np.float32)
+    y = rng.standard_normal(A.output_shape).astype(np.float32)
+    Ax, ATy = _gpu(torch, dev, A, x), _gpu(torch, dev, A, y, adj=True)
+    assert O.rel_l2(Ax, C.project_2d(x, T, A.ny)) <= TOL
+    assert O.rel_l2(ATy, C.back_project_2d(y, T, nx)) <= TOL
+    ns, ref = O.adjoint_gap(Ax, y, x, ATy)
+    assert ns < TOL
+    for v in sorted({0, V // 3, V - 1}):
+        inds, w = debug_weights_2d(A, v)
+        rinds, rw = C.weights_2d(T[v], nx)
+        np.testing.assert_array_equal(inds, rinds)
+        assert np.abs(w - rw).max() <= 2.4e-7
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(f)[:-4] for f in GOLDEN])
+def test_golden_fixtures(torch_dev, path):
+    torch, dev = torch_dev
+    g = np.load(path)
+    if str(g["kind"]) == "2d":
+        A = sb.XRayTransform2D(tuple(g["nx"]), g["angles"], dx=tuple(g["dx"]), det_count=int(g["det_count"]))
+        np.testing.assert_array_equal(A.view_table, g["table"])
+    else:
+        A = sb.XRayTransform3D(tuple(g["N"]), g["matrices"], tuple(g["D"]))
+    assert O.rel_l2(_gpu(torch, dev, A, g["x"]), g["Ax"]) <= TOL
+    assert O.rel_l2(_gpu(torch, dev, A, g["y"], adj=True), g["ATy"]) <= TOL
+
+
+def test_known_answers_exact(torch_dev):
+    """scico/test/linop/xray/test_xray_3d.py:29-60 through the CUDA path (rtol 1e-7 as there)."""
+    torch, dev = torch_dev
+    x = np.zeros((4, 4, 1), np.float32)
+    x[1:3, 1:3, 0] = 1.0
+    H = sb.XRayTransform3D(x.shape, sb.matrices_from_euler_angles(x.shape, (4, 4), "X", [[0.0]]), (4, 4))
+    np.testing.assert_allclose(_gpu(torch, dev, H, x), [[[0, 0, 0, 0], [0, 1, 1, 0], [0, 1, 1, 0], [0, 0, 0, 0]]])
+    H = sb.XRayTransform3D(x.shape, sb.matrices_from_euler_angles(x.shape, (4, 4), "X", [[0.0]], voxel_spacing=[2.0, 1.0, 1.0]), (4, 4))
+    np.testing.assert_allclose(_gpu(torch, dev, H, x), [[[0, 0.5, 0.5, 0]] * 4])
+
+
+def test_reference_adjoint_tests(torch_dev):
+    """valid_adjoint as the reference's tests call it (test_xray_2d.py:52-85, test_xray_3d.py:9-26),
+    NumPy arrays in -> host-buffer C-ABI entry points."""
+    A = sb.XRayTransform2D((12, 13), np.linspace(0, np.pi, 10, endpoint=False))
+    assert sb.valid_adjoint(A, A.T, eps=1e-4)
+    N = 16
+    det = int(N * 1.05 / np.sqrt(2.0))
+    A = sb.XRayTransform2D((N, N), np.linspace(0, np.pi, 3, endpoint=False), det_count=det, dx=1.0 / np.sqrt(2))
+    assert sb.valid_adjoint(A, A.T, eps=1e-5)
+    H = sb.XRayTransform3D((N,) * 3, _x_mats((N,) * 3, (det, det), 3), (det, det))
+    assert sb.valid_adjoint(H, H.T, eps=1e-5)
+
+
+def test_host_and_device_entry_points_agree(torch_dev):
+    torch, dev = torch_dev
+    rng = np.random.default_rng(9)
+    H = sb.XRayTransform3D((6, 40, 50), _x_mats((6, 40, 50), (6, 70), 7), (6, 70))
+    x = rng.standard_normal(H.input_shape).astype(np.float32)
+    y = rng.standard_normal(H.output_shape).astype(np.float32)
+    out = H(x)
+    assert isinstance(out, np.ndarray) and out.dtype == np.float32
+    assert O.rel_l2(out, _gpu(torch, dev, H, x)) <= 1e-6
+    np.testing.assert_array_equal(H.adj(y), _gpu(torch, dev, H, y, adj=True))  # gather: deterministic
+    # float64 input is accepted by __call__ (no dtype check) and rejected by adj
+    assert O.rel_l2(H(x.astype(np.float64)), out) <= 1e-6
+    with pytest.raises(ValueError):
+        H.adj(y.astype(np.float64))
+
+
+def test_forward_overwrites_output_and_is_linear(torch_dev):
+    torch, dev = torch_dev
+    rng = np.random.default_rng(10)
+    A = sb.XRayTransform2D((70, 90), np.linspace(0, np.pi, 33, endpoint=False))
+    x1 = torch.as_tensor(rng.standard_normal((70, 90)).astype(np.float32), device=dev)
+    x2 = torch.as_tensor(rng.standard_normal((70, 90)).astype(np.float32), device=dev)
+    y12 = A(2.0 * x1 - 3.0 * x2).cpu().numpy()
+    lin = (2.0 * A(x1) - 3.0 * A(x2)).cpu().numpy()
+    assert O.rel_l2(y12, lin) <= TOL
+    assert float(A(torch.zeros_like(x1)).abs().max()) == 0.0
+
+
+def test_2d_batch(torch_dev):
+    torch, dev = torch_dev
+    rng = np.random.default_rng(11)
+    angles = np.linspace(0, np.pi, 21, endpoint=False)
+    A = sb.XRayTransform2D((50, 60), angles)
+    xb = rng.standard_normal((3, 50, 60)).astype(np.float32)
+    yb = rng.standard_normal((3,) + A.output_shape).astype(np.float32)
+    Ab = A.project(torch.as_tensor(xb, device=dev)).cpu().numpy()
+    ATb = A.back_project(torch.as_tensor(yb, device=dev)).cpu().numpy()
+    T = A.view_table
+    for b in range(3):
+        assert O.rel_l2(Ab[b], C.project_2d(xb[b], T, A.ny)) <= TOL
+        assert O.rel_l2(ATb[b], C.back_project_2d(yb[b], T, (50, 60))) <= TOL
+    with pytest.raises(ValueError):
+        A(torch.as_tensor(xb, device=dev))  # __call__ enforces the exact input_shape
+
+
+def test_mass_conservation(torch_dev):
+    """Per voxel the 2 (2D) / 4 (3D) weights sum to 1: each view's projection sums to sum(x)
+    when nothing falls off the detector (SURVEY.md section 8a invariants)."""
+    torch, dev = torch_dev
+    A = sb.XRayTransform2D((12, 13), np.linspace(0, np.pi, 10, endpoint=False))
+    y = _gpu(torch, dev, A, np.ones((12, 13), np.float32))
+    np.testing.assert_allclose(y.sum(axis=1), 156.0, rtol=1e-5)
+    N, D = (10, 30, 30), (10, 45)
+    H = sb.XRayTransform3D(N, _x_mats(N, D, 9), D)
+    x = np.random.default_rng(12).random(N).astype(np.float32)
+    p = _gpu(torch, dev, H, x)
+    np.testing.assert_allclose(p.sum(axis=(1, 2)), x.sum(dtype=np.float64), rtol=1e-5)
+
+
+def test_fbp_psnr(torch_dev):
+    """scico/test/linop/xray/test_xray_2d.py:88-102 on the CUDA path (device tensors, torch.fft)."""
+    torch, dev = torch_dev
+    N = 256
+    x_gt = np.zeros((N, N), dtype=np.float32)
+    x_gt[N // 4 : -N // 4, N // 4 : -N // 4] = 1.0
+    for dx in (0.5, 1.0 / np.sqrt(2)):
+        for f in (1.02 / np.sqrt(2.0), 1.0):
+            A = sb.XRayTransform2D((N, N), np.linspace(0, np.pi, 360, endpoint=False), det_count=int(f * N), dx=dx)
+            y = A(torch.as_tensor(x_gt, device=dev))
+            x_fbp = A.fbp(y).cpu().numpy()
+            mse = np.mean((x_gt.astype(np.float64) - x_fbp) ** 2)
+            assert 10 * np.log10(1.0 / mse) > 28
+    A = sb.XRayTransform2D((64, 64), np.linspace(0, np.pi, 90, endpoint=False), det_count=64)
+    assert A.fbp(A(np.ones((64, 64), np.float32))).shape == (64, 64)  # NumPy path (test_fbp_jit shape)
+
+
+def test_slab_decomposition_matches_full_operator(torch_dev):
+    """z-slab sharding hook (_xray3d.py:212 slice_offset): slabs of the volume map to row blocks of
+    the sinogram; the adjoint is bit-identical, the forward agrees to accumulation order."""
+    torch, dev = torch_dev
+    N, D, V = (24, 40, 36), (24, 52), 9
+    M = _x_mats(N, D, V)
+    H = sb.XRayTransform3D(N, M, D)
+    rng = np.random.default_rng(13)
+    x = rng.standard_normal(N).astype(np.float32)
+    y = rng.standard_normal(H.output_shape).astype(np.float32)
+    full_f, full_a = _gpu(torch, dev, H, x), _gpu(torch, dev, H, y, adj=True)
+    for force in (0, _lib.FLAG_FORCE_GENERAL):
+        parts_f, parts_a = [], []
+        for z0, z1 in ((0, 8), (8, 16), (16, 24)):
+            Hs = sb.XRayTransform3D((z1 - z0,) + N[1:], M, (z1 - z0, D[1]), slice_offset=z0, det_row_offset=z0,
+                                    det_rows_total=D[0], _flags=force)
+            parts_f.append(_gpu(torch, dev, Hs, x[z0:z1]))
+            parts_a.append(_gpu(torch, dev, Hs, np.ascontiguousarray(y[:, z0:z1]), adj=True))
+        assert O.rel_l2(np.concatenate(parts_f, axis=1), full_f) <= 1e-6
+        slab_a = np.concatenate(parts_a, axis=0)
+        if force == 0:
+            np.testing.assert_array_equal(slab_a, full_a)
+        else:
+            assert O.rel_l2(slab_a, full_a) <= 1e-6
+
+
+def test_view_block_decomposition(torch_dev):
+    """View-block sharding: forward rows are independent per view; adjoint partials sum."""
+    torch, dev = torch_dev
+    angles = np.linspace(0, np.pi, 40, endpoint=False)
+    A = sb.XRayTransform2D((96, 80), angles)
+    rng = np.random.default_rng(14)
+    x = rng.standard_normal((96, 80)).astype(np.float32)
+    y = rng.standard_normal(A.output_shape).astype(np.float32)
+    full_f, full_a = _gpu(torch, dev, A, x), _gpu(torch, dev, A, y, adj=True)
+    acc = np.zeros((96, 80), np.float64)
+    for v0, v1 in ((0, 13), (13, 26), (26, 40)):
+        Ab = sb.XRayTransform2D((96, 80), angles[v0:v1], det_count=A.ny)
+        assert O.rel_l2(_gpu(torch, dev, Ab, x), full_f[v0:v1]) <= 1e-6
+        acc += _gpu(torch, dev, Ab, np.ascontiguousarray(y[v0:v1]), adj=True)
+    assert O.rel_l2(acc, full_a) <= 1e-6

@@ -1,0 +1,180 @@
+"""Host-side logic: geometry tables, operator protocol, error behaviour, C-ABI surface (no GPU)."""
+import ctypes
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+import scico_b200 as sb
+from scico_b200 import _lib, geometry
+from oracle import xray_np as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- geometry -----------------------------------------------------------------------------
+@pytest.mark.parametrize("nx,V,dx", [((12, 13), 10, None), ((64, 64), 90, 0.5), ((300, 200), 50, (0.6, 0.7))])
+def test_view_table_matches_oracle_bitwise(nx, V, dx):
+    angles = np.linspace(0, np.pi, V, endpoint=False)
+    A = sb.XRayTransform2D(nx, angles, dx=dx)
+    T = O.view_table_2d(angles, A.x0, A.dx, A.y0)
+    np.testing.assert_array_equal(A.view_table, T)
+    assert A.view_table.dtype == np.float32 and A.view_table.flags.c_contiguous
+
+
+def test_euler_matches_scipy_and_oracle():
+    from scipy.spatial.transform import Rotation
+
+    rng = np.random.default_rng(2)
+    for seq in ["X", "Y", "Z", "XY", "xy", "XYZ", "zyx"]:
+        ang = rng.uniform(-3, 3, (5, len(seq)))
+        np.testing.assert_allclose(geometry.euler_matrices(seq, ang), Rotation.from_euler(seq, ang).as_matrix(), atol=1e-14)
+        np.testing.assert_allclose(
+            sb.matrices_from_euler_angles((5, 6, 7), (8, 9), seq, ang, voxel_spacing=[1, 2, 3], det_spacing=[0.5, 2]),
+            O.matrices_from_euler_angles((5, 6, 7), (8, 9), seq, ang, voxel_spacing=[1, 2, 3], det_spacing=[0.5, 2]),
+            atol=1e-13,
+        )
+    with pytest.raises(ValueError):
+        geometry.euler_matrices("Xy", np.zeros((2, 2)))
+
+
+def test_x_rotation_is_separable_with_exact_zeros():
+    M = sb.matrices_from_euler_angles((16,) * 3, (16, 16), "X", np.linspace(0, np.pi, 7, endpoint=False)[:, None])
+    assert geometry.is_axis0_separable(M)
+    M2 = sb.matrices_from_euler_angles((16,) * 3, (16, 16), "XY", np.array([[0.3, 1.2]]))
+    assert not geometry.is_axis0_separable(M2)
+
+
+def test_slab_row_range():
+    M = sb.matrices_from_euler_angles((64, 8, 8), (64, 12), "X", np.linspace(0, np.pi, 5, endpoint=False)[:, None])
+    assert geometry.slab_row_range(M, 16, 32, 64) == (16, 32)
+    M = sb.matrices_from_euler_angles((64, 8, 8), (80, 12), "X", np.zeros((1, 1)))  # t0 = 8
+    assert geometry.slab_row_range(M, 0, 16, 80) == (8, 24)
+
+
+# ---- operator protocol ----------------------------------------------------------------------
+@pytest.mark.filterwarnings("error")
+def test_init_warnings():
+    """scico/test/linop/xray/test_xray_2d.py:14-30."""
+    sb.XRayTransform2D((3, 3), np.array([np.pi / 4]))
+    sb.XRayTransform2D((3, 3), np.array([0]), dx=np.array([1, 1]))
+    with pytest.warns(UserWarning):
+        sb.XRayTransform2D((3, 3), np.array([0.1]), dx=np.array([1.1, 1.1]))
+    with pytest.warns(UserWarning):
+        sb.XRayTransform2D((3, 3), np.array([0]), dx=np.array([1.1, 1.1]))
+
+
+def test_2d_attributes_and_defaults():
+    angles = np.linspace(0, np.pi, 10, endpoint=False)
+    A = sb.XRayTransform2D((12, 13), angles)
+    assert A.input_shape == (12, 13) and A.output_shape == (10, 18)
+    assert A.det_count == A.ny == 18 and A.y0 == -9.0 and A.dy == 1.0
+    assert A.input_dtype == np.float32 and A.output_dtype == np.float32
+    assert A.input_size == 156 and A.output_size == 180 and A.matrix_shape == (180, 156)
+    assert A.shape == ((10, 18), (12, 13))
+    np.testing.assert_allclose(A.x0, -(np.array([12, 13]) * np.sqrt(2) / 2) / 2)
+    assert sb.XRayTransform2D((12, 13), angles, det_count=14).output_shape == (10, 14)
+    assert sb.XRayTransform2D((12, 13), angles, dx=0.5).dx == (0.5, 0.5)
+
+
+def test_3d_attributes():
+    M = sb.matrices_from_euler_angles((4, 5, 6), (7, 8), "X", np.zeros((3, 1)))
+    A = sb.XRayTransform3D((4, 5, 6), M, [7, 8])
+    assert A.output_shape == (3, 7, 8) and A.det_shape == (7, 8) and A.batch_size == 8
+    assert A.matrices.dtype == np.float32 and A.matrices.shape == (3, 2, 4)
+    assert hasattr(sb.XRayTransform3D, "matrices_from_euler_angles")
+    with pytest.raises(ValueError):
+        sb.XRayTransform3D((4, 5, 6), np.zeros((3, 2, 3)), (7, 8))
+
+
+def test_shape_and_dtype_errors():
+    """Operator.__call__: ValueError on shape mismatch, no dtype check (_operator.py:219-223);
+    LinearOperator.adj: ValueError on dtype or shape mismatch (_linop.py:319-325)."""
+    A = sb.XRayTransform2D((12, 13), np.linspace(0, np.pi, 10, endpoint=False))
+    with pytest.raises(ValueError):
+        A(np.zeros((13, 12), np.float32))
+    with pytest.raises(ValueError):
+        A.adj(np.zeros((10, 18), np.float64))
+    with pytest.raises(ValueError):
+        A.adj(np.zeros((10, 17), np.float32))
+    with pytest.raises(ValueError):
+        A.T(np.zeros((10, 17), np.float32))
+
+
+def test_transpose_wiring_with_fake_kernels():
+    """.T / .H / .adj / gram_op / @ / scaling resolve to the two kernels (_linop.py:296-440)."""
+    Mx = np.arange(12, dtype=np.float32).reshape(3, 4)
+    calls = []
+    A = sb.LinearOperator((4,), (3,), eval_fn=lambda x: (calls.append("f"), Mx @ x)[1],
+                          adj_fn=lambda y: (calls.append("a"), Mx.T @ y)[1])
+    x, y = np.ones(4, np.float32), np.ones(3, np.float32)
+    np.testing.assert_array_equal(A @ x, Mx @ x)
+    np.testing.assert_array_equal(A.T @ y, Mx.T @ y)
+    np.testing.assert_array_equal(A.H(y), Mx.T @ y)
+    np.testing.assert_array_equal(A.conj().T(y), Mx.T @ y)
+    np.testing.assert_array_equal(A.T.T(x), Mx @ x)
+    np.testing.assert_array_equal(A.gram_op(x), Mx.T @ (Mx @ x))
+    np.testing.assert_array_equal((2.0 * A)(x), 2 * (Mx @ x))
+    np.testing.assert_array_equal((2.0 * A).adj(y), 2 * (Mx.T @ y))
+    np.testing.assert_array_equal((A + A)(x), 2 * (Mx @ x))
+    np.testing.assert_array_equal((A.T @ A)(x), Mx.T @ (Mx @ x))
+    assert A.T.input_shape == (3,) and A.T.output_shape == (4,)
+    assert sb.valid_adjoint(A, A.T, eps=1e-6)
+    assert abs(sb.operator_norm(A, maxiter=200) - np.linalg.norm(Mx, 2)) < 1e-3
+    with pytest.raises(TypeError):
+        sb.LinearOperator((4,), (3,), eval_fn=lambda x: x, adj_fn=3)
+
+
+# ---- C ABI ----------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "scico_b200_xray.h")).read()
+    declared = set(re.findall(r"XCT_API\s+[\w\s\*]+?\b(xct\w+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.xct_version() == 100
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(_lib.Geom2D) == 32 and ctypes.sizeof(_lib.Geom3D) == 56
+    assert ctypes.sizeof(_lib.PlanInfo) == 48
+
+
+def test_invalid_arguments_are_reported_not_fatal():
+    L = _lib.lib()
+    pl = ctypes.c_void_p()
+    g = _lib.Geom2D()
+    assert L.xct2d_plan_create(ctypes.byref(pl), ctypes.byref(g)) == _lib.XCT_ERR_INVALID
+    assert b"xct2d_plan_create" in L.xct_last_error()
+    assert L.xct_forward(None, None, None, 1, None) == _lib.XCT_ERR_INVALID
+    assert L.xct_plan_get_info(None, None) == _lib.XCT_ERR_INVALID
+    L.xct_plan_destroy(None)  # no-op
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute call must fail loudly."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    A = sb.XRayTransform2D((12, 13), np.linspace(0, np.pi, 10, endpoint=False))
+    with pytest.raises(_lib.XctError) as ei:
+        A(np.ones((12, 13), np.float32))
+    assert ei.value.code == _lib.XCT_ERR_NO_DEVICE
+    M = sb.matrices_from_euler_angles((4, 4, 4), (4, 4), "X", np.zeros((1, 1)))
+    with pytest.raises(_lib.XctError):
+        sb.XRayTransform3D((4, 4, 4), M, (4, 4)).adj(np.ones((1, 4, 4), np.float32))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "scico_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle's", "").replace("as the oracle", "") or f.endswith((".cuh", ".cu")), f
+                if f.endswith(".py"):
+                    assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
