@@ -58,12 +58,18 @@ typedef enum xct_status {
 
 /* plan_create flags */
 #define XCT_FLAG_FORCE_GENERAL 0x1u /* skip the separable fast path (testing / comparison) */
+#define XCT_FLAG_NO_WALK 0x2u       /* keep the first-generation plane kernels (testing / comparison) */
 
 /* kernel families a plan can resolve to (xct_plan_info.path) */
 #define XCT_PATH_2D_PLANE 1   /* 2D, warp-autonomous plane kernels */
 #define XCT_PATH_2D_GENERAL 2 /* 2D, thread-per-pixel fallback */
 #define XCT_PATH_3D_SEP 3     /* 3D, separable geometry: rows <- axis 0 only, cols <- axes 1,2 only */
 #define XCT_PATH_3D_GENERAL 4 /* 3D, arbitrary 2x4 matrices */
+
+/* kernel generations (xct_plan_info.adj_kernel / fwd_kernel) */
+#define XCT_KERNEL_GENERAL 0 /* thread-per-voxel, any geometry */
+#define XCT_KERNEL_PLANE 1   /* warp-autonomous plane kernels (xct_plane.cuh) */
+#define XCT_KERNEL_WALK 2    /* register-walk kernels with cp.async staging (xct_plane2.cuh) */
 
 typedef struct xct_plan xct_plan; /* opaque */
 
@@ -97,6 +103,8 @@ typedef struct xct_plan_info {
   int32_t fwd_lane_stride; /* conflict-free lane stride of the forward kernel (0 = atomics) */
   int32_t row_aligned;    /* 3D sep: every voxel row lands in exactly one detector row */
   int32_t device;
+  int32_t adj_kernel;     /* XCT_KERNEL_*: what xct_adjoint launches (16-byte aligned input assumed) */
+  int32_t fwd_kernel;     /* XCT_KERNEL_*: what xct_forward launches */
   int64_t in_elems;       /* elements of one forward input (per batch item) */
   int64_t out_elems;      /* elements of one forward output (per batch item) */
   int64_t updates;        /* voxel-view updates per application = in_elems * num_views */

@@ -21,6 +21,8 @@ XCT_ERR_UNSUPPORTED = -3
 XCT_ERR_NO_DEVICE = -4
 
 FLAG_FORCE_GENERAL = 0x1
+FLAG_NO_WALK = 0x2
+KERNEL_NAMES = {0: "general", 1: "plane", 2: "walk"}
 
 PATH_NAMES = {1: "2d_plane", 2: "2d_general", 3: "3d_sep", 4: "3d_general"}
 
@@ -81,6 +83,8 @@ class PlanInfo(ctypes.Structure):
         ("fwd_lane_stride", c_int32),
         ("row_aligned", c_int32),
         ("device", c_int32),
+        ("adj_kernel", c_int32),
+        ("fwd_kernel", c_int32),
         ("in_elems", c_int64),
         ("out_elems", c_int64),
         ("updates", c_int64),

@@ -13,6 +13,7 @@
 #include "../../include/scico_b200_xray.h"
 #include "xct_general.cuh"
 #include "xct_plane.cuh"
+#include "xct_plane2.cuh"
 
 namespace {
 
@@ -41,6 +42,8 @@ constexpr int kAdj2S = 1, kAdj2TA = 32;
 constexpr int kFwdWin = 96;
 constexpr int kFwd3S = 2, kFwd3TN = 16;
 constexpr int kFwd2S = 1, kFwd2TN = 16;
+// walk kernels (xct_plane2.cuh)
+constexpr int kWAdjS = 8, kWAdjTA = 8, kWAdjWin = 64, kWAdjStages = 3;
 
 }  // namespace
 
@@ -60,6 +63,10 @@ struct xct_plan {
   xct::RowRec* d_rows = nullptr;
   float* d_mats = nullptr;
   int* d_list[2] = {nullptr, nullptr};  // [0]: views whose major axis is A, [1]: major axis B
+  // walk kernels: every (view, slice) lands in exactly one detector row with axis-0 weight 2
+  bool rows_unit = false;
+  bool adj_walk = false;
+  long long* d_rowoff = nullptr;  // [V][n0] element offset of the (local) sinogram row, or -1
   int n_list[2] = {0, 0};
   // host-buffer staging (xct_*_host)
   float* stage_in = nullptr;
@@ -100,7 +107,7 @@ int check_device(int device) {
 // Split the views into the two classes of the forward kernel and pick its lane stride.
 // Returns false when some view is outside the plane kernels' envelope.
 struct Envelope {
-  bool adj_ok = true, fwd_ok = true;
+  bool adj_ok = true, fwd_ok = true, adj_walk_ok = true;
   int gs = 2;
   std::vector<int> list[2];
 };
@@ -111,11 +118,13 @@ Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fw
   for (size_t v = 0; v < views.size(); ++v) {
     const float a = std::fabs(views[v].ca), b = std::fabs(views[v].cb);
     if (!std::isfinite(a) || !std::isfinite(b)) {
-      env.adj_ok = env.fwd_ok = false;
+      env.adj_ok = env.fwd_ok = env.adj_walk_ok = false;
       continue;
     }
     // adjoint window: tile adjTA x 32, needs floor(max u) - floor(min u) + 2 <= WIN
     if (a * (adjTA - 1) + b * 31.f + 3.f > (float)kAdjWin) env.adj_ok = false;
+    // walk adjoint: window start is rounded down to a multiple of 4 bins (+3)
+    if (a * (kWAdjTA - 1) + b * 31.f + 6.f > (float)kWAdjWin) env.adj_walk_ok = false;
     const bool major_b = b >= a;
     env.list[major_b ? 1 : 0].push_back((int)v);
     min_major = std::min(min_major, std::max(a, b));
@@ -186,6 +195,23 @@ int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* 
   const size_t smem = (size_t)kWarps * 2 * S * kAdjWin * sizeof(float);
   xct::plane_adjoint_kernel<G, IS3D, S, TA, kAdjWin, kWarps><<<blocks, kWarps * 32, smem, st>>>(p, in, out);
   return launch_ok("plane_adjoint_kernel");
+}
+
+// walk adjoint (3D separable geometry with unit rows; `in` must be 16-byte aligned)
+int launch_walk_adjoint(const xct_plan* pl, const float* in, float* out, cudaStream_t st) {
+  xct::Walk2Params wp{};
+  wp.p = plane_params(pl, 1);
+  wp.rowoff = pl->d_rowoff;
+  wp.out_scale = 2.0f;
+  xct::PlaneParams& p = wp.p;
+  p.tilesA = ceil_div(p.NA, kWAdjTA);
+  p.tilesB = ceil_div(p.NB, 32);
+  const long long tasks = (long long)ceil_div(p.NS, kWAdjS) * p.tilesA * p.tilesB;
+  const int blocks = ceil_div(tasks, kWarps);
+  const size_t smem = (size_t)kWarps * kWAdjStages * kWAdjS * kWAdjWin * sizeof(float);
+  xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps>
+      <<<blocks, kWarps * 32, smem, st>>>(wp, in, out);
+  return launch_ok("walk_adjoint_kernel");
 }
 
 template <class G, bool IS3D, int S, int TN, int GS, bool MAJOR_B>
@@ -382,7 +408,8 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       // result (including signed zeros) is what the general formula gives.  This translation unit
       // is compiled with -ffp-contract=off for host code: every product and sum rounds to fp32.
       std::vector<xct::RowRec> rows((size_t)V * g->n0);
-      bool aligned = true;
+      std::vector<long long> rowoff((size_t)V * g->n0);
+      bool aligned = true, unit = true;
       for (int v = 0; v < V; ++v) {
         const float* M = g->matrices + 8 * (size_t)v;
         for (int i = 0; i < g->n0; ++i) {
@@ -409,10 +436,21 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
           if (!in0) rr.w0 = 0.f;
           if (!in1) rr.w1 = 0.f;
           if (rr.w0 != 0.f && rr.w1 != 0.f) aligned = false;
+          int ri = -1;
+          if (rr.w0 == 2.f && rr.w1 == 0.f) ri = rr.r0;
+          else if (rr.w0 == 0.f && rr.w1 == 2.f) ri = rr.r0 + 1;
+          else if (!(rr.w0 == 0.f && rr.w1 == 0.f)) unit = false;
+          rowoff[(size_t)v * g->n0 + i] = ri < 0 ? -1LL : ((long long)v * g->d0 + ri) * (long long)g->d1;
           rows[(size_t)v * g->n0 + i] = rr;
         }
       }
       pl->row_aligned = aligned;
+      pl->rows_unit = unit;
+      if (unit) {
+        e = cudaMalloc(&pl->d_rowoff, sizeof(long long) * rowoff.size());
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_rowoff, rowoff.data(), sizeof(long long) * rowoff.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return cleanup(fail(XCT_ERR_CUDA, std::string("row index upload: ") + cudaGetErrorString(e)));
+      }
       e = cudaMalloc(&pl->d_views, sizeof(xct::ViewRec) * views.size());
       if (e == cudaSuccess) e = cudaMemcpy(pl->d_views, views.data(), sizeof(xct::ViewRec) * views.size(), cudaMemcpyHostToDevice);
       if (e == cudaSuccess) e = cudaMalloc(&pl->d_rows, sizeof(xct::RowRec) * rows.size());
@@ -421,6 +459,7 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       if ((rc = upload_lists(pl, env))) return cleanup(rc);
       pl->adj_plane = env.adj_ok;
       pl->fwd_plane = env.fwd_ok;
+      pl->adj_walk = env.adj_ok && env.adj_walk_ok && unit && (g->d1 % 4 == 0) && !(g->flags & XCT_FLAG_NO_WALK);
       pl->gs = env.fwd_ok ? env.gs : 0;
       if (pl->adj_plane && pl->fwd_plane) pl->path = XCT_PATH_3D_SEP;
     }
@@ -437,6 +476,7 @@ void xct_plan_destroy(xct_plan* pl) {
   cudaFree(pl->d_mats);
   cudaFree(pl->d_list[0]);
   cudaFree(pl->d_list[1]);
+  cudaFree(pl->d_rowoff);
   cudaFree(pl->stage_in);
   cudaFree(pl->stage_out);
   if (pl->hstream) cudaStreamDestroy(pl->hstream);
@@ -451,6 +491,8 @@ int xct_plan_get_info(const xct_plan* pl, xct_plan_info* info) {
   info->fwd_lane_stride = pl->gs;
   info->row_aligned = pl->row_aligned ? 1 : 0;
   info->device = pl->device;
+  info->adj_kernel = pl->adj_walk ? XCT_KERNEL_WALK : (pl->adj_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL);
+  info->fwd_kernel = pl->fwd_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL;
   info->in_elems = (int64_t)in_elems(pl);
   info->out_elems = (int64_t)out_elems(pl);
   info->updates = info->in_elems * pl->V;
@@ -480,6 +522,7 @@ int xct_adjoint(const xct_plan* pl, const float* in, float* out, int32_t batch, 
   DeviceGuard guard(pl->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (pl->ndim == 3) {
+    if (pl->adj_walk && (reinterpret_cast<uintptr_t>(in) & 15) == 0) return launch_walk_adjoint(pl, in, out, st);
     if (pl->adj_plane) return launch_plane_adjoint<xct::Geom3, true, kAdj3S, kAdj3TA>(pl, 1, in, out, st);
     xct::gen3d_adjoint_kernel<<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, out);
     return launch_ok("gen3d_adjoint_kernel");

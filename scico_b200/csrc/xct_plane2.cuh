@@ -1,0 +1,212 @@
+// Second-generation plane kernels ("walk" kernels): same problem decomposition as xct_plane.cuh
+// (a stack of independent slices whose in-plane points (a, b) project to ONE detector coordinate
+// u(a, b) per view with a 2-bin footprint), but each thread now WALKS along plane axis A and keeps
+// the two bins under its current position in registers:
+//
+//   adjoint : lane = column b, thread owns TA rows x S slices (register accumulators), loops over
+//             all views in order.  The S sinogram row segments a tile projects onto are copied
+//             global -> shared with 16-byte cp.async (LDGSTS) into a STAGES-deep ring, no
+//             registers and no branches in the fetch.  Walking down the rows the bin index moves
+//             by at most one per step (|ca| <= 1), so the pair (z[c], z[c+1]) is carried in
+//             registers and only ONE new tap is read from shared memory per voxel-view update
+//             (xct_plane.cuh reads two): the kernel moves from LSU-bound to issue-bound.
+//
+// Race freedom / exactness: identical coordinate arithmetic to xct_geom.cuh (the bin index is the
+// oracle's bit for bit); accumulation order per voxel is views ascending, tap c then tap c+1, as in
+// the reference's lax.scan (_xray3d.py:189,200-203).  A bin jump other than the expected +-1
+// (possible only when |ca| > 1) takes a cold path that reloads both taps, so the kernel is correct
+// for any geometry inside the window envelope checked at plan creation.
+#pragma once
+#include <type_traits>
+
+#include "xct_plane.cuh"
+
+namespace xct {
+
+struct Walk2Params {
+  PlaneParams p;
+  const long long* rowoff;  // [V][NS] element offset of the sinogram row slice s reads in view v, -1 = none
+  float out_scale;          // 3D: 2.0 (= 4 * 0.5, the axis-0 weight of a full row); 2D: 1
+};
+
+__device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const float* gmem_src, bool valid) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// Window start rounded down to a multiple of 4 bins so that every 16-byte chunk of a staged row is
+// either entirely inside [0, D1) or entirely outside (D1 % 4 == 0 is required by the launcher).
+template <class G>
+__device__ __forceinline__ int window_start4(const ViewRec& vr, int a_lo, int a_hi, int b_lo, int b_hi) {
+  return window_start<G>(vr, a_lo, a_hi, b_lo, b_hi) & ~3;
+}
+
+// Tile: TA rows (axis A) x 32 columns (axis B, lane = column) x S slices.
+// smem per warp: STAGES * S * WIN floats.
+template <class G, bool IS3D, int S, int TA, int WIN, int STAGES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __restrict__ out) {
+  static_assert(WIN % 64 == 0 || WIN == 32, "chunk indexing assumes a power-of-two window");
+  constexpr int CPR = WIN / 4;                    // 16-byte chunks per staged row
+  constexpr int CHUNKS = S * CPR;                 // chunks per view
+  constexpr int CPL = (CHUNKS + 31) / 32;         // chunks per lane
+  const PlaneParams& p = wp.p;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sgroups = (p.NS + S - 1) / S;
+  const long long ntasks = (long long)sgroups * p.tilesA * p.tilesB;
+  long long task = (long long)blockIdx.x * WARPS + warp;
+  if (task >= ntasks) return;  // warp-uniform; no block barrier below
+  const int tb = (int)(task % p.tilesB);
+  task /= p.tilesB;
+  const int ta = (int)(task % p.tilesA);
+  const int sg = (int)(task / p.tilesA);
+  const int a0 = ta * TA, b0 = tb * 32, s0 = sg * S;
+  const int b = b0 + lane;
+  float* ring = smem + (size_t)warp * (STAGES * S * WIN);
+
+  float acc[TA][S];
+#pragma unroll
+  for (int n = 0; n < TA; ++n)
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[n][s] = 0.f;
+
+  // ---- producer: one view's S row segments, global -> shared, asynchronous.
+  // Chunk -> (slice, 4-bin group) assignment is fixed per lane; only the row offset and the
+  // window start change from view to view.
+  int ck_soff[CPL];   // smem float offset of the chunk inside a stage
+  int ck_col[CPL];    // 4 * k
+  int ck_sl[CPL];     // slice, clamped into [0, NS)
+  bool ck_live[CPL];  // slice exists and the chunk id is in range
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    const int id = lane + 32 * q;
+    const int s = id / CPR, k = id % CPR;
+    ck_soff[q] = s * WIN + 4 * k;
+    ck_col[q] = 4 * k;
+    ck_live[q] = id < CHUNKS && s0 + s < p.NS;
+    ck_sl[q] = min(s0 + s, p.NS - 1);
+  }
+  auto fetch = [&](int v, int c0) {
+    float* zb = ring + (v % STAGES) * (S * WIN);
+    const long long* ro = wp.rowoff + (size_t)v * p.NS;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const long long off = __ldg(ro + ck_sl[q]);  // element offset of the row, -1 = no row
+      const int col = c0 + ck_col[q];
+      const bool ok = ck_live[q] && off >= 0 && (unsigned)col < (unsigned)p.D1;
+      const float* src = sino + (ok ? off + col : 0);
+      if (CHUNKS % 32 == 0 || lane + 32 * q < CHUNKS) cp_async16_zfill(zb + ck_soff[q], src, ok);
+    }
+  };
+  auto view_c0 = [&](int v) {
+    const ViewRec vr = load_view(p.views + v);
+    return window_start4<G>(vr, a0, a0 + TA - 1, b0, b0 + 31);
+  };
+
+  // ---- consumer: walk down the TA rows of this thread's column, carrying (z[c], z[c+1])
+  const float xa0 = G::coordA(a0);
+  auto walk = [&](auto up_c, const float* zb, const ViewRec& vr, int c0, float hB) {
+    constexpr bool UP = decltype(up_c)::value;
+    float lo[S], hi[S];
+    int tp = 0;
+#pragma unroll
+    for (int n = 0; n < TA; ++n) {
+      const float u = G::combine(vr, G::hoistA_x(vr, xa0 + (float)n), hB);
+      int c;
+      float w0, w1;
+      G::bins(vr, u, c, w0, w1);
+      const int t = (int)min((unsigned)(c - c0), (unsigned)(WIN - 2));
+      const float* z = zb + t;
+      if (n == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          lo[s] = z[s * WIN];
+          hi[s] = z[s * WIN + 1];
+        }
+      } else {
+        const bool moved = t != tp;
+        if (UP) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            lo[s] = moved ? hi[s] : lo[s];
+            hi[s] = z[s * WIN + 1];
+          }
+          if (moved && t != tp + 1) {  // cold: only when |ca| > 1
+#pragma unroll
+            for (int s = 0; s < S; ++s) lo[s] = z[s * WIN];
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            hi[s] = moved ? lo[s] : hi[s];
+            lo[s] = z[s * WIN];
+          }
+          if (moved && t != tp - 1) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) hi[s] = z[s * WIN + 1];
+          }
+        }
+      }
+      tp = t;
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[n][s] = fmaf(hi[s], w1, fmaf(lo[s], w0, acc[n][s]));
+    }
+  };
+
+  // c0 of the views in flight (register ring, rotated once per view)
+  int c0q[STAGES];
+#pragma unroll
+  for (int i = 0; i < STAGES; ++i) c0q[i] = 0;
+#pragma unroll
+  for (int i = 0; i < STAGES - 1; ++i) {
+    if (i < p.n_list) {
+      c0q[i] = view_c0(i);
+      fetch(i, c0q[i]);
+    }
+    cp_async_commit();
+  }
+
+  for (int v = 0; v < p.n_list; ++v) {
+    // all lanes have finished reading the stage that fetch(v + STAGES - 1) overwrites
+    __syncwarp();
+    if (v + STAGES - 1 < p.n_list) {
+      c0q[STAGES - 1] = view_c0(v + STAGES - 1);
+      fetch(v + STAGES - 1, c0q[STAGES - 1]);
+    }
+    cp_async_commit();
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();  // every lane's copies of stage v are complete and visible
+
+    const float* zb = ring + (v % STAGES) * (S * WIN);
+    const ViewRec vr = load_view(p.views + v);
+    const int c0 = c0q[0];
+#pragma unroll
+    for (int i = 0; i + 1 < STAGES; ++i) c0q[i] = c0q[i + 1];
+    const float hB = G::hoistB(vr, b);
+    if (vr.ca >= 0.f) walk(std::true_type{}, zb, vr, c0, hB);   // bins non-decreasing down the rows
+    else walk(std::false_type{}, zb, vr, c0, hB);
+  }
+  cp_async_wait<0>();
+
+  if (b < p.NB) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if (s0 + s >= p.NS) break;
+#pragma unroll
+      for (int n = 0; n < TA; ++n) {
+        if (a0 + n < p.NA)
+          out[((size_t)(s0 + s) * p.NA + (a0 + n)) * (size_t)p.NB + b] = acc[n][s] * wp.out_scale;
+      }
+    }
+  }
+}
+
+}  // namespace xct
