@@ -44,6 +44,7 @@ constexpr int kFwd3S = 2, kFwd3TN = 16;
 constexpr int kFwd2S = 1, kFwd2TN = 16;
 // walk kernels (xct_plane2.cuh)
 constexpr int kWAdjS = 8, kWAdjTA = 8, kWAdjWin = 64, kWAdjStages = 3;
+constexpr int kWFwdS = 4, kWFwdTN = 8;  // walk forward tile: 64 (major) x 8 (minor) x 4 slices
 
 }  // namespace
 
@@ -66,6 +67,9 @@ struct xct_plan {
   // walk kernels: every (view, slice) lands in exactly one detector row with axis-0 weight 2
   bool rows_unit = false;
   bool adj_walk = false;
+  bool fwd_walk = false;
+  int* d_list4[4] = {nullptr, nullptr, nullptr, nullptr};  // walk forward: [2*major_b + minor_up]
+  int n_list4[4] = {0, 0, 0, 0};
   long long* d_rowoff = nullptr;  // [V][n0] element offset of the (local) sinogram row, or -1
   int n_list[2] = {0, 0};
   // host-buffer staging (xct_*_host)
@@ -110,6 +114,7 @@ struct Envelope {
   bool adj_ok = true, fwd_ok = true, adj_walk_ok = true;
   int gs = 2;
   std::vector<int> list[2];
+  std::vector<int> list4[4];  // [2*major_b + minor_up]: minor-axis coefficient >= 0
 };
 
 Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fwdTN) {
@@ -127,6 +132,8 @@ Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fw
     if (a * (kWAdjTA - 1) + b * 31.f + 6.f > (float)kWAdjWin) env.adj_walk_ok = false;
     const bool major_b = b >= a;
     env.list[major_b ? 1 : 0].push_back((int)v);
+    const float minor = major_b ? views[v].ca : views[v].cb;
+    env.list4[(major_b ? 2 : 0) + (minor >= 0.f ? 1 : 0)].push_back((int)v);
     min_major = std::min(min_major, std::max(a, b));
   }
   // lanes GS voxels apart along the major axis must land >= 1 bin apart
@@ -149,6 +156,13 @@ int upload_lists(xct_plan* pl, const Envelope& env) {
     if (pl->n_list[c] == 0) continue;
     XCT_CUDA(cudaMalloc(&pl->d_list[c], sizeof(int) * env.list[c].size()));
     XCT_CUDA(cudaMemcpy(pl->d_list[c], env.list[c].data(), sizeof(int) * env.list[c].size(),
+                        cudaMemcpyHostToDevice));
+  }
+  for (int c = 0; c < 4; ++c) {
+    pl->n_list4[c] = (int)env.list4[c].size();
+    if (pl->n_list4[c] == 0) continue;
+    XCT_CUDA(cudaMalloc(&pl->d_list4[c], sizeof(int) * env.list4[c].size()));
+    XCT_CUDA(cudaMemcpy(pl->d_list4[c], env.list4[c].data(), sizeof(int) * env.list4[c].size(),
                         cudaMemcpyHostToDevice));
   }
   return XCT_OK;
@@ -232,7 +246,7 @@ int launch_plane_forward_class(const xct_plan* pl, int batch, const float* in, f
   if (tasks < target_warps) chunks = (int)std::min<long long>((target_warps + tasks - 1) / tasks, std::max(1, p.n_list / 4));
   p.views_per_chunk = ceil_div(p.n_list, chunks);
   chunks = ceil_div(p.n_list, p.views_per_chunk);
-  const size_t smem = (size_t)kWarps * S * kFwdWin * sizeof(float2);
+  const size_t smem = (size_t)kWarps * S * xct::FwdSlots<kFwdWin>::SIZE * sizeof(float2);
   dim3 grid(blocks, chunks);
   xct::plane_forward_kernel<G, IS3D, S, TN, GS, kFwdWin, MAJOR_B, kWarps><<<grid, kWarps * 32, smem, st>>>(p, in, out);
   return launch_ok("plane_forward_kernel");
@@ -247,6 +261,39 @@ int launch_plane_forward(const xct_plan* pl, int batch, const float* in, float* 
   }
   if ((rc = launch_plane_forward_class<G, IS3D, S, TN, 3, true>(pl, batch, in, out, st))) return rc;
   return launch_plane_forward_class<G, IS3D, S, TN, 3, false>(pl, batch, in, out, st);
+}
+
+// walk forward: one launch per (major axis, minor-axis sign) class
+template <class G, bool IS3D, int S, int TN, int GS, bool MAJOR_B, bool MINOR_UP>
+int launch_walk_forward_class(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+  const int cls = (MAJOR_B ? 2 : 0) + (MINOR_UP ? 1 : 0);
+  if (pl->n_list4[cls] == 0) return XCT_OK;
+  xct::PlaneParams p = plane_params(pl, batch);
+  p.view_list = pl->d_list4[cls];
+  p.n_list = pl->n_list4[cls];
+  constexpr int TM = 32 * GS;
+  p.tilesA = ceil_div(p.NA, MAJOR_B ? TN : TM);
+  p.tilesB = ceil_div(p.NB, MAJOR_B ? TM : TN);
+  const long long tasks = (long long)ceil_div(p.NS, S) * p.tilesA * p.tilesB;
+  const int blocks = ceil_div(tasks, kWarps);
+  const long long target_warps = 148LL * 32;
+  int chunks = 1;
+  if (tasks < target_warps) chunks = (int)std::min<long long>((target_warps + tasks - 1) / tasks, std::max(1, p.n_list / 4));
+  p.views_per_chunk = ceil_div(p.n_list, chunks);
+  chunks = ceil_div(p.n_list, p.views_per_chunk);
+  const size_t smem = (size_t)kWarps * S * kFwdWin * sizeof(float);
+  dim3 grid(blocks, chunks);
+  xct::walk_forward_kernel<G, IS3D, S, TN, GS, kFwdWin, MAJOR_B, MINOR_UP, kWarps><<<grid, kWarps * 32, smem, st>>>(p, in, out);
+  return launch_ok("walk_forward_kernel");
+}
+
+template <class G, bool IS3D, int S, int TN>
+int launch_walk_forward(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+  int rc;
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, true>(pl, batch, in, out, st))) return rc;
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, false>(pl, batch, in, out, st))) return rc;
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, false, true>(pl, batch, in, out, st))) return rc;
+  return launch_walk_forward_class<G, IS3D, S, TN, 2, false, false>(pl, batch, in, out, st);
 }
 
 xct::Gen3Params gen3_params(const xct_plan* pl) {
@@ -459,6 +506,7 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       if ((rc = upload_lists(pl, env))) return cleanup(rc);
       pl->adj_plane = env.adj_ok;
       pl->fwd_plane = env.fwd_ok;
+      pl->fwd_walk = env.fwd_ok && env.gs == 2 && !(g->flags & XCT_FLAG_NO_WALK);
       pl->adj_walk = env.adj_ok && env.adj_walk_ok && unit && (g->d1 % 4 == 0) && !(g->flags & XCT_FLAG_NO_WALK);
       pl->gs = env.fwd_ok ? env.gs : 0;
       if (pl->adj_plane && pl->fwd_plane) pl->path = XCT_PATH_3D_SEP;
@@ -477,6 +525,7 @@ void xct_plan_destroy(xct_plan* pl) {
   cudaFree(pl->d_list[0]);
   cudaFree(pl->d_list[1]);
   cudaFree(pl->d_rowoff);
+  for (int c = 0; c < 4; ++c) cudaFree(pl->d_list4[c]);
   cudaFree(pl->stage_in);
   cudaFree(pl->stage_out);
   if (pl->hstream) cudaStreamDestroy(pl->hstream);
@@ -492,7 +541,7 @@ int xct_plan_get_info(const xct_plan* pl, xct_plan_info* info) {
   info->row_aligned = pl->row_aligned ? 1 : 0;
   info->device = pl->device;
   info->adj_kernel = pl->adj_walk ? XCT_KERNEL_WALK : (pl->adj_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL);
-  info->fwd_kernel = pl->fwd_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL;
+  info->fwd_kernel = pl->fwd_walk ? XCT_KERNEL_WALK : (pl->fwd_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL);
   info->in_elems = (int64_t)in_elems(pl);
   info->out_elems = (int64_t)out_elems(pl);
   info->updates = info->in_elems * pl->V;
@@ -507,6 +556,7 @@ int xct_forward(const xct_plan* pl, const float* in, float* out, int32_t batch, 
   // every forward kernel accumulates with RED: the (possibly uninitialised) output is zeroed first
   XCT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * out_elems(pl) * batch, st));
   if (pl->ndim == 3) {
+    if (pl->fwd_walk) return launch_walk_forward<xct::Geom3, true, kWFwdS, kWFwdTN>(pl, 1, in, out, st);
     if (pl->fwd_plane) return launch_plane_forward<xct::Geom3, true, kFwd3S, kFwd3TN>(pl, 1, in, out, st);
     xct::gen3d_forward_kernel<<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, out);
     return launch_ok("gen3d_forward_kernel");

@@ -32,6 +32,8 @@ struct Geom3 {
   // voxel-centre coordinate of row a, and hoistA from it (a + 0.5 + n is exact: walk kernels)
   static __device__ __forceinline__ float coordA(int a) { return (float)a + 0.5f; }
   static __device__ __forceinline__ float hoistA_x(const ViewRec& v, float xa) { return __fmul_rn(v.ca, xa); }
+  static __device__ __forceinline__ float coordB(int b) { return (float)b + 0.5f; }
+  static __device__ __forceinline__ float hoistB_x(const ViewRec& v, float xb) { return __fmul_rn(v.cb, xb); }
   static __device__ __forceinline__ float combine(const ViewRec& v, float hA, float hB) {
     return __fadd_rn(__fadd_rn(__fadd_rn(hA, hB), v.off), -0.25f);
   }
@@ -57,6 +59,8 @@ struct Geom2 {
   static __device__ __forceinline__ float hoistA_x(const ViewRec& v, float xa) {
     return __fadd_rn(v.off, __fmul_rn(v.ca, xa));
   }
+  static __device__ __forceinline__ float coordB(int b) { return (float)b; }
+  static __device__ __forceinline__ float hoistB_x(const ViewRec& v, float xb) { return __fmul_rn(v.cb, xb); }
   static __device__ __forceinline__ float combine(const ViewRec&, float hA, float hB) {
     return __fadd_rn(hA, hB);
   }

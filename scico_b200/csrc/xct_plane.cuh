@@ -165,6 +165,19 @@ plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __res
 }
 
 // ------------------------------------------------------------------------------------ forward
+// Window slot of bin t.  Lanes of one RMW instruction sit >= 1.41 bins apart (GS voxels along the
+// major axis), so a half-warp's 16 bins span up to 32 bins and a linear layout wraps the 16 float2
+// bank slots twice (2-way conflicts, half of all wavefronts in the first ncu capture).  Splitting
+// the window by bin parity halves the span inside each parity class; the odd half is offset by
+// 8 slots (mod 16) so that the two classes of one half-warp rarely meet.
+template <int WIN>
+struct FwdSlots {
+  static constexpr int HALF = WIN / 2;
+  static constexpr int ODD_BASE = ((HALF + 15) / 16) * 16 + 8;
+  static constexpr int SIZE = ODD_BASE + HALF;  // float2 slots per slice
+  static __device__ __forceinline__ int of(int t) { return (t >> 1) + ((t & 1) ? ODD_BASE : 0); }
+};
+
 // Tile: 32*GS points along the major axis (lane l owns points GS*l .. GS*l+GS-1) x TN points along
 // the minor axis x S slices.  MAJOR_B: the major axis is plane axis B (the contiguous one).
 template <class G, bool IS3D, int S, int TN, int GS, int WIN, bool MAJOR_B, int WARPS>
@@ -184,7 +197,9 @@ plane_forward_kernel(PlaneParams p, const float* __restrict__ in, float* __restr
   const int ta = (int)(task % p.tilesA);
   const int sg = (int)(task / p.tilesA);
   const int a0 = ta * (MAJOR_B ? TN : TM), b0 = tb * (MAJOR_B ? TM : TN), s0 = sg * S;
-  float2* acc = reinterpret_cast<float2*>(smem) + warp * (S * WIN);
+  using Slots = FwdSlots<WIN>;
+  constexpr int WS = Slots::SIZE;
+  float2* acc = reinterpret_cast<float2*>(smem) + warp * (S * WS);
 
   // this thread's voxels, kept for every view of the launch
   float x[TN][GS][S];
@@ -211,8 +226,7 @@ plane_forward_kernel(PlaneParams p, const float* __restrict__ in, float* __restr
 
 #pragma unroll
     for (int s = 0; s < S; ++s)
-#pragma unroll
-      for (int q = 0; q < Q; ++q) acc[s * WIN + lane + 32 * q] = make_float2(0.f, 0.f);
+      for (int i = lane; i < WS; i += 32) acc[s * WS + i] = make_float2(0.f, 0.f);
     __syncwarp();
 
     float hMaj[GS];
@@ -231,15 +245,15 @@ plane_forward_kernel(PlaneParams p, const float* __restrict__ in, float* __restr
         G::bins(vr, u, c, w0, w1);
         int t = c - c0;
         t = min(max(t, 0), WIN - 2);
-        float2* pa = acc + t;
+        float2* pa = acc + Slots::of(t);
         // lanes are GS voxels apart along the major axis => their bins differ by >= 1:
         // one lane per address, plain RMW is race free within this instruction
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          float2 ab = pa[s * WIN];
+          float2 ab = pa[s * WS];
           ab.x = fmaf(x[n][d][s], w0, ab.x);
           ab.y = fmaf(x[n][d][s], w1, ab.y);
-          pa[s * WIN] = ab;
+          pa[s * WS] = ab;
         }
         __syncwarp();  // order this step's stores before the next step's loads of other lanes
       }
@@ -262,8 +276,8 @@ plane_forward_kernel(PlaneParams p, const float* __restrict__ in, float* __restr
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
         const int t = lane + 32 * q;
-        float val = acc[s * WIN + t].x;
-        if (t > 0) val += acc[s * WIN + t - 1].y;
+        float val = acc[s * WS + Slots::of(t)].x;
+        if (t > 0) val += acc[s * WS + Slots::of(t - 1)].y;
         const int col = c0 + t;
         if (val != 0.f && col >= 0 && col < p.D1) {
           if (rr.w0 != 0.f) atomicAdd(y0 + col, rr.w0 * val);

@@ -209,4 +209,163 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------ forward
+// Tile: 32*GS points along the view's MAJOR axis (lane l owns points GS*l .. GS*l+GS-1) x TN points
+// along the MINOR axis x S slices, voxels register-stationary for every view of the launch (as in
+// plane_forward_kernel).  Each lane WALKS its GS columns along the minor axis, where the bin index
+// moves by at most one per step (|c_minor| <= 0.71 |c_major|...1), and carries the partial sums of
+// the two bins under its current position in registers: shared memory sees one read-modify-write
+// per bin CHANGE instead of one per voxel, which removes most of the LSU traffic (and the bank
+// conflicts) that bound plane_forward_kernel.  Lanes sit GS voxels apart along the major axis, so
+// the bins two lanes flush in one instruction differ by >= 1: plain RMW, no shared atomics.
+// MINOR_UP: bins are non-decreasing along the walk (the launch holds views of one sign class).
+// Window layout: win[t][S] (slice fastest), flushed to the sinogram with RED once per view.
+template <int S>
+struct SliceVec;
+template <>
+struct SliceVec<2> { using type = float2; };
+template <>
+struct SliceVec<4> { using type = float4; };
+
+template <class G, bool IS3D, int S, int TN, int GS, int WIN, bool MAJOR_B, bool MINOR_UP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+walk_forward_kernel(PlaneParams p, const float* __restrict__ in, float* __restrict__ sino) {
+  static_assert(WIN % 32 == 0, "window is flushed 32 bins at a time");
+  static_assert(S == 2 || S == 4, "window slots are float2 / float4");
+  using Vec = typename SliceVec<S>::type;
+  constexpr int Q = WIN / 32;
+  constexpr int TM = 32 * GS;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sgroups = (p.NS + S - 1) / S;
+  const long long ntasks = (long long)sgroups * p.tilesA * p.tilesB;
+  long long task = (long long)blockIdx.x * WARPS + warp;
+  if (task >= ntasks) return;
+  const int tb = (int)(task % p.tilesB);
+  task /= p.tilesB;
+  const int ta = (int)(task % p.tilesA);
+  const int sg = (int)(task / p.tilesA);
+  const int a0 = ta * (MAJOR_B ? TN : TM), b0 = tb * (MAJOR_B ? TM : TN), s0 = sg * S;
+  float* win = smem + (size_t)warp * (WIN * S);
+
+  // this thread's voxels, kept for every view of the launch
+  float x[GS][TN][S];
+#pragma unroll
+  for (int d = 0; d < GS; ++d)
+#pragma unroll
+    for (int n = 0; n < TN; ++n) {
+      const int a = MAJOR_B ? a0 + n : a0 + GS * lane + d;
+      const int b = MAJOR_B ? b0 + GS * lane + d : b0 + n;
+      const bool ok = a < p.NA && b < p.NB;
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+        x[d][n][s] = (ok && s0 + s < p.NS) ? __ldg(in + ((size_t)(s0 + s) * p.NA + a) * (size_t)p.NB + b) : 0.f;
+    }
+
+  // minor-axis coordinate of walk step 0 (a for MAJOR_B, b otherwise); + n is exact
+  const float xmin0 = MAJOR_B ? G::coordA(a0) : G::coordB(b0);
+
+  auto rmw = [&](int t, const float (&v)[S]) {  // win[t][:] += v   (one lane per address)
+    Vec* q = reinterpret_cast<Vec*>(win) + t;
+    Vec cur = *q;
+    float* c = reinterpret_cast<float*>(&cur);
+#pragma unroll
+    for (int s = 0; s < S; ++s) c[s] += v[s];
+    *q = cur;
+  };
+
+  const int v_begin = blockIdx.y * p.views_per_chunk;
+  const int v_end = min(p.n_list, v_begin + p.views_per_chunk);
+  for (int vi = v_begin; vi < v_end; ++vi) {
+    const int v = p.view_list ? __ldg(p.view_list + vi) : vi;
+    const ViewRec vr = load_view(p.views + v);
+    const int c0 = window_start<G>(vr, a0, a0 + (MAJOR_B ? TN : TM) - 1, b0, b0 + (MAJOR_B ? TM : TN) - 1);
+
+#pragma unroll
+    for (int q = 0; q < Q * S; ++q) win[lane + 32 * q] = 0.f;
+    __syncwarp();
+
+#pragma unroll
+    for (int d = 0; d < GS; ++d) {
+      const float hMaj = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + d) : G::hoistA(vr, a0 + GS * lane + d);
+      float lo[S], hi[S];
+      int tp = 0;
+#pragma unroll
+      for (int n = 0; n < TN; ++n) {
+        const float xm = xmin0 + (float)n;
+        const float u = MAJOR_B ? G::combine(vr, G::hoistA_x(vr, xm), hMaj) : G::combine(vr, hMaj, G::hoistB_x(vr, xm));
+        int c;
+        float w0, w1;
+        G::bins(vr, u, c, w0, w1);
+        const int t = (int)min((unsigned)(c - c0), (unsigned)(WIN - 2));
+        if (n == 0) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            lo[s] = x[d][n][s] * w0;
+            hi[s] = x[d][n][s] * w1;
+          }
+        } else {
+          if (t != tp) {
+            const bool step1 = MINOR_UP ? (t == tp + 1) : (t == tp - 1);
+            // the bin that falls out of the carried pair is complete for this walk: flush it
+            if (MINOR_UP) rmw(tp, lo);
+            else rmw(tp + 1, hi);
+            if (step1) {
+#pragma unroll
+              for (int s = 0; s < S; ++s) {
+                if (MINOR_UP) { lo[s] = hi[s]; hi[s] = 0.f; }
+                else { hi[s] = lo[s]; lo[s] = 0.f; }
+              }
+            } else {  // cold: the bin moved by more than one (|c_minor| > 1): flush the other one too
+              if (MINOR_UP) rmw(tp + 1, hi);
+              else rmw(tp, lo);
+#pragma unroll
+              for (int s = 0; s < S; ++s) lo[s] = hi[s] = 0.f;
+            }
+          }
+          // order this step's stores before the next step's loads of other lanes
+          __syncwarp();
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            lo[s] = fmaf(x[d][n][s], w0, lo[s]);
+            hi[s] = fmaf(x[d][n][s], w1, hi[s]);
+          }
+        }
+        tp = t;
+      }
+      rmw(tp, lo);
+      __syncwarp();
+      rmw(tp + 1, hi);
+      __syncwarp();
+    }
+
+    // flush the window: bin (c0 + t) of slice s; rows / weights from the slice's row record
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int sl = s0 + s;
+      if (sl >= p.NS) break;
+      RowRec rr;
+      float* y0;
+      if (IS3D) {
+        rr = load_row(p.rows + (size_t)v * p.NS + sl);
+        y0 = sino + ((size_t)v * p.D0 + rr.r0) * (size_t)p.D1;
+      } else {
+        rr.r0 = 0; rr.w0 = 1.f; rr.w1 = 0.f;
+        y0 = sino + ((size_t)sl * p.V + v) * (size_t)p.D1;
+      }
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int t = lane + 32 * q;
+        const float val = win[t * S + s];
+        const int col = c0 + t;
+        if (val != 0.f && col >= 0 && col < p.D1) {
+          if (rr.w0 != 0.f) atomicAdd(y0 + col, rr.w0 * val);
+          if (IS3D && rr.w1 != 0.f) atomicAdd(y0 + p.D1 + col, rr.w1 * val);
+        }
+      }
+    }
+    __syncwarp();  // all window reads done before the next view zeroes it
+  }
+}
+
 }  // namespace xct

@@ -1,0 +1,290 @@
+"""Multi-GPU partitioning of the projector pair: one process per GPU over ``torch.distributed``.
+
+Two partitionings:
+
+* :class:`SlabShardedXRayTransform3D` -- z-slabs.  For separable geometry (detector rows depend on
+  voxel axis 0 only: any rotation about axis 0) rank ``r`` holds volume slices ``[z0, z1)`` and the
+  detector rows they project onto; the local plan gets ``slice_offset = z0``, the reference's own
+  hook (``scico/linop/xray/_xray3d.py:143,195,208-212``).  No data-path collective, except a halo
+  exchange of the detector rows two neighbouring slabs share when rows straddle a slab edge.
+* :class:`ViewShardedXRayTransform3D` / :class:`ViewShardedXRayTransform2D` -- contiguous view
+  blocks.  The forward needs the whole volume (``all_gather`` of the slab-sharded iterate); the
+  adjoint's partial volumes are combined into slabs with a sum-reduction per destination slab,
+  pipelined so that the back projection of slab ``j+1`` overlaps the reduction of slab ``j``.
+
+The local operator is built by ``op_factory`` (default: the native CUDA operators of
+:mod:`scico_b200.xray`).  Tests inject a CPU stand-in through it to exercise the partitioning and
+the collectives under ``gloo``; the product never does.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import geometry
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def block_bounds(n: int, parts: int, index: int) -> tuple[int, int]:
+    """Contiguous block ``index`` of ``n`` items split into ``parts`` nearly equal blocks."""
+    if not 0 <= index < parts:
+        raise ValueError(f"block index {index} outside [0, {parts})")
+    return (n * index) // parts, (n * (index + 1)) // parts
+
+
+def _world(group) -> tuple[int, int]:
+    if dist is None or not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _native_3d(input_shape, matrices, det_shape, **kw):
+    from .xray import XRayTransform3D
+
+    return XRayTransform3D(input_shape, matrices, det_shape, **kw)
+
+
+def _native_2d(input_shape, angles, **kw):
+    from .xray import XRayTransform2D
+
+    return XRayTransform2D(input_shape, angles, **kw)
+
+
+class SlabShardedXRayTransform3D:
+    """z-slab partition of ``XRayTransform3D`` for axis-0-separable geometry.
+
+    Rank ``r`` owns volume slices ``slab = [z0, z1)`` and works on detector rows
+    ``rows = [r0, r1)``.  ``project`` maps the local slab ``(z1-z0, N1, N2)`` to the local sinogram
+    block ``(V, r1-r0, D1)``; ``back_project`` is its exact adjoint.  When neighbouring row ranges
+    overlap (a voxel slice at a slab edge spreads over two detector rows) the shared rows are
+    summed across the two ranks after ``project`` so that both hold the complete row, and
+    ``owned_rows`` tells which of them this rank counts as its own (for inner products, norms and
+    gathering): every global row is owned by exactly one rank.
+    """
+
+    def __init__(self, input_shape, matrices, det_shape, group=None, op_factory: Optional[Callable] = None,
+                 rank: Optional[int] = None, world_size: Optional[int] = None):
+        self.input_shape = tuple(int(s) for s in input_shape)
+        self.det_shape = tuple(int(s) for s in det_shape)
+        self.matrices = np.asarray(matrices, dtype=np.float32)
+        if not geometry.is_axis0_separable(self.matrices):
+            raise ValueError("z-slab sharding needs axis-0-separable matrices (use ViewShardedXRayTransform3D)")
+        self.group = group
+        r, w = _world(group)
+        self.rank = r if rank is None else rank
+        self.world_size = w if world_size is None else world_size
+        n0 = self.input_shape[0]
+        self.slabs = [block_bounds(n0, self.world_size, i) for i in range(self.world_size)]
+        self.row_ranges = [geometry.slab_row_range(self.matrices, z0, z1, self.det_shape[0]) if z1 > z0 else (0, 0)
+                           for z0, z1 in self.slabs]
+        self.slab = self.slabs[self.rank]
+        self.rows = self.row_ranges[self.rank]
+        # ownership: a row shared with the previous rank belongs to the previous rank
+        own_lo = self.rows[0]
+        if self.rank > 0:
+            own_lo = max(own_lo, self.row_ranges[self.rank - 1][1])
+        self.owned_rows = (min(own_lo, self.rows[1]), self.rows[1])
+        z0, z1 = self.slab
+        self.local_input_shape = (z1 - z0,) + self.input_shape[1:]
+        self.local_output_shape = (len(self.matrices), self.rows[1] - self.rows[0], self.det_shape[1])
+        factory = op_factory or _native_3d
+        self.local = None
+        if z1 > z0 and self.rows[1] > self.rows[0]:
+            self.local = factory(self.local_input_shape, self.matrices, self.local_output_shape[1:],
+                                 slice_offset=z0, det_row_offset=self.rows[0], det_rows_total=self.det_shape[0])
+
+    # -- halo: rows shared with the neighbours --------------------------------------------------
+    def _overlap(self, other: int) -> tuple[int, int]:
+        a, b = self.rows, self.row_ranges[other]
+        return max(a[0], b[0]), min(a[1], b[1])
+
+    def halo_rows(self) -> list[tuple[int, int, int]]:
+        """[(neighbour rank, global row lo, global row hi)] for every non-empty overlap."""
+        out = []
+        for other in (self.rank - 1, self.rank + 1):
+            if 0 <= other < self.world_size:
+                lo, hi = self._overlap(other)
+                if hi > lo:
+                    out.append((other, lo, hi))
+        return out
+
+    def _exchange_halo_sum(self, y):
+        halos = self.halo_rows()
+        if not halos or self.world_size == 1:
+            return y
+        ops, bufs = [], []
+        for other, lo, hi in halos:
+            send = y[:, lo - self.rows[0]:hi - self.rows[0], :].contiguous()
+            recv = torch.empty_like(send)
+            peer = other if self.group is None else dist.get_global_rank(self.group, other)
+            ops += [dist.P2POp(dist.isend, send, peer, self.group), dist.P2POp(dist.irecv, recv, peer, self.group)]
+            bufs.append((lo, hi, recv))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for lo, hi, recv in bufs:
+            y[:, lo - self.rows[0]:hi - self.rows[0], :] += recv
+        return y
+
+    def project(self, x_local):
+        if tuple(x_local.shape) != self.local_input_shape:
+            raise ValueError(f"local slab of shape {tuple(x_local.shape)} does not match {self.local_input_shape}")
+        if self.local is None:
+            return x_local.new_zeros(self.local_output_shape)
+        return self._exchange_halo_sum(self.local.project(x_local))
+
+    def back_project(self, y_local):
+        if tuple(y_local.shape) != self.local_output_shape:
+            raise ValueError(f"local sinogram of shape {tuple(y_local.shape)} does not match {self.local_output_shape}")
+        if self.local is None:
+            return y_local.new_zeros(self.local_input_shape)
+        return self.local.back_project(y_local)
+
+    __call__ = project
+    adj = back_project
+
+
+class _ViewSharded:
+    """Shared machinery of the view-block partitions (volume / image rows sharded on axis 0)."""
+
+    def _setup(self, n_views, axis0, group, rank, world_size):
+        self.group = group
+        r, w = _world(group)
+        self.rank = r if rank is None else rank
+        self.world_size = w if world_size is None else world_size
+        self.view_blocks = [block_bounds(n_views, self.world_size, i) for i in range(self.world_size)]
+        self.views = self.view_blocks[self.rank]
+        self.slabs = [block_bounds(axis0, self.world_size, i) for i in range(self.world_size)]
+        self.slab = self.slabs[self.rank]
+
+    def _gather_volume(self, x_slab):
+        """all_gather of the axis-0 slabs into the full volume (uneven slabs are padded)."""
+        if self.world_size == 1:
+            return x_slab
+        pad = max(z1 - z0 for z0, z1 in self.slabs)
+        buf = x_slab.new_zeros((pad,) + tuple(x_slab.shape[1:]))
+        buf[: x_slab.shape[0]] = x_slab
+        out = x_slab.new_empty((self.world_size * pad,) + tuple(x_slab.shape[1:]))
+        dist.all_gather_into_tensor(out, buf, group=self.group)
+        if all(z1 - z0 == pad for z0, z1 in self.slabs):
+            return out
+        return torch.cat([out[i * pad: i * pad + (z1 - z0)] for i, (z0, z1) in enumerate(self.slabs)], dim=0)
+
+    def _reduce_slabs(self, partial_of_slab: Callable[[int], "torch.Tensor"]):
+        """Sum the partial back projections of every rank, slab by slab, into the slab's owner.
+
+        ``partial_of_slab(j)`` computes this rank's partial result for slab ``j``; the reduction of
+        slab ``j`` is issued asynchronously, so it overlaps the computation of slab ``j+1``."""
+        mine, works, keep = None, [], []
+        for j in range(self.world_size):
+            part = partial_of_slab(j)
+            if self.world_size == 1:
+                return part
+            dst = j if self.group is None else dist.get_global_rank(self.group, j)
+            works.append(dist.reduce(part, dst=dst, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            keep.append(part)
+            if j == self.rank:
+                mine = part
+        for w in works:
+            w.wait()
+        return mine
+
+
+class ViewShardedXRayTransform3D(_ViewSharded):
+    """View-block partition of ``XRayTransform3D`` (any matrices).
+
+    ``project(x_slab)``: all-gathers the slab-sharded volume and projects it onto this rank's views
+    ``(v1-v0, D0, D1)``.  ``back_project(y_views)``: back-projects the local views slab by slab
+    (one plan per destination slab, ``slice_offset`` = slab start) and sum-reduces each slab into
+    its owner; returns this rank's slab ``(z1-z0, N1, N2)``."""
+
+    def __init__(self, input_shape, matrices, det_shape, group=None, op_factory: Optional[Callable] = None,
+                 rank: Optional[int] = None, world_size: Optional[int] = None):
+        self.input_shape = tuple(int(s) for s in input_shape)
+        self.det_shape = tuple(int(s) for s in det_shape)
+        self.matrices = np.asarray(matrices, dtype=np.float32)
+        self._setup(len(self.matrices), self.input_shape[0], group, rank, world_size)
+        v0, v1 = self.views
+        self.local_output_shape = (v1 - v0,) + self.det_shape
+        z0, z1 = self.slab
+        self.local_input_shape = (z1 - z0,) + self.input_shape[1:]
+        factory = op_factory or _native_3d
+        M = self.matrices[v0:v1]
+        self.full = factory(self.input_shape, M, self.det_shape) if v1 > v0 else None
+        self.per_slab = [
+            factory((b - a,) + self.input_shape[1:], M, self.det_shape, slice_offset=a) if (v1 > v0 and b > a) else None
+            for a, b in self.slabs
+        ]
+
+    def project(self, x_slab):
+        if tuple(x_slab.shape) != self.local_input_shape:
+            raise ValueError(f"local slab of shape {tuple(x_slab.shape)} does not match {self.local_input_shape}")
+        x = self._gather_volume(x_slab)
+        if self.full is None:
+            return x_slab.new_zeros(self.local_output_shape)
+        return self.full.project(x)
+
+    def back_project(self, y_views):
+        if tuple(y_views.shape) != self.local_output_shape:
+            raise ValueError(f"local views of shape {tuple(y_views.shape)} do not match {self.local_output_shape}")
+
+        def part(j):
+            a, b = self.slabs[j]
+            if self.per_slab[j] is None:
+                return y_views.new_zeros((b - a,) + self.input_shape[1:])
+            return self.per_slab[j].back_project(y_views)
+
+        return self._reduce_slabs(part)
+
+    __call__ = project
+    adj = back_project
+
+
+class ViewShardedXRayTransform2D(_ViewSharded):
+    """View-block partition of ``XRayTransform2D`` (BASELINE.json configs[2]: 4096^2, 2048 views).
+
+    The image is small next to the sinogram, so it is kept replicated: ``project(x)`` maps the
+    full image to this rank's views ``(v1-v0, ny)``; ``back_project(y_views)`` returns either the
+    row block this rank owns (``scatter=True``, reduce per row block) or the full image on every
+    rank (``scatter=False``, all-reduce)."""
+
+    def __init__(self, input_shape, angles, group=None, op_factory: Optional[Callable] = None,
+                 rank: Optional[int] = None, world_size: Optional[int] = None, **kw):
+        self.input_shape = tuple(int(s) for s in input_shape)
+        self.angles = np.asarray(angles, dtype=np.float64)
+        self._setup(len(self.angles), self.input_shape[0], group, rank, world_size)
+        v0, v1 = self.views
+        if kw.get("det_count") is None:  # the default depends on the image only, not on the views
+            kw["det_count"] = int(np.ceil(np.linalg.norm(self.input_shape)))
+        self.ny = int(kw["det_count"])
+        self.local_output_shape = (v1 - v0, self.ny)
+        factory = op_factory or _native_2d
+        self.local = factory(self.input_shape, self.angles[v0:v1], **kw) if v1 > v0 else None
+
+    def project(self, x):
+        if tuple(x.shape) != self.input_shape:
+            raise ValueError(f"image of shape {tuple(x.shape)} does not match {self.input_shape}")
+        if self.local is None:
+            return x.new_zeros(self.local_output_shape)
+        return self.local.project(x)
+
+    def back_project(self, y_views, scatter: bool = True):
+        if tuple(y_views.shape) != self.local_output_shape:
+            raise ValueError(f"local views of shape {tuple(y_views.shape)} do not match {self.local_output_shape}")
+        full = self.local.back_project(y_views) if self.local is not None else y_views.new_zeros(self.input_shape)
+        if self.world_size == 1:
+            return full
+        if not scatter:
+            dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
+            return full
+        return self._reduce_slabs(lambda j: full[self.slabs[j][0]: self.slabs[j][1]].contiguous())
+
+    __call__ = project
+    adj = back_project

@@ -80,8 +80,12 @@ class _Plans:
         self.close()
 
 
-def _apply(plans: _Plans, x, out_shape, forward: bool, batch: int, default_device: Optional[int]):
-    """Run one operator application on ``x`` (see module docstring for the array rules)."""
+def _apply(plans: _Plans, x, out_shape, forward: bool, batch: int, default_device: Optional[int], out=None):
+    """Run one operator application on ``x`` (see module docstring for the array rules).
+
+    ``out`` (optional): preallocated float32 C-contiguous result of shape ``out_shape`` -- a CUDA
+    tensor for CUDA input, a NumPy array (ideally page-locked, e.g. the ``.numpy()`` view of a
+    ``torch.empty(..., pin_memory=True)``) for host input.  It is overwritten and returned."""
     L = _lib.lib()
     fn_dev = L.xct_forward if forward else L.xct_adjoint
     fn_host = L.xct_forward_host if forward else L.xct_adjoint_host
@@ -91,7 +95,11 @@ def _apply(plans: _Plans, x, out_shape, forward: bool, batch: int, default_devic
         if xin.dtype != torch.float32:
             xin = xin.to(torch.float32)
         xin = xin.contiguous()
-        out = torch.empty(out_shape, dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty(out_shape, dtype=torch.float32, device=x.device)
+        elif not (isinstance(out, torch.Tensor) and out.is_cuda and out.device == x.device and out.dtype == torch.float32
+                  and tuple(out.shape) == tuple(out_shape) and out.is_contiguous()):
+            raise ValueError("'out' must be a contiguous float32 CUDA tensor of the result shape on the input's device")
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(fn_dev(plans.get(dev), xin.data_ptr(), out.data_ptr(), batch, stream))
@@ -100,7 +108,11 @@ def _apply(plans: _Plans, x, out_shape, forward: bool, batch: int, default_devic
         return out
     was_torch = torch is not None and isinstance(x, torch.Tensor)
     xin = np.ascontiguousarray(x.numpy() if was_torch else np.asarray(x), dtype=np.float32)
-    out = np.empty(out_shape, dtype=np.float32)
+    if out is None:
+        out = np.empty(out_shape, dtype=np.float32)
+    elif not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == tuple(out_shape)
+              and out.flags.c_contiguous and out.flags.writeable):
+        raise ValueError("'out' must be a writeable C-contiguous float32 NumPy array of the result shape")
     dev = default_device if default_device is not None else 0
     _lib.check(fn_host(plans.get(dev), xin.ctypes.data, out.ctypes.data, batch))
     return torch.from_numpy(out) if was_torch else out
@@ -169,17 +181,17 @@ class XRayTransform2D(LinearOperator):
     def plan_info(self, device: int = 0) -> dict:
         return self._plans.info(device)
 
-    def project(self, im):
+    def project(self, im, out=None):
         """X-ray projection, ``H @ im``; a leading batch axis is accepted (the reference's
         ``jax.vmap(A)`` use, ``scico/flax/examples/data_generation.py:153-186``)."""
         batch, lead = self._batch(im, self.nx)
         return _apply(self._plans, im, lead + self.output_shape, True, batch,
-                      _device_index(self.output_device))
+                      _device_index(self.output_device), out)
 
-    def back_project(self, y):
+    def back_project(self, y, out=None):
         """X-ray back projection, ``H.T @ y`` (exact adjoint of :meth:`project`)."""
         batch, lead = self._batch(y, self.output_shape)
-        return _apply(self._plans, y, lead + self.nx, False, batch, _device_index(self.input_device))
+        return _apply(self._plans, y, lead + self.nx, False, batch, _device_index(self.input_device), out)
 
     @staticmethod
     def _batch(a, core):
@@ -269,17 +281,17 @@ class XRayTransform3D(LinearOperator):
     def plan_info(self, device: int = 0) -> dict:
         return self._plans.info(device)
 
-    def project(self, im):
-        """Compute X-ray projection."""
+    def project(self, im, out=None):
+        """Compute X-ray projection (``out``: optional preallocated result, see :func:`_apply`)."""
         if tuple(im.shape) != self.input_shape:
             raise ValueError(f"array of shape {tuple(im.shape)} does not match {self.input_shape}")
-        return _apply(self._plans, im, self.output_shape, True, 1, _device_index(self.output_device))
+        return _apply(self._plans, im, self.output_shape, True, 1, _device_index(self.output_device), out)
 
-    def back_project(self, proj):
+    def back_project(self, proj, out=None):
         """Compute X-ray back projection (exact adjoint of :meth:`project`)."""
         if tuple(proj.shape) != self.output_shape:
             raise ValueError(f"array of shape {tuple(proj.shape)} does not match {self.output_shape}")
-        return _apply(self._plans, proj, self.input_shape, False, 1, _device_index(self.input_device))
+        return _apply(self._plans, proj, self.input_shape, False, 1, _device_index(self.input_device), out)
 
     matrices_from_euler_angles = staticmethod(matrices_from_euler_angles)
 

@@ -1,0 +1,90 @@
+"""Multi-GPU (NCCL, one process per GPU) checks of scico_b200/sharded.py with the native CUDA
+operators.  Needs >= 2 GPUs (run with `gpurun --gpus 2`); skipped otherwise."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, case):
+    import torch
+    import torch.distributed as dist
+
+    import scico_b200 as sb
+    from scico_b200 import sharded
+    from oracle import xray_c as C
+    from oracle import xray_np as O
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        rng = np.random.default_rng(3)
+        if case == "slab":
+            N, D, V = (32, 48, 40), (32, 64), 12
+            M = sb.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, V, endpoint=False)[:, None])
+            x = rng.standard_normal(N).astype(np.float32)
+            y = rng.standard_normal((V,) + D).astype(np.float32)
+            op = sharded.SlabShardedXRayTransform3D(N, M, D)
+            (z0, z1), (r0, r1) = op.slab, op.rows
+            got = op.project(torch.as_tensor(x[z0:z1], device=dev)).cpu().numpy()
+            assert O.rel_l2(got, C.project_3d(x, op.matrices, D)[:, r0:r1]) <= 1e-5
+            back = op.back_project(torch.as_tensor(np.ascontiguousarray(y[:, r0:r1]), device=dev)).cpu().numpy()
+            assert O.rel_l2(back, C.back_project_3d(y, op.matrices, N)[z0:z1]) <= 1e-5
+        elif case == "slab_halo":
+            N, D, V = (30, 40, 36), (32, 52), 6
+            M = sb.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, V, endpoint=False)[:, None],
+                                              voxel_spacing=[0.8, 1.0, 1.0])
+            x = rng.standard_normal(N).astype(np.float32)
+            op = sharded.SlabShardedXRayTransform3D(N, M, D)
+            (z0, z1), (r0, r1) = op.slab, op.rows
+            got = op.project(torch.as_tensor(x[z0:z1], device=dev)).cpu().numpy()
+            assert O.rel_l2(got, C.project_3d(x, op.matrices, D)[:, r0:r1]) <= 1e-5
+        elif case == "view3d":
+            N, D, V = (20, 24, 28), (30, 36), 10
+            ang = np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, 0.5)], 1)
+            M = sb.matrices_from_euler_angles(N, D, "XY", ang)
+            x = rng.standard_normal(N).astype(np.float32)
+            y = rng.standard_normal((V,) + D).astype(np.float32)
+            op = sharded.ViewShardedXRayTransform3D(N, M, D)
+            (z0, z1), (v0, v1) = op.slab, op.views
+            got = op.project(torch.as_tensor(x[z0:z1], device=dev)).cpu().numpy()
+            assert O.rel_l2(got, C.project_3d(x, op.matrices, D)[v0:v1]) <= 1e-5
+            back = op.back_project(torch.as_tensor(np.ascontiguousarray(y[v0:v1]), device=dev)).cpu().numpy()
+            assert O.rel_l2(back, C.back_project_3d(y, op.matrices, N)[z0:z1]) <= 1e-5
+        elif case == "view2d":
+            nx, V = (96, 80), 30
+            angles = np.linspace(0, np.pi, V, endpoint=False)
+            op = sharded.ViewShardedXRayTransform2D(nx, angles)
+            full = sb.XRayTransform2D(nx, angles)
+            x = rng.standard_normal(nx).astype(np.float32)
+            y = rng.standard_normal((V, op.ny)).astype(np.float32)
+            T = full.view_table
+            (z0, z1), (v0, v1) = op.slab, op.views
+            got = op.project(torch.as_tensor(x, device=dev)).cpu().numpy()
+            assert O.rel_l2(got, C.project_2d(x, T, op.ny)[v0:v1]) <= 1e-5
+            back = op.back_project(torch.as_tensor(np.ascontiguousarray(y[v0:v1]), device=dev)).cpu().numpy()
+            assert O.rel_l2(back, C.back_project_2d(y, T, nx)[z0:z1]) <= 1e-5
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["slab", "slab_halo", "view3d", "view2d"])
+def test_sharded_operators_nccl(case):
+    import torch
+    import torch.multiprocessing as mp
+
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    mp.spawn(_worker, args=(2, _free_port(), case), nprocs=2, join=True)
