@@ -68,6 +68,8 @@ struct xct_plan {
   bool rows_unit = false;
   bool adj_walk = false;
   bool fwd_walk = false;
+  bool fwd_cold = false;   // some view's minor-axis coefficient can move the bin by more than one per step
+  bool fwd_unit4 = false;  // vector flush possible (unit rows, D1 % 4 == 0, window fits with 4-bin alignment)
   int* d_list4[4] = {nullptr, nullptr, nullptr, nullptr};  // walk forward: [2*major_b + minor_up]
   int n_list4[4] = {0, 0, 0, 0};
   long long* d_rowoff = nullptr;  // [V][n0] element offset of the (local) sinogram row, or -1
@@ -111,7 +113,8 @@ int check_device(int device) {
 // Split the views into the two classes of the forward kernel and pick its lane stride.
 // Returns false when some view is outside the plane kernels' envelope.
 struct Envelope {
-  bool adj_ok = true, fwd_ok = true, adj_walk_ok = true;
+  bool adj_ok = true, fwd_ok = true, adj_walk_ok = true, fwd_unit4_ok = true;
+  float max_minor = 0.f;
   int gs = 2;
   std::vector<int> list[2];
   std::vector<int> list4[4];  // [2*major_b + minor_up]: minor-axis coefficient >= 0
@@ -145,6 +148,9 @@ Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fw
       const float a = std::fabs(vr.ca), b = std::fabs(vr.cb);
       const float mj = std::max(a, b), mn = std::min(a, b);
       if (mj * (32 * env.gs - 1) + mn * (fwdTN - 1) + 3.f > (float)kFwdWin) env.fwd_ok = false;
+      // walk forward with the window start rounded down to a multiple of 4 bins
+      if (mj * (32 * env.gs - 1) + mn * (kWFwdTN - 1) + 6.f > (float)kFwdWin) env.fwd_unit4_ok = false;
+      env.max_minor = std::max(env.max_minor, mn);
     }
   }
   return env;
@@ -264,11 +270,15 @@ int launch_plane_forward(const xct_plan* pl, int batch, const float* in, float* 
 }
 
 // walk forward: one launch per (major axis, minor-axis sign) class
-template <class G, bool IS3D, int S, int TN, int GS, bool MAJOR_B, bool MINOR_UP>
+template <class G, bool IS3D, int S, int TN, int GS, bool MAJOR_B, bool MINOR_UP, bool COLD, bool UNIT4>
 int launch_walk_forward_class(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
   const int cls = (MAJOR_B ? 2 : 0) + (MINOR_UP ? 1 : 0);
   if (pl->n_list4[cls] == 0) return XCT_OK;
-  xct::PlaneParams p = plane_params(pl, batch);
+  xct::Walk2Params wp{};
+  wp.p = plane_params(pl, batch);
+  wp.rowoff = pl->d_rowoff;
+  wp.out_scale = 2.0f;
+  xct::PlaneParams& p = wp.p;
   p.view_list = pl->d_list4[cls];
   p.n_list = pl->n_list4[cls];
   constexpr int TM = 32 * GS;
@@ -283,17 +293,28 @@ int launch_walk_forward_class(const xct_plan* pl, int batch, const float* in, fl
   chunks = ceil_div(p.n_list, p.views_per_chunk);
   const size_t smem = (size_t)kWarps * S * kFwdWin * sizeof(float);
   dim3 grid(blocks, chunks);
-  xct::walk_forward_kernel<G, IS3D, S, TN, GS, kFwdWin, MAJOR_B, MINOR_UP, kWarps><<<grid, kWarps * 32, smem, st>>>(p, in, out);
+  xct::walk_forward_kernel<G, IS3D, S, TN, GS, kFwdWin, MAJOR_B, MINOR_UP, COLD, UNIT4, kWarps>
+      <<<grid, kWarps * 32, smem, st>>>(wp, in, out);
   return launch_ok("walk_forward_kernel");
 }
 
-template <class G, bool IS3D, int S, int TN>
-int launch_walk_forward(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+template <class G, bool IS3D, int S, int TN, bool COLD, bool UNIT4>
+int launch_walk_forward_v(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
   int rc;
-  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, true>(pl, batch, in, out, st))) return rc;
-  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, false>(pl, batch, in, out, st))) return rc;
-  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, false, true>(pl, batch, in, out, st))) return rc;
-  return launch_walk_forward_class<G, IS3D, S, TN, 2, false, false>(pl, batch, in, out, st);
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, true, COLD, UNIT4>(pl, batch, in, out, st))) return rc;
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, false, COLD, UNIT4>(pl, batch, in, out, st))) return rc;
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, false, true, COLD, UNIT4>(pl, batch, in, out, st))) return rc;
+  return launch_walk_forward_class<G, IS3D, S, TN, 2, false, false, COLD, UNIT4>(pl, batch, in, out, st);
+}
+
+// 3D separable forward.  The vector flush needs unit rows, D1 % 4 == 0 and a 16-byte aligned sinogram.
+int launch_walk_forward3(const xct_plan* pl, const float* in, float* out, cudaStream_t st) {
+  const bool unit4 = pl->fwd_unit4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (pl->fwd_cold) {
+    return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, true, false>(pl, 1, in, out, st);
+  }
+  if (unit4) return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, true>(pl, 1, in, out, st);
+  return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, false>(pl, 1, in, out, st);
 }
 
 xct::Gen3Params gen3_params(const xct_plan* pl) {
@@ -507,6 +528,8 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       pl->adj_plane = env.adj_ok;
       pl->fwd_plane = env.fwd_ok;
       pl->fwd_walk = env.fwd_ok && env.gs == 2 && !(g->flags & XCT_FLAG_NO_WALK);
+      pl->fwd_cold = env.max_minor > 0.98f;
+      pl->fwd_unit4 = env.fwd_unit4_ok && unit && (g->d1 % 4 == 0);
       pl->adj_walk = env.adj_ok && env.adj_walk_ok && unit && (g->d1 % 4 == 0) && !(g->flags & XCT_FLAG_NO_WALK);
       pl->gs = env.fwd_ok ? env.gs : 0;
       if (pl->adj_plane && pl->fwd_plane) pl->path = XCT_PATH_3D_SEP;
@@ -556,7 +579,7 @@ int xct_forward(const xct_plan* pl, const float* in, float* out, int32_t batch, 
   // every forward kernel accumulates with RED: the (possibly uninitialised) output is zeroed first
   XCT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * out_elems(pl) * batch, st));
   if (pl->ndim == 3) {
-    if (pl->fwd_walk) return launch_walk_forward<xct::Geom3, true, kWFwdS, kWFwdTN>(pl, 1, in, out, st);
+    if (pl->fwd_walk) return launch_walk_forward3(pl, in, out, st);
     if (pl->fwd_plane) return launch_plane_forward<xct::Geom3, true, kFwd3S, kFwd3TN>(pl, 1, in, out, st);
     xct::gen3d_forward_kernel<<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, out);
     return launch_ok("gen3d_forward_kernel");

@@ -227,14 +227,25 @@ struct SliceVec<2> { using type = float2; };
 template <>
 struct SliceVec<4> { using type = float4; };
 
-template <class G, bool IS3D, int S, int TN, int GS, int WIN, bool MAJOR_B, bool MINOR_UP, int WARPS>
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// COLD : keep the path for bin jumps larger than one (needed only when |c_minor| can reach 1).
+// UNIT4: 3D unit-row mode with 16-byte aligned rows (D1 % 4 == 0, aligned sinogram pointer): the
+//        window starts at a multiple of 4 bins and is flushed with red.global.add.v4.f32, one lane per
+//        4 consecutive bins of one slice (REDG.E.ADD.F32x4: 1.8x the scalar RED rate, 4x fewer ops).
+template <class G, bool IS3D, int S, int TN, int GS, int WIN, bool MAJOR_B, bool MINOR_UP, bool COLD, bool UNIT4,
+          int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-walk_forward_kernel(PlaneParams p, const float* __restrict__ in, float* __restrict__ sino) {
+walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restrict__ sino) {
   static_assert(WIN % 32 == 0, "window is flushed 32 bins at a time");
   static_assert(S == 2 || S == 4, "window slots are float2 / float4");
+  static_assert(!UNIT4 || (S == 4 && IS3D), "the vector flush is written for 4 slices");
   using Vec = typename SliceVec<S>::type;
   constexpr int Q = WIN / 32;
   constexpr int TM = 32 * GS;
+  const PlaneParams& p = wp.p;
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sgroups = (p.NS + S - 1) / S;
@@ -247,6 +258,7 @@ walk_forward_kernel(PlaneParams p, const float* __restrict__ in, float* __restri
   const int sg = (int)(task / p.tilesA);
   const int a0 = ta * (MAJOR_B ? TN : TM), b0 = tb * (MAJOR_B ? TM : TN), s0 = sg * S;
   float* win = smem + (size_t)warp * (WIN * S);
+  Vec* winv = reinterpret_cast<Vec*>(win);
 
   // this thread's voxels, kept for every view of the launch
   float x[GS][TN][S];
@@ -266,23 +278,26 @@ walk_forward_kernel(PlaneParams p, const float* __restrict__ in, float* __restri
   const float xmin0 = MAJOR_B ? G::coordA(a0) : G::coordB(b0);
 
   auto rmw = [&](int t, const float (&v)[S]) {  // win[t][:] += v   (one lane per address)
-    Vec* q = reinterpret_cast<Vec*>(win) + t;
-    Vec cur = *q;
+    Vec cur = winv[t];
     float* c = reinterpret_cast<float*>(&cur);
 #pragma unroll
     for (int s = 0; s < S; ++s) c[s] += v[s];
-    *q = cur;
+    winv[t] = cur;
   };
+  Vec vzero;
+#pragma unroll
+  for (int s = 0; s < S; ++s) reinterpret_cast<float*>(&vzero)[s] = 0.f;
 
   const int v_begin = blockIdx.y * p.views_per_chunk;
   const int v_end = min(p.n_list, v_begin + p.views_per_chunk);
   for (int vi = v_begin; vi < v_end; ++vi) {
     const int v = p.view_list ? __ldg(p.view_list + vi) : vi;
     const ViewRec vr = load_view(p.views + v);
-    const int c0 = window_start<G>(vr, a0, a0 + (MAJOR_B ? TN : TM) - 1, b0, b0 + (MAJOR_B ? TM : TN) - 1);
+    int c0 = window_start<G>(vr, a0, a0 + (MAJOR_B ? TN : TM) - 1, b0, b0 + (MAJOR_B ? TM : TN) - 1);
+    if (UNIT4) c0 &= ~3;
 
 #pragma unroll
-    for (int q = 0; q < Q * S; ++q) win[lane + 32 * q] = 0.f;
+    for (int q = 0; q < Q; ++q) winv[lane + 32 * q] = vzero;
     __syncwarp();
 
 #pragma unroll
@@ -306,17 +321,16 @@ walk_forward_kernel(PlaneParams p, const float* __restrict__ in, float* __restri
           }
         } else {
           if (t != tp) {
-            const bool step1 = MINOR_UP ? (t == tp + 1) : (t == tp - 1);
             // the bin that falls out of the carried pair is complete for this walk: flush it
             if (MINOR_UP) rmw(tp, lo);
             else rmw(tp + 1, hi);
-            if (step1) {
+            if (!COLD || (MINOR_UP ? (t == tp + 1) : (t == tp - 1))) {
 #pragma unroll
               for (int s = 0; s < S; ++s) {
                 if (MINOR_UP) { lo[s] = hi[s]; hi[s] = 0.f; }
                 else { hi[s] = lo[s]; lo[s] = 0.f; }
               }
-            } else {  // cold: the bin moved by more than one (|c_minor| > 1): flush the other one too
+            } else {  // the bin moved by more than one (|c_minor| > 1): flush the other one too
               if (MINOR_UP) rmw(tp + 1, hi);
               else rmw(tp, lo);
 #pragma unroll
@@ -339,28 +353,60 @@ walk_forward_kernel(PlaneParams p, const float* __restrict__ in, float* __restri
       __syncwarp();
     }
 
-    // flush the window: bin (c0 + t) of slice s; rows / weights from the slice's row record
+    // ---- flush the window to the sinogram
+    if (UNIT4) {
+      // lane j owns bins 4j .. 4j+3; column group is entirely inside or outside [0, D1)
+      const int col = c0 + 4 * lane;
+      if (lane < WIN / 4 && (unsigned)col < (unsigned)p.D1) {
+        float blk[4][S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const int sl = s0 + s;
-      if (sl >= p.NS) break;
-      RowRec rr;
-      float* y0;
-      if (IS3D) {
-        rr = load_row(p.rows + (size_t)v * p.NS + sl);
-        y0 = sino + ((size_t)v * p.D0 + rr.r0) * (size_t)p.D1;
-      } else {
-        rr.r0 = 0; rr.w0 = 1.f; rr.w1 = 0.f;
-        y0 = sino + ((size_t)sl * p.V + v) * (size_t)p.D1;
+        for (int k = 0; k < 4; ++k) {
+          const Vec r = winv[4 * lane + k];
+#pragma unroll
+          for (int s = 0; s < S; ++s) blk[k][s] = reinterpret_cast<const float*>(&r)[s];
+        }
+        const long long* ro = wp.rowoff + (size_t)v * p.NS;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int sl = s0 + s;
+          if (sl >= p.NS) break;
+          const long long off = __ldg(ro + sl);
+          const bool any = blk[0][s] != 0.f || blk[1][s] != 0.f || blk[2][s] != 0.f || blk[3][s] != 0.f;
+          if (off >= 0 && any)
+            red_add_v4(sino + off + col, wp.out_scale * blk[0][s], wp.out_scale * blk[1][s],
+                       wp.out_scale * blk[2][s], wp.out_scale * blk[3][s]);
+        }
+      }
+    } else {
+      // bin (c0 + t) of slice s; rows / weights from the slice's row record
+      RowRec rr[S];
+      float* y0[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int sl = min(s0 + s, p.NS - 1);
+        if (IS3D) {
+          rr[s] = load_row(p.rows + (size_t)v * p.NS + sl);
+          y0[s] = sino + ((size_t)v * p.D0 + rr[s].r0) * (size_t)p.D1;
+        } else {
+          rr[s].r0 = 0; rr[s].w0 = 1.f; rr[s].w1 = 0.f;
+          y0[s] = sino + ((size_t)sl * p.V + v) * (size_t)p.D1;
+        }
+        if (s0 + s >= p.NS) rr[s].w0 = rr[s].w1 = 0.f;
       }
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
         const int t = lane + 32 * q;
-        const float val = win[t * S + s];
+        const Vec r = winv[t];
         const int col = c0 + t;
-        if (val != 0.f && col >= 0 && col < p.D1) {
-          if (rr.w0 != 0.f) atomicAdd(y0 + col, rr.w0 * val);
-          if (IS3D && rr.w1 != 0.f) atomicAdd(y0 + p.D1 + col, rr.w1 * val);
+        if (col >= 0 && col < p.D1) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            const float val = reinterpret_cast<const float*>(&r)[s];
+            if (val != 0.f) {
+              if (rr[s].w0 != 0.f) atomicAdd(y0[s] + col, rr[s].w0 * val);
+              if (IS3D && rr[s].w1 != 0.f) atomicAdd(y0[s] + p.D1 + col, rr[s].w1 * val);
+            }
+          }
         }
       }
     }

@@ -65,6 +65,9 @@ CASES_3D.update({
     "walk_det_rows_offcentre": ((12, 30, 30), (20, 44), lambda: _x_mats((12, 30, 30), (20, 44), 5)),
     "walk_one_view": ((8, 33, 31), (8, 48), lambda: _x_mats((8, 33, 31), (8, 48), 1)),
     "walk_two_views": ((8, 33, 31), (8, 48), lambda: _x_mats((8, 33, 31), (8, 48), 2)),
+    # in-plane voxel spacing 1.4: minor-axis coefficient reaches 0.99 -> bins can jump by two (cold path)
+    "walk_cold_spacing": ((6, 40, 44), (6, 96), lambda: _x_mats((6, 40, 44), (6, 96), 16, voxel_spacing=[1.0, 1.4, 1.4])),
+    "walk_many_slices": ((70, 24, 20), (70, 36), lambda: _x_mats((70, 24, 20), (70, 36), 6)),
 })
 
 
@@ -113,9 +116,12 @@ def test_walk_kernels_selected_and_match_plane_kernels(torch_dev):
         A = sb.XRayTransform3D(N, M, D)
         B = sb.XRayTransform3D(N, M, D, _flags=_lib.FLAG_NO_WALK)
         assert A.plan_info()["adj_kernel"] == 2 and B.plan_info()["adj_kernel"] == 1
+        assert A.plan_info()["fwd_kernel"] == 2 and B.plan_info()["fwd_kernel"] == 1
         y = rng.standard_normal(A.output_shape).astype(np.float32)
         a, b = _gpu(torch, dev, A, y, adj=True), _gpu(torch, dev, B, y, adj=True)
         assert O.rel_l2(a, b) <= 1e-6
+        x = rng.standard_normal(N).astype(np.float32)
+        assert O.rel_l2(_gpu(torch, dev, A, x), _gpu(torch, dev, B, x)) <= 2e-6
     # a sliced (unaligned) sinogram pointer falls back to the plane kernel and still agrees
     N, D, mk = CASES_3D["walk_basic"]
     A = sb.XRayTransform3D(N, mk(), D)
@@ -125,6 +131,13 @@ def test_walk_kernels_selected_and_match_plane_kernels(torch_dev):
     assert buf[1:].data_ptr() % 16 != 0
     got = A.adj(buf[1:].view(A.output_shape)).cpu().numpy()
     assert O.rel_l2(got, C.back_project_3d(y, A.matrices, N)) <= TOL
+    # ... and an unaligned OUTPUT pointer makes the forward fall back from the vector flush
+    x = rng.standard_normal(N).astype(np.float32)
+    obuf = torch.empty(int(np.prod(A.output_shape)) + 1, device=dev)
+    out = obuf[1:].view(A.output_shape)
+    assert out.data_ptr() % 16 != 0
+    A.project(torch.as_tensor(x, device=dev), out=out)
+    assert O.rel_l2(out.cpu().numpy(), C.project_3d(x, A.matrices, D)) <= TOL
 
 
 def test_3d_paths_selected(torch_dev):
