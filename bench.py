@@ -278,13 +278,13 @@ def main():
     peak, peak_src = hbm_peak()
     loc_updates = float((z1 - z0) * N[1] * N[2]) * V
     loc_bytes = 4.0 * (loc_updates + float(V) * (r1 - r0) * D[1])
-    n_fwd_launch = 2
+    n_fwd_launch = max(1, int(launches) // max(1, args.steps) - 1)  # per step: forward class launches + 1 adjoint
     ach_fwd = loc_bytes / (fwd_ms * 1e-3) / 1e9
     ach_adj = loc_bytes / (adj_ms * 1e-3) / 1e9
     kname = {0: "gen3d", 1: "plane", 2: "walk"}
     prof = ncu_profile()
     roofline = {
-        "bound": "hbm", "kernel": f"{kname[info['fwd_kernel']]}_forward_kernel<Geom3> (2 launches per application, one per view class)",
+        "bound": "hbm", "kernel": f"{kname[info['fwd_kernel']]}_forward_kernel<Geom3> ({n_fwd_launch} launches per application, one per view class)",
         "achieved": ach_fwd, "peak": peak, "unit": "GB/s", "frac": ach_fwd / peak,
         "algorithmic_bytes_per_launch": loc_bytes / n_fwd_launch, "launch_ms": fwd_ms / n_fwd_launch,
         "traffic": prof.get("forward_traffic_bytes_per_launch_at_bench_size"), "peak_source": peak_src + ", of measured",

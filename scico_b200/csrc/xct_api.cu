@@ -123,6 +123,7 @@ struct Envelope {
 Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fwdTN) {
   Envelope env;
   float min_major = 1e30f;
+  std::vector<int> zero_minor[2];
   for (size_t v = 0; v < views.size(); ++v) {
     const float a = std::fabs(views[v].ca), b = std::fabs(views[v].cb);
     if (!std::isfinite(a) || !std::isfinite(b)) {
@@ -136,8 +137,14 @@ Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fw
     const bool major_b = b >= a;
     env.list[major_b ? 1 : 0].push_back((int)v);
     const float minor = major_b ? views[v].ca : views[v].cb;
-    env.list4[(major_b ? 2 : 0) + (minor >= 0.f ? 1 : 0)].push_back((int)v);
+    if (minor == 0.f) zero_minor[major_b ? 1 : 0].push_back((int)v);  // no bin movement: either sign class
+    else env.list4[(major_b ? 2 : 0) + (minor > 0.f ? 1 : 0)].push_back((int)v);
     min_major = std::min(min_major, std::max(a, b));
+  }
+  for (int m = 0; m < 2; ++m) {  // views with a zero minor coefficient join the larger sign class
+    auto& dst = env.list4[2 * m + (env.list4[2 * m + 1].size() >= env.list4[2 * m].size() ? 1 : 0)];
+    dst.insert(dst.end(), zero_minor[m].begin(), zero_minor[m].end());
+    std::sort(dst.begin(), dst.end());
   }
   // lanes GS voxels apart along the major axis must land >= 1 bin apart
   if (2.f * min_major >= 1.01f) env.gs = 2;
