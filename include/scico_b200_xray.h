@@ -142,6 +142,34 @@ XCT_API int xct3d_debug_weights(const xct_plan *plan, int32_t view, int32_t *ul_
 XCT_API int xct2d_debug_weights(const xct_plan *plan, int32_t view, int32_t *inds_dev, float *w_dev,
                                 void *stream);
 
+/* ---- TV-regularised PDHG around the projector pair --------------------------
+ * Fused device kernels for C = VerticalStack((A, D)), D = FiniteDifference(append=0)
+ * (scico/linop/_diff.py:25-96), g = Separable(SquaredL2Loss(y), lam * L21Norm())
+ * (scico/loss.py:220-226, scico/functional/_norm.py:254-263), f = ZeroFunctional or
+ * NonNegativeIndicator; one PDHG iteration (scico/optimize/_primaldual.py:219-231) is
+ *   atz = xct_adjoint(z0);  xct_tv_primal_step;  ax = xct_forward(xbar);  xct_tv_dual_step;  xct_l2_dual_step.
+ * All pointers are DEVICE pointers, float32, C-contiguous; nothing allocates or synchronises. */
+typedef struct xct_tv_block {
+  int32_t n0, n1, n2; /* LOCAL volume block (a z-slab of the global volume when sharded) */
+  int32_t is_first;   /* block holds the global first slice along axis 0 */
+  int32_t is_last;    /* block holds the global last slice along axis 0 */
+} xct_tv_block;
+
+/* x <- prox_{tau f}(x - tau (atz + D^T z1)),  xbar <- (1 + alpha) x_new - alpha x_old.
+ * z1: (3, n0, n1, n2).  lo_halo: plane z1[0][-1] of the previous slab (NULL when is_first). */
+XCT_API int xct_tv_primal_step(const xct_tv_block *blk, float *x, float *xbar, const float *atz,
+                               const float *z1, const float *lo_halo, float tau, float alpha,
+                               int32_t nonneg, void *stream);
+/* z1 <- conj_prox_{sigma, lam ||.||_{2,1}}(z1 + sigma D xbar).  hi_halo: plane xbar[n0] of the next
+ * slab (NULL when is_last). */
+XCT_API int xct_tv_dual_step(const xct_tv_block *blk, float *z1, const float *xbar, const float *hi_halo,
+                             float sigma, float lam, void *stream);
+/* z0 <- conj_prox_{sigma, 1/2 ||. - y||^2}(z0 + sigma ax), n elements. */
+XCT_API int xct_l2_dual_step(int64_t n, float *z0, const float *ax, const float *y, float sigma, void *stream);
+/* FiniteDifference(append=0): out (3, n0, n1, n2) = D x;  out (n0, n1, n2) = D^T z1. */
+XCT_API int xct_fd_forward(const xct_tv_block *blk, const float *x, const float *hi_halo, float *out, void *stream);
+XCT_API int xct_fd_adjoint(const xct_tv_block *blk, const float *z1, const float *lo_halo, float *out, void *stream);
+
 /* Number of this library's kernels launched by the calling thread since the last reset
  * (bench.py's gpu_launches claim). */
 XCT_API int64_t xct_launch_count(void);

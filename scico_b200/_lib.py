@@ -43,6 +43,11 @@ EXPORTED_SYMBOLS = (
     "xct2d_debug_weights",
     "xct_launch_count",
     "xct_launch_count_reset",
+    "xct_tv_primal_step",
+    "xct_tv_dual_step",
+    "xct_l2_dual_step",
+    "xct_fd_forward",
+    "xct_fd_adjoint",
 )
 
 
@@ -91,6 +96,10 @@ class PlanInfo(ctypes.Structure):
     ]
 
 
+class TvBlock(ctypes.Structure):
+    _fields_ = [("n0", c_int32), ("n1", c_int32), ("n2", c_int32), ("is_first", c_int32), ("is_last", c_int32)]
+
+
 class XctError(RuntimeError):
     """Raised when a C-ABI call returns a negative status."""
 
@@ -127,6 +136,12 @@ def lib() -> ctypes.CDLL:
         getattr(L, name).argtypes = [c_void_p, c_void_p, c_void_p, c_int32]
     L.xct3d_debug_weights.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
     L.xct2d_debug_weights.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
+    cf = ctypes.c_float
+    L.xct_tv_primal_step.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, cf, cf, c_int32, c_void_p]
+    L.xct_tv_dual_step.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, cf, cf, c_void_p]
+    L.xct_l2_dual_step.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, cf, c_void_p]
+    L.xct_fd_forward.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p]
+    L.xct_fd_adjoint.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p]
     L.xct_launch_count.restype = c_int64
     L.xct_launch_count_reset.restype = None
     _lib = L

@@ -14,6 +14,7 @@
 #include "xct_general.cuh"
 #include "xct_plane.cuh"
 #include "xct_plane2.cuh"
+#include "xct_tv.cuh"
 
 namespace {
 
@@ -633,6 +634,62 @@ int xct_forward_host(xct_plan* pl, const float* in_host, float* out_host, int32_
 }
 int xct_adjoint_host(xct_plan* pl, const float* in_host, float* out_host, int32_t batch) {
   return run_host(pl, in_host, out_host, batch, false);
+}
+
+// ---------------------------------------------------------------- TV / PDHG kernels (xct_tv.cuh)
+static int tv_check(const xct_tv_block* b, const void* p0, const void* p1) {
+  if (!b || !p0 || !p1) return fail(XCT_ERR_INVALID, "null argument");
+  if (b->n0 < 1 || b->n1 < 1 || b->n2 < 1) return fail(XCT_ERR_INVALID, "bad volume block shape");
+  return XCT_OK;
+}
+static xct::TvDims tv_dims(const xct_tv_block* b) {
+  xct::TvDims d{};
+  d.n0 = b->n0; d.n1 = b->n1; d.n2 = b->n2; d.first = b->is_first ? 1 : 0; d.last = b->is_last ? 1 : 0;
+  return d;
+}
+static int tv_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148u * 32u); }
+
+int xct_tv_primal_step(const xct_tv_block* b, float* x, float* xbar, const float* atz, const float* z1,
+                       const float* lo_halo, float tau, float alpha, int32_t nonneg, void* stream) {
+  int rc = tv_check(b, x, xbar);
+  if (rc) return rc;
+  if (!atz || !z1) return fail(XCT_ERR_INVALID, "null argument");
+  const size_t n = (size_t)b->n0 * b->n1 * b->n2;
+  xct::tv_primal_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), x, xbar, atz, z1, lo_halo, tau, alpha, nonneg);
+  return launch_ok("tv_primal_kernel");
+}
+
+int xct_tv_dual_step(const xct_tv_block* b, float* z1, const float* xbar, const float* hi_halo, float sigma,
+                     float lam, void* stream) {
+  int rc = tv_check(b, z1, xbar);
+  if (rc) return rc;
+  if (!(sigma > 0.f)) return fail(XCT_ERR_INVALID, "sigma must be positive");
+  const size_t n = (size_t)b->n0 * b->n1 * b->n2;
+  xct::tv_dual_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), z1, xbar, hi_halo, sigma, lam);
+  return launch_ok("tv_dual_kernel");
+}
+
+int xct_l2_dual_step(int64_t n, float* z0, const float* ax, const float* y, float sigma, void* stream) {
+  if (!z0 || !ax || !y || n < 1) return fail(XCT_ERR_INVALID, "null argument or empty array");
+  if (!(sigma > 0.f)) return fail(XCT_ERR_INVALID, "sigma must be positive");
+  xct::l2_dual_kernel<<<tv_grid((size_t)n), 256, 0, (cudaStream_t)stream>>>((size_t)n, z0, ax, y, sigma);
+  return launch_ok("l2_dual_kernel");
+}
+
+int xct_fd_forward(const xct_tv_block* b, const float* x, const float* hi_halo, float* out, void* stream) {
+  int rc = tv_check(b, x, out);
+  if (rc) return rc;
+  const size_t n = (size_t)b->n0 * b->n1 * b->n2;
+  xct::fd_forward_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), x, hi_halo, out);
+  return launch_ok("fd_forward_kernel");
+}
+
+int xct_fd_adjoint(const xct_tv_block* b, const float* z1, const float* lo_halo, float* out, void* stream) {
+  int rc = tv_check(b, z1, out);
+  if (rc) return rc;
+  const size_t n = (size_t)b->n0 * b->n1 * b->n2;
+  xct::fd_adjoint_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), z1, lo_halo, out);
+  return launch_ok("fd_adjoint_kernel");
 }
 
 int xct3d_debug_weights(const xct_plan* pl, int32_t view, int32_t* ul, float* w, void* stream) {
