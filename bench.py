@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--views", type=int, default=1024)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--solver-iters", type=int, default=3, help="TV-PDHG iterations timed after the operator bench (0 = skip)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -201,6 +202,7 @@ def main():
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
+        os.environ.pop("NCCL_DEBUG", None)  # NCCL's version banner goes to stdout: keep it to ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     wl = workload(args)
@@ -321,6 +323,29 @@ def main():
                "d2h_bytes_per_step": int(per_dir * world), "ms_per_step": dt * 1e3,
                "api": "XRayTransform3D.project/.back_project(host array, out=pinned host array) -> xct_forward_host/xct_adjoint_host"}
 
+    # second half of BASELINE.json's metric: TV-regularised PDHG iterations/s on the same operator
+    # (device-resident state, iteration statistics off: no host sync inside an iteration)
+    solver = None
+    if args.solver_iters > 0:
+        from scico_b200.optimize import TVPDHG
+
+        xh = sh = so = xo = xh_np = sh_np = None  # release the pinned e2e buffers
+        S = TVPDHG(SA if world > 1 else A, y, lam=0.1, tau=0.01, sigma=0.01, maxiter=args.solver_iters)
+        S.step()  # warm-up
+        barrier()
+        s0, s1 = ev(), ev()
+        s0.record()
+        for _ in range(args.solver_iters):
+            S.step()
+        s1.record()
+        barrier()
+        it_ms = reduce_max(s0.elapsed_time(s1)) / args.solver_iters
+        solver = {"algorithm": "PDHG, 1/2||Ax-y||^2 + lam ||Dx||_{2,1} (scico/optimize/_primaldual.py:219-231)",
+                  "iters_per_s": 1e3 / it_ms, "ms_per_iter": it_ms, "iters_timed": args.solver_iters,
+                  "per_iter": "1 back projection + 1 forward projection + 3 fused TV kernels", "itstats": "off",
+                  "state": "x, xbar, A^T z (volume), z1 (3 x volume), z0, y, A xbar (sinogram) resident in HBM"}
+        del S
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = cpu_sample(wl)
@@ -338,7 +363,7 @@ def main():
                        "partition": f"{world} z-slab(s), no collective", "kernel_path": info["path_name"],
                        "l2": "no flush: per-rank volume and sinogram (>= 0.5 GB each at 8 GPUs) exceed the 126 MB L2",
                        "fwd_ms": fwd_ms, "adj_ms": adj_ms},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "solver": solver, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

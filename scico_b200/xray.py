@@ -113,7 +113,10 @@ def _apply(plans: _Plans, x, out_shape, forward: bool, batch: int, default_devic
     elif not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == tuple(out_shape)
               and out.flags.c_contiguous and out.flags.writeable):
         raise ValueError("'out' must be a writeable C-contiguous float32 NumPy array of the result shape")
-    dev = default_device if default_device is not None else 0
+    if default_device is not None:
+        dev = default_device
+    else:  # host arrays run on the process's current CUDA device (one process per GPU under torchrun)
+        dev = torch.cuda.current_device() if (torch is not None and torch.cuda.is_available()) else 0
     _lib.check(fn_host(plans.get(dev), xin.ctypes.data, out.ctypes.data, batch))
     return torch.from_numpy(out) if was_torch else out
 

@@ -75,12 +75,32 @@ def _worker(rank, world, port, case):
             assert O.rel_l2(got, C.project_2d(x, T, op.ny)[v0:v1]) <= 1e-5
             back = op.back_project(torch.as_tensor(np.ascontiguousarray(y[v0:v1]), device=dev)).cpu().numpy()
             assert O.rel_l2(back, C.back_project_2d(y, T, nx)[z0:z1]) <= 1e-5
+        elif case == "pdhg_slab":
+            from scico_b200.optimize import TVPDHG
+
+            N, D, V = (16, 24, 20), (16, 32), 10
+            M = sb.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, V, endpoint=False)[:, None])
+            x_gt = np.zeros(N, np.float32)
+            x_gt[3:13, 6:16, 5:14] = 1.0
+            full = sb.XRayTransform3D(N, M, D)
+            y = full(torch.as_tensor(x_gt, device=dev)) + 0.05 * torch.randn((V,) + D, device=dev,
+                                                                              generator=torch.Generator(device=dev).manual_seed(1))
+            dist.broadcast(y, src=0)  # same data on both ranks
+            ref = TVPDHG(full, y, 0.1, 0.05, 0.05, maxiter=20)
+            ref.solve()
+            op = sharded.SlabShardedXRayTransform3D(N, M, D)
+            (z0, z1), (r0, r1) = op.slab, op.rows
+            S = TVPDHG(op, y[:, r0:r1].contiguous(), 0.1, 0.05, 0.05, maxiter=20)
+            S.solve()
+            rel = (torch.linalg.vector_norm(S.x - ref.x[z0:z1]) / torch.linalg.vector_norm(ref.x[z0:z1])).item()
+            assert rel <= 1e-5, rel
+            assert abs(S.objective() - ref.objective()) <= 1e-5 * ref.objective()
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["slab", "slab_halo", "view3d", "view2d"])
+@pytest.mark.parametrize("case", ["slab", "slab_halo", "view3d", "view2d", "pdhg_slab"])
 def test_sharded_operators_nccl(case):
     import torch
     import torch.multiprocessing as mp
