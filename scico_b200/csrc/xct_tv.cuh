@@ -71,11 +71,13 @@ tv_dual_kernel(TvDims d, float* __restrict__ z1, const float* __restrict__ xbar,
     if (k < d.n2 - 1) d2 = xbar[idx + 1] - xc;
     const float p0 = z1[idx] + sigma * d0, p1 = z1[idx + n] + sigma * d1, p2 = z1[idx + 2 * n] + sigma * d2;
     // conj_prox: p - sigma * prox_{(lam/sigma) ||.||}(p / sigma)
-    const float v0 = p0 / sigma, v1 = p1 / sigma, v2 = p2 / sigma;
+    // (v = p / sigma is evaluated as p * (1/sigma): 1 ulp from the reference's division, far inside
+    // the 1e-5 tolerance, and keeps this kernel HBM-bound instead of issue-bound)
+    const float v0 = p0 * inv_sigma, v1 = p1 * inv_sigma, v2 = p2 * inv_sigma;
     const float len = sqrtf((v0 * v0 + v1 * v1) + v2 * v2);
     float nl = len - lam * inv_sigma;
     nl = 0.5f * (nl + fabsf(nl));
-    const float sc = len != 0.f ? nl / len : 0.f;
+    const float sc = len != 0.f ? __fdividef(nl, len) : 0.f;
     z1[idx] = p0 - sigma * (v0 * sc);
     z1[idx + n] = p1 - sigma * (v1 * sc);
     z1[idx + 2 * n] = p2 - sigma * (v2 * sc);
@@ -86,10 +88,11 @@ tv_dual_kernel(TvDims d, float* __restrict__ z1, const float* __restrict__ xbar,
 __global__ void __launch_bounds__(256)
 l2_dual_kernel(size_t n, float* __restrict__ z0, const float* __restrict__ ax, const float* __restrict__ y, float sigma) {
   const float c = 1.0f / sigma;  // 2 * scale * lam with scale = 1/2, lam = 1/sigma
+  const float rc1 = 1.0f / (c + 1.0f);
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     const float p = z0[idx] + sigma * ax[idx];
-    const float v = p / sigma;
-    z0[idx] = p - sigma * ((c * y[idx] + v) / (c + 1.0f));
+    const float v = p * c;
+    z0[idx] = p - sigma * ((c * y[idx] + v) * rc1);
   }
 }
 
