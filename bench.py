@@ -345,6 +345,34 @@ def main():
                   "per_iter": "1 back projection + 1 forward projection + 3 fused TV kernels", "itstats": "off",
                   "state": "x, xbar, A^T z (volume), z1 (3 x volume), z0, y, A xbar (sinogram) resident in HBM"}
         del S
+        # the ADMM variants of the metric's name: proximal ADMM (ct_3d_tv_padmm.py) and ADMM + CG (ct_tv_admm.py)
+        from scico_b200.optimize import TVADMM, TVProximalADMM
+
+        def time_steps(S, n):
+            S.step()  # warm-up
+            barrier()
+            a, b = ev(), ev()
+            a.record()
+            for _ in range(n):
+                S.step()
+            b.record()
+            barrier()
+            return reduce_max(a.elapsed_time(b)) / n
+
+        S = TVProximalADMM(SA if world > 1 else A, y, lam=2.0, rho=5e-3, mu=1.3e6, nu=1.01, alpha=1e2, maxiter=args.solver_iters)
+        it_ms = time_steps(S, args.solver_iters)
+        solver["padmm"] = {"algorithm": "ProximalADMM, A=(C; alpha D), B=-I (scico/optimize/_padmm.py:349-363, ct_3d_tv_padmm.py)",
+                           "iters_per_s": 1e3 / it_ms, "ms_per_iter": it_ms, "iters_timed": args.solver_iters,
+                           "per_iter": "1 back projection + 1 forward projection + 3 fused kernels", "itstats": "off"}
+        del S
+        cg_it = 2
+        S = TVADMM(SA if world > 1 else A, y, lam=2.0, rho=5.0, maxiter=1, cg_tol=1e-30, cg_maxiter=cg_it)
+        it_ms = time_steps(S, 1)
+        solver["admm_cg"] = {"algorithm": "ADMM + CG x-step (scico/optimize/_admm.py:334-378, _admmaux.py:231-269, solver.py:367-405)",
+                             "iters_per_s": 1e3 / it_ms, "ms_per_iter": it_ms, "iters_timed": 1, "cg_iters_per_admm_iter": cg_it,
+                             "per_iter": f"{cg_it + 1} forward + {cg_it + 1} back projections + {3 * cg_it + 3} fused kernels; "
+                                         "host reads one scalar per CG iteration (termination test)", "itstats": "off"}
+        del S
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

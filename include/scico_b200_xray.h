@@ -170,6 +170,54 @@ XCT_API int xct_l2_dual_step(int64_t n, float *z0, const float *ax, const float 
 XCT_API int xct_fd_forward(const xct_tv_block *blk, const float *x, const float *hi_halo, float *out, void *stream);
 XCT_API int xct_fd_adjoint(const xct_tv_block *blk, const float *z1, const float *lo_halo, float *out, void *stream);
 
+/* ---- ADMM family around the projector pair ----------------------------------
+ * Fused device kernels for the TV-regularised CT problems the reference's examples solve with
+ *   ADMM + CG            scico/optimize/_admm.py:334-378, _admmaux.py:231-269, scico/solver.py:367-405
+ *                        (examples/scripts/ct_tv_admm.py: f = SquaredL2Loss(y, A), g = lam L21Norm, C = D)
+ *   LinearizedADMM       scico/optimize/_ladmm.py:253-277   (C = VerticalStack((A, D)))
+ *   ProximalADMM         scico/optimize/_padmm.py:349-363   (examples/scripts/ct_3d_tv_padmm.py:
+ *                        A = VerticalStack((C, alpha D)), B = -I, g = Separable(SquaredL2Loss(y), (lam/alpha) L21Norm))
+ * D = FiniteDifference(append=0).  Gradient-shaped arrays are (3, n0, n1, n2); a 2D image is the block
+ * (1, n0, n1) (its axis-0 component stays exactly zero).  DEVICE pointers, float32; reductions go to
+ * DEVICE doubles; nothing allocates or synchronises. */
+#define XCT_SPLIT_ADMM 0
+#define XCT_SPLIT_LADMM 1
+#define XCT_SPLIT_PADMM 2
+
+/* Gradient block.  Cx = dscale * D x;
+ *   ADMM/LADMM: z1 <- prox_{thr ||.||_{2,1}}(Cx + u1);                       u1 <- (u1 + Cx) - z1
+ *   PADMM:      z1 <- prox_{thr ||.||_{2,1}}(z1 + inv_nu ((Cx - z1) + u1));  u1 <- (u1 + Cx) - z1
+ *   w1 (LADMM) <- (Cx - z1) + u1;  w1 (PADMM) <- 2 u1_new - u1_old;  w1 unused (may be NULL) for ADMM.
+ * hi_halo: plane x[n0] of the next slab (NULL when is_last). */
+XCT_API int xct_grad_prox_step(const xct_tv_block *blk, const float *x, const float *hi_halo, float *z1, float *u1,
+                               float *w1, float dscale, float thr, float inv_nu, int32_t mode, void *stream);
+/* Sinogram block, g0 = 1/2 ||. - y||^2: prox_{c g0}(v) = (c y + v) / (c + 1) (scico/loss.py:220-226);
+ * z0, u0, w0 updated as above with Cx = ax.  mode: XCT_SPLIT_LADMM or XCT_SPLIT_PADMM. */
+XCT_API int xct_sino_prox_step(int64_t n, const float *ax, const float *y, float *z0, float *u0, float *w0, float c,
+                               float inv_nu, int32_t mode, void *stream);
+/* x <- prox_f(x - step (atq + dscale D^T w1)), f = 0 or the non-negativity indicator.
+ * lo_halo: plane w1[0][-1] of the previous slab (NULL when is_first). */
+XCT_API int xct_grad_primal_step(const xct_tv_block *blk, float *x, const float *atq, const float *w1,
+                                 const float *lo_halo, float step, float dscale, int32_t nonneg, void *stream);
+/* ADMM x-step right-hand side: rhs <- aty + rho D^T (z1 - u1);  *sumsq += ||rhs||^2.
+ * lo_halo: plane (z1 - u1)[0][-1] of the previous slab. */
+XCT_API int xct_admm_rhs(const xct_tv_block *blk, const float *aty, const float *z1, const float *u1,
+                         const float *lo_halo, float rho, float *rhs, double *sumsq, void *stream);
+/* CG on (A^T A + rho D^T D) x = rhs (scico/solver.py:367-405); the caller applies the projector pair.
+ *   init:      r <- rhs - (rho D^T D x + atax);  p <- r;  *num += r.r
+ *   lhs:       q <- rho D^T D p + atap;  *pq += p.q;  *zero_me <- 0 (may be NULL)
+ *   update_xr: alpha = *num / *pq;  x += alpha p;  r -= alpha q;  *num_new += r.r;  *zero_me <- 0
+ *   update_p:  beta = *num_new / *num;  p <- r + beta p
+ * lo_halo / hi_halo: planes [-1] / [n0] of the neighbouring slabs of the array D^T D is applied to. */
+XCT_API int xct_cg_init(const xct_tv_block *blk, const float *x, const float *lo_halo, const float *hi_halo,
+                        const float *atax, const float *rhs, float rho, float *r, float *p, double *num, void *stream);
+XCT_API int xct_cg_lhs(const xct_tv_block *blk, const float *p, const float *lo_halo, const float *hi_halo,
+                       const float *atap, float rho, float *q, double *pq, double *zero_me, void *stream);
+XCT_API int xct_cg_update_xr(int64_t n, float *x, float *r, const float *p, const float *q, const double *num,
+                             const double *pq, double *num_new, double *zero_me, void *stream);
+XCT_API int xct_cg_update_p(int64_t n, float *p, const float *r, const double *num, const double *num_new,
+                            void *stream);
+
 /* Number of this library's kernels launched by the calling thread since the last reset
  * (bench.py's gpu_launches claim). */
 XCT_API int64_t xct_launch_count(void);

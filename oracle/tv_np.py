@@ -13,6 +13,14 @@ Restates, in float32 and in the reference's operation order:
 * ``PDHG.step`` for ``C = VerticalStack((A, D))``, ``g = Separable(SquaredL2Loss(y), lam*L21Norm)``,
   ``f = ZeroFunctional`` or ``NonNegativeIndicator``: ``scico/optimize/_primaldual.py:219-231``.
 
+* ``scico.solver.cg``: ``scico/solver.py:367-405``.
+* ``ADMM.step`` with ``LinearSubproblemSolver`` for ``f = SquaredL2Loss(y, A)``, ``g = lam*L21Norm``,
+  ``C = FiniteDifference(append=0)`` (``examples/scripts/ct_tv_admm.py:68-84``):
+  ``scico/optimize/_admm.py:334-378``, ``scico/optimize/_admmaux.py:206-269``.
+* ``LinearizedADMM.step`` for ``C = VerticalStack((A, D))``: ``scico/optimize/_ladmm.py:253-277``.
+* ``ProximalADMM.step`` for ``A = VerticalStack((C, alpha*D))``, ``B = -I``
+  (``examples/scripts/ct_3d_tv_padmm.py:96-120``): ``scico/optimize/_padmm.py:349-363``.
+
 Pinning: these functions have no golden vectors in the reference's tests beyond generic operator
 identities (``scico/test/linop/test_diff.py``, ``scico/test/functional/test_norm.py`` check the adjoint
 identity and prox optimality); ``tests/test_tv_oracle.py`` checks the same identities here.
@@ -93,3 +101,109 @@ def tv_objective(x, A, y, lam) -> float:
     r = (A(x) - y).astype(np.float64)
     d = finite_difference(x).astype(np.float64)
     return float(0.5 * np.sum(r * r) + lam * np.sum(np.sqrt((d * d).sum(axis=0))))
+
+
+# ---------------------------------------------------------------------------------------------
+# ADMM family (scico/optimize/_admm.py, _ladmm.py, _padmm.py) and CG (scico/solver.py)
+# ---------------------------------------------------------------------------------------------
+def cg(A, b, x0, tol=1e-5, atol=0.0, maxiter=1000):
+    """``scico.solver.cg`` without preconditioner (``scico/solver.py:367-405``); float32 arrays,
+    scalars as NumPy float32 like the reference's jax scalars.  Returns (x, info)."""
+    b = np.asarray(b, dtype=f32)
+    x = np.asarray(x0, dtype=f32)
+    Ax = A(x)
+    bn = np.linalg.norm(b.ravel()).astype(f32)
+    r = (b - Ax).astype(f32)
+    p = r
+    num = np.sum(r * r, dtype=f32)
+    ii = 0
+    termination_tol_sq = np.maximum(f32(tol) * bn, f32(atol)) ** 2
+    while ii < maxiter and num > termination_tol_sq:
+        Ap = A(p)
+        alpha = f32(num / np.sum(p * Ap, dtype=f32))
+        x = (x + alpha * p).astype(f32)
+        r = (r - alpha * Ap).astype(f32)
+        num_old = num
+        num = np.sum(r * r, dtype=f32)
+        beta = f32(num / num_old)
+        p = (r + beta * p).astype(f32)
+        ii += 1
+    return x, {"num_iter": ii, "rel_res": float(np.sqrt(num) / bn) if bn > 0 else 0.0}
+
+
+def admm_tv_init(x0):
+    """``ADMM.z_init`` / ``u_init`` (``_admm.py:297-332``): z = C x0, u = 0."""
+    z = finite_difference(x0)
+    return np.asarray(x0, dtype=f32), z, np.zeros_like(z)
+
+
+def admm_tv_step(x, z, u, A, AT, y, lam, rho, cg_tol=1e-4, cg_maxiter=100):
+    """One ADMM iteration for f = 1/2||Ax - y||^2, g = lam||.||_{2,1}, C = D, alpha = 1.
+    Returns (x, z, u, cg_info)."""
+    rho32 = f32(rho)
+    # LinearSubproblemSolver.compute_rhs (_admmaux.py:231-255): 2*scale = 1, W = I
+    rhs = np.zeros(x.shape, dtype=f32)
+    rhs = rhs + f32(1.0) * AT(np.asarray(y, dtype=f32))
+    rhs = (rhs + rho32 * finite_difference_adj(z - u)).astype(f32)
+
+    def lhs(v):  # rho * C.gram_op + f.hessian  (_admmaux.py:218-227)
+        return (rho32 * finite_difference_adj(finite_difference(v)) + AT(A(v))).astype(f32)
+
+    x, info = cg(lhs, rhs, x, tol=cg_tol, maxiter=cg_maxiter)
+    Cx = finite_difference(x)
+    z_new = l21_prox(Cx + u, f32(lam) * f32(1.0 / rho))
+    u_new = (u + Cx - z_new).astype(f32)
+    return x, z_new, u_new, info
+
+
+def ladmm_tv_init(x0, A):
+    """``LinearizedADMM.z_init`` / ``u_init`` (``_ladmm.py:216-251``) for C = (A; D)."""
+    x0 = np.asarray(x0, dtype=f32)
+    z0, z1 = A(x0).astype(f32), finite_difference(x0)
+    return x0, (z0, z1), (np.zeros_like(z0), np.zeros_like(z1))
+
+
+def ladmm_tv_step(x, z, u, A, AT, y, lam, mu, nu, nonneg=False):
+    """One linearized-ADMM iteration, C = VerticalStack((A, D)), g = Separable(SquaredL2Loss(y),
+    lam*L21Norm), f = ZeroFunctional or NonNegativeIndicator.  z, u: (sinogram, gradient) pairs."""
+    z0, z1 = z
+    u0, u1 = u
+    c = f32(mu / nu)
+    t0 = A(x) - z0 + u0
+    t1 = finite_difference(x) - z1 + u1
+    proxarg = x - c * (AT(t0.astype(f32)) + finite_difference_adj(t1.astype(f32)))
+    x_new = (np.maximum(proxarg, f32(0)) if nonneg else proxarg).astype(f32)
+    Cx0, Cx1 = A(x_new).astype(f32), finite_difference(x_new)
+    z0n = sql2_prox(Cx0 + u0, y, nu)
+    z1n = l21_prox(Cx1 + u1, f32(lam) * f32(nu))
+    u0n = (u0 + Cx0 - z0n).astype(f32)
+    u1n = (u1 + Cx1 - z1n).astype(f32)
+    return x_new, (z0n, z1n), (u0n, u1n)
+
+
+def padmm_tv_init(x_shape, y_shape):
+    """``ProximalADMMBase.__init__`` defaults (``_padmm.py:106-134``): x, z, u, u_old all zero."""
+    x = np.zeros(x_shape, dtype=f32)
+    z = (np.zeros(y_shape, dtype=f32), np.zeros((len(x_shape),) + tuple(x_shape), dtype=f32))
+    u = (np.zeros_like(z[0]), np.zeros_like(z[1]))
+    return x, z, u, (u[0].copy(), u[1].copy())
+
+
+def padmm_tv_step(x, z, u, u_old, A, AT, y, lam, alpha, rho, mu, nu, nonneg=False):
+    """One proximal-ADMM iteration for A_stack = (A; alpha*D), B = -I, c = 0,
+    g = Separable(SquaredL2Loss(y), (lam/alpha)*L21Norm) (``ct_3d_tv_padmm.py:96-120``)."""
+    al = f32(alpha)
+    inv_mu, inv_nu = f32(1.0 / mu), f32(1.0 / nu)
+    q0 = f32(2.0) * u[0] - u_old[0]
+    q1 = f32(2.0) * u[1] - u_old[1]
+    proxarg = x - inv_mu * (AT(q0.astype(f32)) + al * finite_difference_adj(q1.astype(f32)))
+    x_new = (np.maximum(proxarg, f32(0)) if nonneg else proxarg).astype(f32)
+    Ax0, Ax1 = A(x_new).astype(f32), (al * finite_difference(x_new)).astype(f32)
+    p0 = z[0] + inv_nu * ((Ax0 - z[0]) + u[0])
+    p1 = z[1] + inv_nu * ((Ax1 - z[1]) + u[1])
+    plam = 1.0 / (rho * nu)
+    z0n = sql2_prox(p0.astype(f32), y, plam)
+    z1n = l21_prox(p1.astype(f32), f32(lam / alpha) * f32(plam))
+    u0n = ((u[0] + Ax0) - z0n).astype(f32)
+    u1n = ((u[1] + Ax1) - z1n).astype(f32)
+    return x_new, (z0n, z1n), (u0n, u1n), (u[0], u[1])

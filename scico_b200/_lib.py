@@ -20,6 +20,8 @@ XCT_ERR_CUDA = -2
 XCT_ERR_UNSUPPORTED = -3
 XCT_ERR_NO_DEVICE = -4
 
+SPLIT_ADMM, SPLIT_LADMM, SPLIT_PADMM = 0, 1, 2
+
 FLAG_FORCE_GENERAL = 0x1
 FLAG_NO_WALK = 0x2
 KERNEL_NAMES = {0: "general", 1: "plane", 2: "walk"}
@@ -48,6 +50,14 @@ EXPORTED_SYMBOLS = (
     "xct_l2_dual_step",
     "xct_fd_forward",
     "xct_fd_adjoint",
+    "xct_grad_prox_step",
+    "xct_sino_prox_step",
+    "xct_grad_primal_step",
+    "xct_admm_rhs",
+    "xct_cg_init",
+    "xct_cg_lhs",
+    "xct_cg_update_xr",
+    "xct_cg_update_p",
 )
 
 
@@ -142,6 +152,14 @@ def lib() -> ctypes.CDLL:
     L.xct_l2_dual_step.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, cf, c_void_p]
     L.xct_fd_forward.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p]
     L.xct_fd_adjoint.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p]
+    L.xct_grad_prox_step.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, cf, cf, cf, c_int32, c_void_p]
+    L.xct_sino_prox_step.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, cf, cf, c_int32, c_void_p]
+    L.xct_grad_primal_step.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p, cf, cf, c_int32, c_void_p]
+    L.xct_admm_rhs.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p, cf, c_void_p, c_void_p, c_void_p]
+    L.xct_cg_init.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, cf, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.xct_cg_lhs.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p, cf, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.xct_cg_update_xr.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.xct_cg_update_p.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.xct_launch_count.restype = c_int64
     L.xct_launch_count_reset.restype = None
     _lib = L

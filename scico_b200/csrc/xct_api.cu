@@ -15,6 +15,7 @@
 #include "xct_plane.cuh"
 #include "xct_plane2.cuh"
 #include "xct_tv.cuh"
+#include "xct_solver.cuh"
 
 namespace {
 
@@ -690,6 +691,98 @@ int xct_fd_adjoint(const xct_tv_block* b, const float* z1, const float* lo_halo,
   const size_t n = (size_t)b->n0 * b->n1 * b->n2;
   xct::fd_adjoint_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), z1, lo_halo, out);
   return launch_ok("fd_adjoint_kernel");
+}
+
+// ------------------------------------------------- ADMM / LADMM / PADMM kernels (xct_solver.cuh)
+int xct_grad_prox_step(const xct_tv_block* b, const float* x, const float* hi_halo, float* z1, float* u1, float* w1,
+                       float dscale, float thr, float inv_nu, int32_t mode, void* stream) {
+  int rc = tv_check(b, x, z1);
+  if (rc) return rc;
+  if (!u1 || (mode != XCT_SPLIT_ADMM && !w1)) return fail(XCT_ERR_INVALID, "null argument");
+  if (!(thr >= 0.f)) return fail(XCT_ERR_INVALID, "threshold must be non-negative");
+  const size_t n = (size_t)b->n0 * b->n1 * b->n2;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mode) {
+    case XCT_SPLIT_ADMM:
+      xct::grad_prox_kernel<xct::kSplitAdmm><<<tv_grid(n), 256, 0, st>>>(tv_dims(b), x, hi_halo, z1, u1, w1, dscale, thr, inv_nu);
+      break;
+    case XCT_SPLIT_LADMM:
+      xct::grad_prox_kernel<xct::kSplitLadmm><<<tv_grid(n), 256, 0, st>>>(tv_dims(b), x, hi_halo, z1, u1, w1, dscale, thr, inv_nu);
+      break;
+    case XCT_SPLIT_PADMM:
+      xct::grad_prox_kernel<xct::kSplitPadmm><<<tv_grid(n), 256, 0, st>>>(tv_dims(b), x, hi_halo, z1, u1, w1, dscale, thr, inv_nu);
+      break;
+    default:
+      return fail(XCT_ERR_INVALID, "unknown split mode");
+  }
+  return launch_ok("grad_prox_kernel");
+}
+
+int xct_sino_prox_step(int64_t n, const float* ax, const float* y, float* z0, float* u0, float* w0, float c,
+                       float inv_nu, int32_t mode, void* stream) {
+  if (!ax || !y || !z0 || !u0 || !w0 || n < 1) return fail(XCT_ERR_INVALID, "null argument or empty array");
+  if (!(c > 0.f)) return fail(XCT_ERR_INVALID, "prox parameter must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == XCT_SPLIT_LADMM)
+    xct::sino_prox_kernel<xct::kSplitLadmm><<<tv_grid((size_t)n), 256, 0, st>>>((size_t)n, ax, y, z0, u0, w0, c, inv_nu);
+  else if (mode == XCT_SPLIT_PADMM)
+    xct::sino_prox_kernel<xct::kSplitPadmm><<<tv_grid((size_t)n), 256, 0, st>>>((size_t)n, ax, y, z0, u0, w0, c, inv_nu);
+  else
+    return fail(XCT_ERR_INVALID, "unknown split mode");
+  return launch_ok("sino_prox_kernel");
+}
+
+int xct_grad_primal_step(const xct_tv_block* b, float* x, const float* atq, const float* w1, const float* lo_halo,
+                         float step, float dscale, int32_t nonneg, void* stream) {
+  int rc = tv_check(b, x, atq);
+  if (rc) return rc;
+  if (!w1) return fail(XCT_ERR_INVALID, "null argument");
+  const size_t n = (size_t)b->n0 * b->n1 * b->n2;
+  xct::grad_primal_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), x, atq, w1, lo_halo, step, dscale, nonneg);
+  return launch_ok("grad_primal_kernel");
+}
+
+int xct_admm_rhs(const xct_tv_block* b, const float* aty, const float* z1, const float* u1, const float* lo_halo,
+                 float rho, float* rhs, double* sumsq, void* stream) {
+  int rc = tv_check(b, aty, rhs);
+  if (rc) return rc;
+  if (!z1 || !u1 || !sumsq) return fail(XCT_ERR_INVALID, "null argument");
+  const size_t n = (size_t)b->n0 * b->n1 * b->n2;
+  xct::admm_rhs_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), aty, z1, u1, lo_halo, rho, rhs, sumsq);
+  return launch_ok("admm_rhs_kernel");
+}
+
+int xct_cg_init(const xct_tv_block* b, const float* x, const float* lo_halo, const float* hi_halo, const float* atax,
+                const float* rhs, float rho, float* r, float* p, double* num, void* stream) {
+  int rc = tv_check(b, x, atax);
+  if (rc) return rc;
+  if (!rhs || !r || !p || !num) return fail(XCT_ERR_INVALID, "null argument");
+  const size_t n = (size_t)b->n0 * b->n1 * b->n2;
+  xct::cg_init_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), x, lo_halo, hi_halo, atax, rhs, rho, r, p, num);
+  return launch_ok("cg_init_kernel");
+}
+
+int xct_cg_lhs(const xct_tv_block* b, const float* p, const float* lo_halo, const float* hi_halo, const float* atap,
+               float rho, float* q, double* pq, double* zero_me, void* stream) {
+  int rc = tv_check(b, p, atap);
+  if (rc) return rc;
+  if (!q || !pq) return fail(XCT_ERR_INVALID, "null argument");
+  const size_t n = (size_t)b->n0 * b->n1 * b->n2;
+  xct::cg_lhs_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), p, lo_halo, hi_halo, atap, rho, q, pq, zero_me);
+  return launch_ok("cg_lhs_kernel");
+}
+
+int xct_cg_update_xr(int64_t n, float* x, float* r, const float* p, const float* q, const double* num, const double* pq,
+                     double* num_new, double* zero_me, void* stream) {
+  if (!x || !r || !p || !q || !num || !pq || !num_new || n < 1) return fail(XCT_ERR_INVALID, "null argument or empty array");
+  xct::cg_xr_kernel<<<tv_grid((size_t)n), 256, 0, (cudaStream_t)stream>>>((size_t)n, x, r, p, q, num, pq, num_new, zero_me);
+  return launch_ok("cg_xr_kernel");
+}
+
+int xct_cg_update_p(int64_t n, float* p, const float* r, const double* num, const double* num_new, void* stream) {
+  if (!p || !r || !num || !num_new || n < 1) return fail(XCT_ERR_INVALID, "null argument or empty array");
+  xct::cg_p_kernel<<<tv_grid((size_t)n), 256, 0, (cudaStream_t)stream>>>((size_t)n, p, r, num, num_new);
+  return launch_ok("cg_p_kernel");
 }
 
 int xct3d_debug_weights(const xct_plan* pl, int32_t view, int32_t* ul, float* w, void* stream) {

@@ -1,4 +1,6 @@
-"""Device-resident TV-regularised PDHG for CT around the projector pair.
+"""Device-resident TV-regularised CT solvers around the projector pair:
+:class:`TVPDHG`, :class:`TVADMM` (ADMM with a CG x-step), :class:`TVLinearizedADMM` and
+:class:`TVProximalADMM`.
 
 :class:`TVPDHG` restates ``scico.optimize.PDHG.step`` (``scico/optimize/_primaldual.py:219-231``) for
 the problem every 3D CT example of the reference sets up,
@@ -16,6 +18,13 @@ host synchronisation happens inside :meth:`step` (the reference syncs once per i
 With a :class:`~scico_b200.sharded.SlabShardedXRayTransform3D` the state is z-slab sharded: the
 projector needs no collective, the finite difference along axis 0 needs a one-plane halo per
 iteration in each direction (``N1*N2*4`` bytes, point-to-point between neighbouring ranks).
+
+The ADMM-family classes restate ``ADMM.step`` + ``LinearSubproblemSolver`` + ``scico.solver.cg``
+(``scico/optimize/_admm.py:334-378``, ``_admmaux.py:206-269``, ``scico/solver.py:367-405``; the
+problem of ``examples/scripts/ct_tv_admm.py``), ``LinearizedADMM.step`` (``_ladmm.py:253-277``) and
+``ProximalADMM.step`` (``_padmm.py:349-363``; the problem of ``examples/scripts/ct_3d_tv_padmm.py``)
+on the same fused kernels (``scico_b200/csrc/xct_solver.cuh``).  2D operators are handled as the
+volume block ``(1, N0, N1)``: the axis-0 component of every gradient-shaped array stays exactly 0.
 """
 from __future__ import annotations
 
@@ -67,48 +76,49 @@ class FiniteDifference:
         return out
 
 
-class TVPDHG:
-    """PDHG for ``1/2||Ax - y||^2 + lam ||Dx||_{2,1}`` with the state on the GPU.
+class _TVSolver:
+    """State and plumbing shared by the TV solvers: operator / sharding bookkeeping, halo exchange of
+    boundary planes between neighbouring z-slabs, operator applications into preallocated buffers,
+    global sums and the TV objective."""
 
-    Args:
-        A: ``XRayTransform3D`` (single GPU) or ``SlabShardedXRayTransform3D`` (one slab per rank).
-        y: measured sinogram, CUDA tensor of ``A``'s (local) output shape.
-        lam: TV weight.  tau, sigma: step sizes (``tau * sigma * ||C||^2 < 1``; see
-            :meth:`estimate_parameters`).  alpha: relaxation (reference default 1.0).
-        nonneg: use ``f = NonNegativeIndicator`` instead of ``ZeroFunctional``.
-        x0: initial volume (default zeros).  maxiter: iterations run by :meth:`solve`.
-        itstat: record objective / residual norms every iteration (host sync, extra forward).
-    """
-
-    def __init__(self, A, y, lam: float, tau: float, sigma: float, alpha: float = 1.0, nonneg: bool = False,
-                 x0=None, maxiter: int = 100, itstat: bool = False):
+    def _setup(self, A, y, x0=None):
         self.A = A
         self.sharded = hasattr(A, "slab")
         self.group = getattr(A, "group", None)
         self.rank = getattr(A, "rank", 0)
         self.world = getattr(A, "world_size", 1)
-        in_shape = A.local_input_shape if self.sharded else A.input_shape
-        out_shape = A.local_output_shape if self.sharded else A.output_shape
-        if tuple(y.shape) != tuple(out_shape) or not y.is_cuda:
-            raise ValueError(f"y must be a CUDA tensor of shape {tuple(out_shape)}")
+        in_shape = tuple(A.local_input_shape if self.sharded else A.input_shape)
+        out_shape = tuple(A.local_output_shape if self.sharded else A.output_shape)
+        if len(in_shape) not in (2, 3):
+            raise ValueError(f"operator input must be 2D or 3D, got shape {in_shape}")
+        if tuple(y.shape) != out_shape or not y.is_cuda:
+            raise ValueError(f"y must be a CUDA tensor of shape {out_shape}")
+        self.in_shape, self.out_shape = in_shape, out_shape
+        self.vol_shape = in_shape if len(in_shape) == 3 else (1,) + in_shape  # 2D image = one slice
         self.dev = y.device
         self.y = y.to(torch.float32).contiguous()
-        self.lam, self.tau, self.sigma, self.alpha = float(lam), float(tau), float(sigma), float(alpha)
-        self.nonneg = bool(nonneg)
-        self.maxiter = int(maxiter)
-        self.itstat = bool(itstat)
-        self.blk = _lib.TvBlock(*in_shape, int(self.rank == 0), int(self.rank == self.world - 1))
-        self.x = torch.zeros(in_shape, dtype=torch.float32, device=self.dev) if x0 is None \
-            else x0.to(torch.float32).clone().contiguous()
-        self.xbar = self.x.clone()
-        self.z0 = torch.zeros(out_shape, dtype=torch.float32, device=self.dev)
-        self.z1 = torch.zeros((3,) + tuple(in_shape), dtype=torch.float32, device=self.dev)
-        self.atz = torch.empty(in_shape, dtype=torch.float32, device=self.dev)
-        self.ax = torch.empty(out_shape, dtype=torch.float32, device=self.dev)
-        self.x_old = None
+        self.blk = _lib.TvBlock(*self.vol_shape, int(self.rank == 0), int(self.rank == self.world - 1))
+        if x0 is None:
+            self.x = torch.zeros(in_shape, dtype=torch.float32, device=self.dev)
+        else:
+            if tuple(x0.shape) != in_shape:
+                raise ValueError(f"x0 must have shape {in_shape}")
+            self.x = x0.to(device=self.dev, dtype=torch.float32).clone().contiguous()
         self.itnum = 0
         self.history = []
-        self._dx2 = None
+
+    def _vol(self):
+        return torch.empty(self.in_shape, dtype=torch.float32, device=self.dev)
+
+    def _sino(self, zero=False):
+        return (torch.zeros if zero else torch.empty)(self.out_shape, dtype=torch.float32, device=self.dev)
+
+    def _grad(self):
+        return torch.zeros((3,) + self.vol_shape, dtype=torch.float32, device=self.dev)
+
+    def _grad_view(self, g):
+        """Gradient-shaped state in the reference's shape: (3, N0, N1, N2) or (2, N0, N1)."""
+        return g if len(self.in_shape) == 3 else g[1:, 0]
 
     # -- halo exchange (z-slab sharding only) ---------------------------------------------------
     def _neighbour(self, r):
@@ -141,38 +151,24 @@ class TVPDHG:
             req.wait()
         return recv
 
+    def _lo_plane(self, g):
+        """Halo for ``D^T g``: plane ``g[0][-1]`` of the previous slab."""
+        return None if self.world == 1 else self._halo_from_prev(g[0, -1].contiguous())
+
+    def _hi_plane(self, v):
+        """Halo for ``D v``: plane ``v[0]`` of the next slab."""
+        return None if self.world == 1 else self._halo_from_next(v[0].contiguous())
+
+    @staticmethod
+    def _ptr(t):
+        return t.data_ptr() if t is not None else None
+
     # -- operator applications -------------------------------------------------------------------
     def _fwd(self, x, out):
         return self.A.project(x) if self.sharded else self.A.project(x, out=out)
 
     def _adj(self, y, out):
         return self.A.back_project(y) if self.sharded else self.A.back_project(y, out=out)
-
-    def step(self):
-        """One PDHG iteration (``_primaldual.py:219-231``)."""
-        L = _lib.lib()
-        if self.itstat:
-            self.x_old = self.x.clone()
-            z0_old, z1_old = self.z0.clone(), self.z1.clone()
-        with torch.cuda.device(self.dev):
-            st = _stream(self.dev)
-            self.atz = self._adj(self.z0, self.atz)                       # A^T z0
-            lo = self._halo_from_prev(self.z1[0, -1].contiguous())        # z1[0][-1] of the previous slab
-            _lib.check(L.xct_tv_primal_step(ctypes.byref(self.blk), self.x.data_ptr(), self.xbar.data_ptr(),
-                                            self.atz.data_ptr(), self.z1.data_ptr(),
-                                            lo.data_ptr() if lo is not None else None,
-                                            self.tau, self.alpha, int(self.nonneg), st))
-            self.ax = self._fwd(self.xbar, self.ax)                       # A xbar
-            hi = self._halo_from_next(self.xbar[0].contiguous())          # xbar[n0] of the next slab
-            _lib.check(L.xct_tv_dual_step(ctypes.byref(self.blk), self.z1.data_ptr(), self.xbar.data_ptr(),
-                                          hi.data_ptr() if hi is not None else None, self.sigma, self.lam, st))
-            _lib.check(L.xct_l2_dual_step(self.z0.numel(), self.z0.data_ptr(), self.ax.data_ptr(),
-                                          self.y.data_ptr(), self.sigma, st))
-        self.itnum += 1
-        if self.itstat:
-            pr = self._norm(self.x - self.x_old) / self.tau
-            du = math.sqrt(self._norm(self.z0 - z0_old) ** 2 + self._norm(self.z1 - z1_old) ** 2) / self.sigma
-            self.history.append({"iter": self.itnum, "objective": self.objective(), "prml_rsdl": pr, "dual_rsdl": du})
 
     def solve(self, callback=None):
         for _ in range(self.maxiter):
@@ -188,57 +184,332 @@ class TVPDHG:
             dist.all_reduce(s, group=self.group)
         return float(s.item())
 
-    def _norm(self, t) -> float:
-        if self.sharded and t.shape == self.z0.shape:  # count shared detector rows once
+    def _owned(self, t):
+        """Sinogram-shaped array restricted to the detector rows this rank owns (shared rows are
+        counted once in global sums)."""
+        if self.sharded and tuple(t.shape) == self.out_shape:
             lo, hi = self.A.owned_rows
-            t = t[:, lo - self.A.rows[0]: hi - self.A.rows[0]]
-        return math.sqrt(self._sum(t.double() ** 2))
+            return t[:, lo - self.A.rows[0]: hi - self.A.rows[0]]
+        return t
+
+    def _norm(self, t) -> float:
+        return math.sqrt(self._sum(self._owned(t).double() ** 2))
+
+    def _fd(self):
+        return FiniteDifference(self.vol_shape, self.rank == 0, self.rank == self.world - 1)
+
+    def _l21(self, g) -> float:
+        return self._sum(torch.sqrt((g.double() ** 2).sum(dim=0)))
 
     def objective(self, x=None) -> float:
-        """``f(x) + g(Cx)`` = ``1/2||Ax - y||^2 + lam ||Dx||_{2,1}`` (``_primaldual.py:172-189``)."""
+        """``1/2||Ax - y||^2 + lam ||Dx||_{2,1}`` at ``x`` (default: the current iterate)."""
         x = self.x if x is None else x
-        r = (self.A.project(x) - self.y)
-        if self.sharded:
-            lo, hi = self.A.owned_rows
-            r = r[:, lo - self.A.rows[0]: hi - self.A.rows[0]]
-        hi_h = self._halo_from_next(x[0].contiguous())
-        d = FiniteDifference(x.shape, self.rank == 0, self.rank == self.world - 1)(x, hi_h)
-        return 0.5 * self._sum(r.double() ** 2) + self.lam * self._sum(torch.sqrt((d.double() ** 2).sum(dim=0)))
+        r = self._owned(self.A.project(x) - self.y)
+        xv = x.reshape(self.vol_shape)
+        d = self._fd()(xv, self._hi_plane(xv))
+        return 0.5 * self._sum(r.double() ** 2) + self.lam * self._l21(d)
+
+    @staticmethod
+    def operator_norm_sq(A, dscale: float = 1.0, maxiter: int = 20, seed: int = 0) -> float:
+        """``|| (A; dscale*D) ||_2^2`` by power iteration of ``A^T A + dscale^2 D^T D`` on the device
+        (``scico/linop/_util.py:27-110``; the reference runs 100 iterations by default)."""
+        h = _TVSolver()
+        sharded = hasattr(A, "slab")
+        shape = tuple(A.local_input_shape if sharded else A.input_shape)
+        vshape = shape if len(shape) == 3 else (1,) + shape
+        h.world, h.rank, h.group = getattr(A, "world_size", 1), getattr(A, "rank", 0), getattr(A, "group", None)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        g = torch.Generator(device=dev).manual_seed(seed + h.rank)
+        v = torch.randn(shape, device=dev, generator=g)
+        D = FiniteDifference(vshape, h.rank == 0, h.rank == h.world - 1)
+        mu = 1.0
+        for _ in range(maxiter):
+            v = v / math.sqrt(h._sum(v * v))
+            vv = v.reshape(vshape)
+            dz = D(vv, h._hi_plane(vv))
+            w = A.back_project(A.project(v)) + (dscale * dscale) * D.adj(dz, h._lo_plane(dz)).reshape(shape)
+            mu = h._sum(v * w)
+            v = w
+        return mu
+
+
+class TVPDHG(_TVSolver):
+    """PDHG for ``1/2||Ax - y||^2 + lam ||Dx||_{2,1}`` with the state on the GPU.
+
+    Args:
+        A: ``XRayTransform3D`` / ``XRayTransform2D`` (single GPU) or ``SlabShardedXRayTransform3D``
+            (one slab per rank).
+        y: measured sinogram, CUDA tensor of ``A``'s (local) output shape.
+        lam: TV weight.  tau, sigma: step sizes (``tau * sigma * ||C||^2 < 1``; see
+            :meth:`estimate_parameters`).  alpha: relaxation (reference default 1.0).
+        nonneg: use ``f = NonNegativeIndicator`` instead of ``ZeroFunctional``.
+        x0: initial volume (default zeros).  maxiter: iterations run by :meth:`solve`.
+        itstat: record objective / residual norms every iteration (host sync, extra forward).
+    """
+
+    def __init__(self, A, y, lam: float, tau: float, sigma: float, alpha: float = 1.0, nonneg: bool = False,
+                 x0=None, maxiter: int = 100, itstat: bool = False):
+        self._setup(A, y, x0)
+        self.lam, self.tau, self.sigma, self.alpha = float(lam), float(tau), float(sigma), float(alpha)
+        self.nonneg = bool(nonneg)
+        self.maxiter = int(maxiter)
+        self.itstat = bool(itstat)
+        self.xbar = self.x.clone()
+        self.z0 = self._sino(zero=True)
+        self.z1 = self._grad()
+        self.atz = self._vol()
+        self.ax = self._sino()
+        self.x_old = None
+
+    def step(self):
+        """One PDHG iteration (``_primaldual.py:219-231``)."""
+        L = _lib.lib()
+        if self.itstat:
+            self.x_old = self.x.clone()
+            z0_old, z1_old = self.z0.clone(), self.z1.clone()
+        with torch.cuda.device(self.dev):
+            st = _stream(self.dev)
+            self.atz = self._adj(self.z0, self.atz)                       # A^T z0
+            lo = self._lo_plane(self.z1)                                  # z1[0][-1] of the previous slab
+            _lib.check(L.xct_tv_primal_step(ctypes.byref(self.blk), self.x.data_ptr(), self.xbar.data_ptr(),
+                                            self.atz.data_ptr(), self.z1.data_ptr(), self._ptr(lo),
+                                            self.tau, self.alpha, int(self.nonneg), st))
+            self.ax = self._fwd(self.xbar, self.ax)                       # A xbar
+            hi = self._hi_plane(self.xbar.reshape(self.vol_shape))        # xbar[n0] of the next slab
+            _lib.check(L.xct_tv_dual_step(ctypes.byref(self.blk), self.z1.data_ptr(), self.xbar.data_ptr(),
+                                          self._ptr(hi), self.sigma, self.lam, st))
+            _lib.check(L.xct_l2_dual_step(self.z0.numel(), self.z0.data_ptr(), self.ax.data_ptr(),
+                                          self.y.data_ptr(), self.sigma, st))
+        self.itnum += 1
+        if self.itstat:
+            pr = self._norm(self.x - self.x_old) / self.tau
+            du = math.sqrt(self._norm(self.z0 - z0_old) ** 2 + self._norm(self.z1 - z1_old) ** 2) / self.sigma
+            self.history.append({"iter": self.itnum, "objective": self.objective(), "prml_rsdl": pr, "dual_rsdl": du})
 
     @staticmethod
     def estimate_parameters(A, ratio: float = 1.0, factor: Optional[float] = 1.01, maxiter: int = 20, seed: int = 0):
         """(tau, sigma) from ``||C||_2`` by power iteration of ``C^T C = A^T A + D^T D`` on the device
         (``_primaldual.py:234-288``, ``scico/linop/_util.py:27-110``; the reference runs 100
         iterations, 20 are enough for the 1 % safety factor)."""
-        sharded = hasattr(A, "slab")
-        shape = A.local_input_shape if sharded else A.input_shape
-        rank, world = getattr(A, "rank", 0), getattr(A, "world_size", 1)
-        group = getattr(A, "group", None)
-        dev = torch.device("cuda", torch.cuda.current_device())
-        g = torch.Generator(device=dev).manual_seed(seed + rank)
-        v = torch.randn(shape, device=dev, generator=g)
-        D = FiniteDifference(shape, rank == 0, rank == world - 1)
-        helper = TVPDHG.__new__(TVPDHG)
-        helper.world, helper.rank, helper.group = world, rank, group
-
-        def gsum(t):
-            s = t.double().sum()
-            if world > 1:
-                dist.all_reduce(s, group=group)
-            return float(s.item())
-
+        cnorm = math.sqrt(_TVSolver.operator_norm_sq(A, 1.0, maxiter, seed))
         factor = 1.0 if factor is None else factor
-        mu = 1.0
-        for _ in range(maxiter):
-            v = v / math.sqrt(gsum(v * v))
-            hi = helper._halo_from_next(v[0].contiguous())
-            dz = D(v, hi)
-            lo = helper._halo_from_prev(dz[0, -1].contiguous())
-            w = A.back_project(A.project(v)) + D.adj(dz, lo)
-            mu = gsum(v * w)
-            v = w
-        cnorm = math.sqrt(mu)
         # reference formula (_primaldual.py:286-288); note that factor > 1 loosens tau*sigma*||C||^2 < 1,
         # pass factor < 1 for a strict bound
         tau = math.sqrt(factor / ratio) / cnorm
         return tau, ratio * tau
+
+
+class TVADMM(_TVSolver):
+    """ADMM with a conjugate-gradient x-step for ``1/2||Ax - y||^2 + lam ||Dx||_{2,1}``
+    (``examples/scripts/ct_tv_admm.py:68-84``: ``f = SquaredL2Loss(y, A)``, ``g_list = [lam*L21Norm()]``,
+    ``C_list = [FiniteDifference(append=0)]``, ``rho_list = [rho]``, ``LinearSubproblemSolver``).
+
+    x-step: CG on ``(A^T A + rho D^T D) x = A^T y + rho D^T (z - u)`` started from the current ``x``
+    (``_admmaux.py:231-269``, ``scico/solver.py:367-405``); ``A^T y`` is computed once (the reference
+    recomputes it every iteration, ``_admmaux.py:246-248``).  One CG iteration is one forward + one back
+    projection and three fused kernels; ``alpha``/``beta`` stay on the device, the host reads back only
+    the squared residual norm that decides termination (the reference's ``while`` test does the same).
+
+    Args:
+        A, y, lam, x0, maxiter, itstat: as :class:`TVPDHG` (``x0`` e.g. ``clip(A.fbp(y), 0, 1)``).
+        rho: ADMM penalty parameter.  cg_tol, cg_maxiter: ``cg_kwargs`` of the reference
+            (defaults of ``LinearSubproblemSolver``: 1e-4, 100).
+    """
+
+    def __init__(self, A, y, lam: float, rho: float, x0=None, maxiter: int = 100, cg_tol: float = 1e-4,
+                 cg_maxiter: int = 100, itstat: bool = False):
+        self._setup(A, y, x0)
+        self.lam, self.rho = float(lam), float(rho)
+        self.maxiter, self.cg_tol, self.cg_maxiter = int(maxiter), float(cg_tol), int(cg_maxiter)
+        self.itstat = bool(itstat)
+        xv = self.x.reshape(self.vol_shape)
+        self.z1 = self._fd()(xv, self._hi_plane(xv))  # z_init: z = C x0 (_admm.py:297-316)
+        self.u1 = self._grad()                        # u_init: zeros (_admm.py:318-332)
+        self.aty = self.A.back_project(self.y).contiguous()
+        self.rhs, self.r, self.p, self.q, self.atq = (self._vol() for _ in range(5))
+        self.ax = self._sino()
+        self.scal = torch.zeros(8, dtype=torch.float64, device=self.dev)  # CG inner products (device)
+        self.cg_info = {"num_iter": 0, "rel_res": 0.0}
+        self.cg_iters_total = 0
+
+    def _allreduce(self, i):
+        if self.world > 1:
+            dist.all_reduce(self.scal[i:i + 1], group=self.group)
+
+    def _halos(self, v):
+        """(lo, hi) halo planes of ``v`` for ``D^T D v``: ``v[-1]`` of the previous, ``v[0]`` of the next slab."""
+        if self.world == 1:
+            return None, None
+        vv = v.reshape(self.vol_shape)
+        return self._halo_from_prev(vv[-1].contiguous()), self._halo_from_next(vv[0].contiguous())
+
+    def _xstep(self):
+        L, blk, st, n = _lib.lib(), ctypes.byref(self.blk), _stream(self.dev), self.x.numel()
+        sc = self.scal
+        sp = lambda i: sc.data_ptr() + 8 * i  # noqa: E731  (slots 0-2: r.r ring, 3-4: p.q ring, 5: ||b||^2)
+        sc.zero_()
+        zu_lo = None if self.world == 1 else self._halo_from_prev((self.z1[0, -1] - self.u1[0, -1]).contiguous())
+        _lib.check(L.xct_admm_rhs(blk, self.aty.data_ptr(), self.z1.data_ptr(), self.u1.data_ptr(), self._ptr(zu_lo),
+                                  self.rho, self.rhs.data_ptr(), sp(5), st))
+        self.ax = self._fwd(self.x, self.ax)
+        self.atq = self._adj(self.ax, self.atq)
+        lo, hi = self._halos(self.x)
+        _lib.check(L.xct_cg_init(blk, self.x.data_ptr(), self._ptr(lo), self._ptr(hi), self.atq.data_ptr(),
+                                 self.rhs.data_ptr(), self.rho, self.r.data_ptr(), self.p.data_ptr(), sp(0), st))
+        self._allreduce(0)
+        self._allreduce(5)
+        host = sc.cpu()
+        num, bn2 = float(host[0]), float(host[5])
+        tol_sq = (self.cg_tol ** 2) * bn2
+        k = 0
+        while k < self.cg_maxiter and num > tol_sq:
+            cur, nxt, pq, pq_nxt = k % 3, (k + 1) % 3, 3 + k % 2, 3 + (k + 1) % 2
+            self.ax = self._fwd(self.p, self.ax)
+            self.atq = self._adj(self.ax, self.atq)
+            lo, hi = self._halos(self.p)
+            _lib.check(L.xct_cg_lhs(blk, self.p.data_ptr(), self._ptr(lo), self._ptr(hi), self.atq.data_ptr(),
+                                    self.rho, self.q.data_ptr(), sp(pq), sp(nxt), st))
+            self._allreduce(pq)
+            _lib.check(L.xct_cg_update_xr(n, self.x.data_ptr(), self.r.data_ptr(), self.p.data_ptr(), self.q.data_ptr(),
+                                          sp(cur), sp(pq), sp(nxt), sp(pq_nxt), st))
+            self._allreduce(nxt)
+            _lib.check(L.xct_cg_update_p(n, self.p.data_ptr(), self.r.data_ptr(), sp(cur), sp(nxt), st))
+            num = float(sc[nxt].item())
+            k += 1
+        self.cg_info = {"num_iter": k, "rel_res": math.sqrt(num / bn2) if bn2 > 0 else 0.0}
+        self.cg_iters_total += k
+
+    def step(self):
+        """One ADMM iteration (``_admm.py:334-378`` with ``alpha = 1``)."""
+        if self.itstat:
+            z_old = self.z1.clone()
+        with torch.cuda.device(self.dev):
+            self._xstep()
+            xv = self.x.reshape(self.vol_shape)
+            hi = self._hi_plane(xv)
+            _lib.check(_lib.lib().xct_grad_prox_step(ctypes.byref(self.blk), self.x.data_ptr(), self._ptr(hi),
+                                                     self.z1.data_ptr(), self.u1.data_ptr(), None, 1.0,
+                                                     self.lam / self.rho, 1.0, _lib.SPLIT_ADMM, _stream(self.dev)))
+        self.itnum += 1
+        if self.itstat:
+            D = self._fd()
+            xv = self.x.reshape(self.vol_shape)
+            pr = math.sqrt(self.rho) * self._norm(D(xv, self._hi_plane(xv)) - self.z1)  # _admm.py:253-277
+            dz = self.z1 - z_old
+            du = self.rho * self._norm(D.adj(dz, self._lo_plane(dz)))                     # _admm.py:279-295
+            r = self._owned(self.A.project(self.x) - self.y)
+            obj = 0.5 * self._sum(r.double() ** 2) + self.lam * self._l21(self.z1)        # f(x) + g(z), _admm.py:215-251
+            self.history.append({"iter": self.itnum, "objective": obj, "prml_rsdl": pr, "dual_rsdl": du,
+                                 "cg_iters": self.cg_info["num_iter"], "cg_rel_res": self.cg_info["rel_res"]})
+
+    @property
+    def z(self):
+        return self._grad_view(self.z1)
+
+    @property
+    def u(self):
+        return self._grad_view(self.u1)
+
+
+class _TVSplitSolver(_TVSolver):
+    """Shared by :class:`TVLinearizedADMM` and :class:`TVProximalADMM`: the split variable is the pair
+    (sinogram block, gradient block) of ``(A; dscale*D) x``; ``w0`` / ``w1`` hold the array the next
+    x-step applies the adjoint to.  One iteration = one back projection, one forward projection and
+    three fused kernels, no host synchronisation."""
+
+    def _alloc(self):
+        self.z0, self.u0, self.w0 = (self._sino(zero=True) for _ in range(3))
+        self.z1, self.u1, self.w1 = (self._grad() for _ in range(3))
+        self.atq, self.ax = self._vol(), self._sino()
+
+    def _iterate(self, mode, step, dscale, thr, c, inv_nu):
+        L, blk = _lib.lib(), ctypes.byref(self.blk)
+        if self.itstat:
+            z_old = (self.z0.clone(), self.z1.clone())
+        with torch.cuda.device(self.dev):
+            st = _stream(self.dev)
+            self.atq = self._adj(self.w0, self.atq)
+            lo = self._lo_plane(self.w1)
+            _lib.check(L.xct_grad_primal_step(blk, self.x.data_ptr(), self.atq.data_ptr(), self.w1.data_ptr(),
+                                              self._ptr(lo), step, dscale, int(self.nonneg), st))
+            self.ax = self._fwd(self.x, self.ax)
+            hi = self._hi_plane(self.x.reshape(self.vol_shape))
+            _lib.check(L.xct_grad_prox_step(blk, self.x.data_ptr(), self._ptr(hi), self.z1.data_ptr(), self.u1.data_ptr(),
+                                            self.w1.data_ptr(), dscale, thr, inv_nu, mode, st))
+            _lib.check(L.xct_sino_prox_step(self.z0.numel(), self.ax.data_ptr(), self.y.data_ptr(), self.z0.data_ptr(),
+                                            self.u0.data_ptr(), self.w0.data_ptr(), c, inv_nu, mode, st))
+        self.itnum += 1
+        if self.itstat:
+            self._stats(z_old, dscale)
+
+    def _stats(self, z_old, dscale):
+        D = self._fd()
+        xv = self.x.reshape(self.vol_shape)
+        pr = math.sqrt(self._norm(self.ax - self.z0) ** 2
+                       + self._norm(dscale * D(xv, self._hi_plane(xv)) - self.z1) ** 2)
+        dz0, dz1 = self.z0 - z_old[0], self.z1 - z_old[1]
+        du = self._norm(self.A.back_project(dz0).reshape(self.vol_shape) + dscale * D.adj(dz1, self._lo_plane(dz1)))
+        r = self._owned(self.z0 - self.y)
+        obj = 0.5 * self._sum(r.double() ** 2) + (self.lam / dscale) * self._l21(self.z1)  # f(x) + g(z)
+        self.history.append({"iter": self.itnum, "objective": obj, "prml_rsdl": pr, "dual_rsdl": du})
+
+    @property
+    def z(self):
+        return self.z0, self._grad_view(self.z1)
+
+    @property
+    def u(self):
+        return self.u0, self._grad_view(self.u1)
+
+
+class TVLinearizedADMM(_TVSplitSolver):
+    """Linearized ADMM (``scico/optimize/_ladmm.py:253-277``) for ``C = VerticalStack((A, D))``,
+    ``g = Separable(SquaredL2Loss(y), lam*L21Norm())``, ``f = ZeroFunctional`` or ``NonNegativeIndicator``.
+    ``mu / nu`` must be below ``1 / ||C||^2`` (see :meth:`estimate_parameters`).  ``C x`` of the previous
+    iteration is reused, so one iteration is one forward and one back projection (the reference applies
+    ``C`` twice)."""
+
+    def __init__(self, A, y, lam: float, mu: float, nu: float, x0=None, nonneg: bool = False, maxiter: int = 100,
+                 itstat: bool = False):
+        self._setup(A, y, x0)
+        self.lam, self.mu, self.nu = float(lam), float(mu), float(nu)
+        self.nonneg, self.maxiter, self.itstat = bool(nonneg), int(maxiter), bool(itstat)
+        self._alloc()
+        # z_init: z = C x0, u = 0 (_ladmm.py:216-251)  =>  w = (C x0 - z) + u = 0 exactly
+        self.z0.copy_(self.A.project(self.x))
+        xv = self.x.reshape(self.vol_shape)
+        self.z1.copy_(self._fd()(xv, self._hi_plane(xv)))
+
+    def step(self):
+        self._iterate(_lib.SPLIT_LADMM, self.mu / self.nu, 1.0, self.lam * self.nu, self.nu, 1.0)
+
+    @staticmethod
+    def estimate_parameters(A, nu: float = 1.0, factor: float = 1.01, maxiter: int = 20, seed: int = 0):
+        """(mu, nu) with ``mu = nu / (factor ||C||^2)``."""
+        return nu / (factor * _TVSolver.operator_norm_sq(A, 1.0, maxiter, seed)), nu
+
+
+class TVProximalADMM(_TVSplitSolver):
+    """Proximal ADMM (``scico/optimize/_padmm.py:349-363``) for the splitting of
+    ``examples/scripts/ct_3d_tv_padmm.py:96-120``: ``A_stack = VerticalStack((A, alpha*D))``, ``B = -I``,
+    ``c = 0``, ``f = ZeroFunctional`` (or ``NonNegativeIndicator``),
+    ``g = Separable(SquaredL2Loss(y), (lam/alpha)*L21Norm())``; ``x, z, u`` start at zero unless ``x0``
+    is given (``_padmm.py:106-118``)."""
+
+    def __init__(self, A, y, lam: float, rho: float, mu: float, nu: float, alpha: float = 1.0, x0=None,
+                 nonneg: bool = False, maxiter: int = 100, itstat: bool = False):
+        self._setup(A, y, x0)
+        self.lam, self.rho, self.mu, self.nu, self.alpha = float(lam), float(rho), float(mu), float(nu), float(alpha)
+        self.nonneg, self.maxiter, self.itstat = bool(nonneg), int(maxiter), bool(itstat)
+        self._alloc()
+
+    def step(self):
+        plam = 1.0 / (self.rho * self.nu)
+        self._iterate(_lib.SPLIT_PADMM, 1.0 / self.mu, self.alpha, (self.lam / self.alpha) * plam, plam, 1.0 / self.nu)
+
+    @staticmethod
+    def estimate_parameters(A, alpha: float = 1.0, factor: Optional[float] = 1.01, maxiter: int = 20, seed: int = 0):
+        """(mu, nu) = factor * (``||(A; alpha D)||^2``, ``||-I||^2 = 1``) (``_padmm.py:365-412``)."""
+        mu = _TVSolver.operator_norm_sq(A, alpha, maxiter, seed)
+        f = 1.0 if factor is None else factor
+        return f * mu, f * 1.0

@@ -95,12 +95,40 @@ def _worker(rank, world, port, case):
             rel = (torch.linalg.vector_norm(S.x - ref.x[z0:z1]) / torch.linalg.vector_norm(ref.x[z0:z1])).item()
             assert rel <= 1e-5, rel
             assert abs(S.objective() - ref.objective()) <= 1e-5 * ref.objective()
+        elif case in ("admm_slab", "ladmm_slab", "padmm_slab"):
+            from scico_b200.optimize import TVADMM, TVLinearizedADMM, TVProximalADMM
+
+            N, D, V = (16, 24, 20), (16, 32), 10
+            M = sb.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, V, endpoint=False)[:, None])
+            x_gt = np.zeros(N, np.float32)
+            x_gt[3:13, 6:16, 5:14] = 1.0
+            full = sb.XRayTransform3D(N, M, D)
+            y = full(torch.as_tensor(x_gt, device=dev)) + 0.05 * torch.randn((V,) + D, device=dev,
+                                                                              generator=torch.Generator(device=dev).manual_seed(1))
+            dist.broadcast(y, src=0)
+            op = sharded.SlabShardedXRayTransform3D(N, M, D)
+            (z0, z1), (r0, r1) = op.slab, op.rows
+            yl = y[:, r0:r1].contiguous()
+            if case == "admm_slab":
+                mk = lambda A, yy: TVADMM(A, yy, 0.5, 5.0, maxiter=5, cg_tol=1e-30, cg_maxiter=6)  # noqa: E731
+            elif case == "ladmm_slab":
+                mk = lambda A, yy: TVLinearizedADMM(A, yy, 0.1, 1.0 / 130.0, 1.0, maxiter=20)  # noqa: E731
+            else:
+                mk = lambda A, yy: TVProximalADMM(A, yy, 0.1, 0.05, 400.0, 1.01, alpha=4.0, maxiter=20, itstat=True)  # noqa: E731
+            ref, S = mk(full, y), mk(op, yl)
+            ref.solve()
+            S.solve()
+            rel = (torch.linalg.vector_norm(S.x - ref.x[z0:z1]) / torch.linalg.vector_norm(ref.x[z0:z1])).item()
+            assert rel <= 1e-5, rel
+            if case == "padmm_slab":
+                assert abs(S.history[-1]["objective"] - ref.history[-1]["objective"]) <= 1e-5 * ref.history[-1]["objective"]
+                assert abs(S.history[-1]["prml_rsdl"] - ref.history[-1]["prml_rsdl"]) <= 1e-4 * ref.history[-1]["prml_rsdl"]
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["slab", "slab_halo", "view3d", "view2d", "pdhg_slab"])
+@pytest.mark.parametrize("case", ["slab", "slab_halo", "view3d", "view2d", "pdhg_slab", "admm_slab", "ladmm_slab", "padmm_slab"])
 def test_sharded_operators_nccl(case):
     import torch
     import torch.multiprocessing as mp
