@@ -59,6 +59,7 @@ typedef enum xct_status {
 /* plan_create flags */
 #define XCT_FLAG_FORCE_GENERAL 0x1u /* skip the separable fast path (testing / comparison) */
 #define XCT_FLAG_NO_WALK 0x2u       /* keep the first-generation plane kernels (testing / comparison) */
+#define XCT_FLAG_NO_HOST_PIPELINE 0x4u /* xct_*_host: one H2D, kernels, one D2H (testing / comparison) */
 
 /* kernel families a plan can resolve to (xct_plan_info.path) */
 #define XCT_PATH_2D_PLANE 1   /* 2D, warp-autonomous plane kernels */
@@ -129,7 +130,9 @@ XCT_API int xct_adjoint(const xct_plan *plan, const float *in_dev, float *out_de
 
 /* Same two operators for HOST buffers: H2D copy, kernel(s), D2H copy, synchronous on return.
  * Device staging buffers are cached inside the plan (these two calls are therefore NOT
- * re-entrant on one plan). */
+ * re-entrant on one plan).  3D separable plans on the walk kernels cut the volume into chunks of
+ * slices and overlap the H2D copy of chunk k+1 and the D2H copy of chunk k-1 with the kernels of
+ * chunk k (page-locked host buffers are needed for the overlap; pageable ones still work). */
 XCT_API int xct_forward_host(xct_plan *plan, const float *in_host, float *out_host, int32_t batch);
 XCT_API int xct_adjoint_host(xct_plan *plan, const float *in_host, float *out_host, int32_t batch);
 

@@ -81,6 +81,12 @@ struct xct_plan {
   float* stage_out = nullptr;
   size_t cap_in = 0, cap_out = 0;
   cudaStream_t hstream = nullptr;
+  // pipelined host path (3D separable, unit rows monotone in the slice index): H2D of slice chunk
+  // k+1 and D2H of chunk k-1 overlap the kernels of chunk k
+  bool pipe_ok = false;
+  std::vector<int> h_row_lo, h_row_hi;  // per slice: smallest / largest local detector row over views (-1: none)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> events;
 };
 
 namespace {
@@ -227,12 +233,18 @@ int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* 
 }
 
 // walk adjoint (3D separable geometry with unit rows; `in` must be 16-byte aligned)
-int launch_walk_adjoint(const xct_plan* pl, const float* in, float* out, cudaStream_t st) {
+// Slices [s_begin, s_begin + s_count) of the plan only (s_count < 0: all); `out` is the full volume.
+int launch_walk_adjoint(const xct_plan* pl, const float* in, float* out, cudaStream_t st, int s_begin = 0,
+                        int s_count = -1) {
   xct::Walk2Params wp{};
   wp.p = plane_params(pl, 1);
   wp.rowoff = pl->d_rowoff;
   wp.out_scale = 2.0f;
+  wp.row_stride = pl->n0;
+  wp.s_base = s_begin;
   xct::PlaneParams& p = wp.p;
+  if (s_count >= 0) p.NS = s_count;
+  out += (size_t)s_begin * pl->n1 * pl->n2;
   p.tilesA = ceil_div(p.NA, kWAdjTA);
   p.tilesB = ceil_div(p.NB, 32);
   const long long tasks = (long long)ceil_div(p.NS, kWAdjS) * p.tilesA * p.tilesB;
@@ -280,14 +292,19 @@ int launch_plane_forward(const xct_plan* pl, int batch, const float* in, float* 
 
 // walk forward: one launch per (major axis, minor-axis sign) class
 template <class G, bool IS3D, int S, int TN, int GS, bool MAJOR_B, bool MINOR_UP, bool COLD, bool UNIT4>
-int launch_walk_forward_class(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+int launch_walk_forward_class(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st,
+                              int s_begin, int s_count) {
   const int cls = (MAJOR_B ? 2 : 0) + (MINOR_UP ? 1 : 0);
   if (pl->n_list4[cls] == 0) return XCT_OK;
   xct::Walk2Params wp{};
   wp.p = plane_params(pl, batch);
   wp.rowoff = pl->d_rowoff;
   wp.out_scale = 2.0f;
+  wp.row_stride = wp.p.NS;
+  wp.s_base = s_begin;
   xct::PlaneParams& p = wp.p;
+  if (s_count >= 0) p.NS = s_count;
+  in += (size_t)s_begin * p.NA * p.NB;
   p.view_list = pl->d_list4[cls];
   p.n_list = pl->n_list4[cls];
   constexpr int TM = 32 * GS;
@@ -308,22 +325,25 @@ int launch_walk_forward_class(const xct_plan* pl, int batch, const float* in, fl
 }
 
 template <class G, bool IS3D, int S, int TN, bool COLD, bool UNIT4>
-int launch_walk_forward_v(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+int launch_walk_forward_v(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st, int s_begin,
+                          int s_count) {
   int rc;
-  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, true, COLD, UNIT4>(pl, batch, in, out, st))) return rc;
-  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, false, COLD, UNIT4>(pl, batch, in, out, st))) return rc;
-  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, false, true, COLD, UNIT4>(pl, batch, in, out, st))) return rc;
-  return launch_walk_forward_class<G, IS3D, S, TN, 2, false, false, COLD, UNIT4>(pl, batch, in, out, st);
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, true, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, false, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, false, true, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count))) return rc;
+  return launch_walk_forward_class<G, IS3D, S, TN, 2, false, false, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count);
 }
 
 // 3D separable forward.  The vector flush needs unit rows, D1 % 4 == 0 and a 16-byte aligned sinogram.
-int launch_walk_forward3(const xct_plan* pl, const float* in, float* out, cudaStream_t st) {
+// Slices [s_begin, s_begin + s_count) of the plan only (s_count < 0: all); `in` is the full volume.
+int launch_walk_forward3(const xct_plan* pl, const float* in, float* out, cudaStream_t st, int s_begin = 0,
+                         int s_count = -1) {
   const bool unit4 = pl->fwd_unit4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (pl->fwd_cold) {
-    return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, true, false>(pl, 1, in, out, st);
+    return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, true, false>(pl, 1, in, out, st, s_begin, s_count);
   }
-  if (unit4) return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, true>(pl, 1, in, out, st);
-  return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, false>(pl, 1, in, out, st);
+  if (unit4) return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, true>(pl, 1, in, out, st, s_begin, s_count);
+  return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, false>(pl, 1, in, out, st, s_begin, s_count);
 }
 
 xct::Gen3Params gen3_params(const xct_plan* pl) {
@@ -524,6 +544,26 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       pl->row_aligned = aligned;
       pl->rows_unit = unit;
       if (unit) {
+        // per-slice detector row range over the views, and whether rows never decrease with the slice
+        // index (any rotation about axis 0 with a positive axis-0 scale): the host pipeline relies on it
+        pl->h_row_lo.assign(g->n0, -1);
+        pl->h_row_hi.assign(g->n0, -1);
+        bool mono = true;
+        for (int v = 0; v < V; ++v) {
+          long long prev = -1;
+          for (int i = 0; i < g->n0; ++i) {
+            const long long off = rowoff[(size_t)v * g->n0 + i];
+            if (off < 0) continue;
+            const int r = (int)(off / g->d1 - (long long)v * g->d0);
+            if (r < prev) mono = false;
+            prev = r;
+            pl->h_row_lo[i] = pl->h_row_lo[i] < 0 ? r : std::min(pl->h_row_lo[i], r);
+            pl->h_row_hi[i] = std::max(pl->h_row_hi[i], r);
+          }
+        }
+        pl->pipe_ok = mono;
+      }
+      if (unit) {
         e = cudaMalloc(&pl->d_rowoff, sizeof(long long) * rowoff.size());
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_rowoff, rowoff.data(), sizeof(long long) * rowoff.size(), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return cleanup(fail(XCT_ERR_CUDA, std::string("row index upload: ") + cudaGetErrorString(e)));
@@ -541,6 +581,7 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       pl->fwd_unit4 = env.fwd_unit4_ok && unit && (g->d1 % 4 == 0);
       pl->adj_walk = env.adj_ok && env.adj_walk_ok && unit && (g->d1 % 4 == 0) && !(g->flags & XCT_FLAG_NO_WALK);
       pl->gs = env.fwd_ok ? env.gs : 0;
+      pl->pipe_ok = pl->pipe_ok && pl->fwd_walk && pl->adj_walk && !(g->flags & XCT_FLAG_NO_HOST_PIPELINE);
       if (pl->adj_plane && pl->fwd_plane) pl->path = XCT_PATH_3D_SEP;
     }
   }
@@ -561,6 +602,9 @@ void xct_plan_destroy(xct_plan* pl) {
   cudaFree(pl->stage_in);
   cudaFree(pl->stage_out);
   if (pl->hstream) cudaStreamDestroy(pl->hstream);
+  if (pl->s_in) cudaStreamDestroy(pl->s_in);
+  if (pl->s_out) cudaStreamDestroy(pl->s_out);
+  for (cudaEvent_t ev : pl->events) cudaEventDestroy(ev);
   delete pl;
 }
 
@@ -614,10 +658,86 @@ int xct_adjoint(const xct_plan* pl, const float* in, float* out, int32_t batch, 
   return launch_ok("gen2d_adjoint_kernel");
 }
 
+// Pipelined host path for 3D separable plans with unit, monotone rows: the volume is cut into
+// chunks of slices; chunk k's kernels (stream hstream) overlap the H2D copy of chunk k+1 (stream
+// s_in) and the D2H copy of what chunk k-1 completed (stream s_out).  Detector rows of a slice
+// chunk are a row block of every view: strided 2D copies with the view pitch.
+static int run_host_pipelined(xct_plan* pl, const float* in_host, float* out_host, bool forward) {
+  int rc;
+  const size_t n_vol = in_elems(pl), n_sino = out_elems(pl);
+  if ((rc = ensure_stage(pl, forward ? n_vol : n_sino, forward ? n_sino : n_vol))) return rc;
+  if (!pl->s_in) XCT_CUDA(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
+  if (!pl->s_out) XCT_CUDA(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
+  const int NS = pl->n0, D0 = pl->d0, D1 = pl->d1, V = pl->V;
+  int chunk = std::max(32, (NS + 15) / 16);
+  chunk = (chunk + 7) & ~7;  // whole slice groups of both kernels (S = 4 / 8)
+  const int nchunks = ceil_div(NS, chunk);
+  while ((int)pl->events.size() < 2 * nchunks) {
+    cudaEvent_t ev;
+    XCT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    pl->events.push_back(ev);
+  }
+  const size_t slice = (size_t)pl->n1 * pl->n2;
+  const size_t vpitch = (size_t)D0 * D1 * sizeof(float);  // bytes between the same row of two views
+  float* vol_dev = forward ? pl->stage_in : pl->stage_out;
+  float* sino_dev = forward ? pl->stage_out : pl->stage_in;
+  auto rows_copy = [&](int r0, int r1, bool to_device, cudaStream_t st) -> cudaError_t {
+    if (r1 <= r0) return cudaSuccess;
+    const size_t off = (size_t)r0 * D1;
+    const size_t width = (size_t)(r1 - r0) * D1 * sizeof(float);
+    if (to_device)
+      return cudaMemcpy2DAsync(sino_dev + off, vpitch, in_host + off, vpitch, width, V, cudaMemcpyHostToDevice, st);
+    return cudaMemcpy2DAsync(out_host + off, vpitch, sino_dev + off, vpitch, width, V, cudaMemcpyDeviceToHost, st);
+  };
+  if (forward) {
+    XCT_CUDA(cudaMemsetAsync(sino_dev, 0, n_sino * sizeof(float), pl->hstream));
+    // first row any slice >= i touches (rows never decrease with the slice index)
+    std::vector<int> first_from(NS + 1, D0);
+    for (int i = NS - 1; i >= 0; --i) first_from[i] = pl->h_row_lo[i] >= 0 ? std::min(first_from[i + 1], pl->h_row_lo[i]) : first_from[i + 1];
+    int rows_done = 0;
+    for (int k = 0; k < nchunks; ++k) {
+      const int a = k * chunk, b = std::min(NS, a + chunk);
+      XCT_CUDA(cudaMemcpyAsync(vol_dev + a * slice, in_host + a * slice, (size_t)(b - a) * slice * sizeof(float),
+                               cudaMemcpyHostToDevice, pl->s_in));
+      XCT_CUDA(cudaEventRecord(pl->events[2 * k], pl->s_in));
+      XCT_CUDA(cudaStreamWaitEvent(pl->hstream, pl->events[2 * k], 0));
+      if ((rc = launch_walk_forward3(pl, vol_dev, sino_dev, pl->hstream, a, b - a))) return rc;
+      XCT_CUDA(cudaEventRecord(pl->events[2 * k + 1], pl->hstream));
+      const int complete = b == NS ? D0 : std::max(rows_done, first_from[b]);  // rows no later chunk adds to
+      if (complete > rows_done) {
+        XCT_CUDA(cudaStreamWaitEvent(pl->s_out, pl->events[2 * k + 1], 0));
+        XCT_CUDA(rows_copy(rows_done, complete, false, pl->s_out));
+        rows_done = complete;
+      }
+    }
+  } else {
+    int rows_up = 0;  // detector rows [0, rows_up) are on the device
+    for (int k = 0; k < nchunks; ++k) {
+      const int a = k * chunk, b = std::min(NS, a + chunk);
+      int need = rows_up;
+      for (int i = a; i < b; ++i) need = std::max(need, pl->h_row_hi[i] + 1);
+      XCT_CUDA(rows_copy(rows_up, need, true, pl->s_in));
+      rows_up = need;
+      XCT_CUDA(cudaEventRecord(pl->events[2 * k], pl->s_in));
+      XCT_CUDA(cudaStreamWaitEvent(pl->hstream, pl->events[2 * k], 0));
+      if ((rc = launch_walk_adjoint(pl, sino_dev, vol_dev, pl->hstream, a, b - a))) return rc;
+      XCT_CUDA(cudaEventRecord(pl->events[2 * k + 1], pl->hstream));
+      XCT_CUDA(cudaStreamWaitEvent(pl->s_out, pl->events[2 * k + 1], 0));
+      XCT_CUDA(cudaMemcpyAsync(out_host + a * slice, vol_dev + a * slice, (size_t)(b - a) * slice * sizeof(float),
+                               cudaMemcpyDeviceToHost, pl->s_out));
+    }
+  }
+  XCT_CUDA(cudaStreamSynchronize(pl->s_out));
+  XCT_CUDA(cudaStreamSynchronize(pl->hstream));
+  XCT_CUDA(cudaStreamSynchronize(pl->s_in));
+  return XCT_OK;
+}
+
 static int run_host(xct_plan* pl, const float* in_host, float* out_host, int32_t batch, bool forward) {
   int rc = check_call(pl, in_host, out_host, batch);
   if (rc) return rc;
   DeviceGuard guard(pl->device);
+  if (pl->pipe_ok && pl->n0 >= 64) return run_host_pipelined(pl, in_host, out_host, forward);
   const size_t n_in = (forward ? in_elems(pl) : out_elems(pl)) * batch;
   const size_t n_out = (forward ? out_elems(pl) : in_elems(pl)) * batch;
   if ((rc = ensure_stage(pl, n_in, n_out))) return rc;

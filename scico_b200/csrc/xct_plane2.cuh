@@ -25,8 +25,13 @@ namespace xct {
 
 struct Walk2Params {
   PlaneParams p;
-  const long long* rowoff;  // [V][NS] element offset of the sinogram row slice s reads in view v, -1 = none
+  const long long* rowoff;  // [V][row_stride] element offset of the sinogram row slice s reads in view v, -1 = none
   float out_scale;          // 3D: 2.0 (= 4 * 0.5, the axis-0 weight of a full row); 2D: 1
+  // slice sub-range launches (host pipeline, xct_api.cu): the kernel sees p.NS slices starting at
+  // slice s_base of the plan; `in` / `out` volume pointers are already offset by the caller, the
+  // per-(view, slice) tables are indexed with the plan's stride.
+  int row_stride;           // slices per view in rowoff / p.rows (the plan's n0)
+  int s_base;               // first slice of this launch
 };
 
 __device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const float* gmem_src, bool valid) {
@@ -96,7 +101,7 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
   }
   auto fetch = [&](int v, int c0) {
     float* zb = ring + (v % STAGES) * (S * WIN);
-    const long long* ro = wp.rowoff + (size_t)v * p.NS;
+    const long long* ro = wp.rowoff + (size_t)v * wp.row_stride + wp.s_base;
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
       const long long off = __ldg(ro + ck_sl[q]);  // element offset of the row, -1 = no row
@@ -365,7 +370,7 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
 #pragma unroll
           for (int s = 0; s < S; ++s) blk[k][s] = reinterpret_cast<const float*>(&r)[s];
         }
-        const long long* ro = wp.rowoff + (size_t)v * p.NS;
+        const long long* ro = wp.rowoff + (size_t)v * wp.row_stride + wp.s_base;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           const int sl = s0 + s;
@@ -385,7 +390,7 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
       for (int s = 0; s < S; ++s) {
         const int sl = min(s0 + s, p.NS - 1);
         if (IS3D) {
-          rr[s] = load_row(p.rows + (size_t)v * p.NS + sl);
+          rr[s] = load_row(p.rows + (size_t)v * wp.row_stride + wp.s_base + sl);
           y0[s] = sino + ((size_t)v * p.D0 + rr[s].r0) * (size_t)p.D1;
         } else {
           rr[s].r0 = 0; rr[s].w0 = 1.f; rr[s].w1 = 0.f;
