@@ -178,3 +178,76 @@ def test_product_never_imports_oracle():
                 assert "oracle" not in src.replace("the oracle's", "").replace("as the oracle", "") or f.endswith((".cuh", ".cu")), f
                 if f.endswith(".py"):
                     assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+# ---- ASTRA-free geometry conversion (scico/linop/xray/astra/_astra_3d.py:185-307,595-631) ------------
+def _fixture_vectors():
+    """scico/test/linop/xray/astra/test_astra_3d.py:123-155: project along z, rows with y, columns
+    with x, detector centre shifted by (1, 2, 3)."""
+    return np.array([[0, 0, 1, 1, 2, 3, 1, 0, 0, 0, 1, 0]], dtype=np.float64)
+
+
+def test_convert_to_scico_geometry_known_answer():
+    """test_astra_3d.py:200-207: the fixture converts to [[[0,1,0,-2],[0,0,1,-1]]]."""
+    from scico_b200 import geometry as G
+
+    M = G.convert_to_scico_geometry((30, 31, 32), (31, 32), vectors=_fixture_vectors())
+    np.testing.assert_allclose(M, np.array([[[0.0, 1.0, 0.0, -2.0], [0.0, 0.0, 1.0, -1.0]]]), atol=1e-12)
+    # test_astra_3d.py:185-197: voxel (i, j, k) lands on detector index (j - 2, k - 1)
+    rng = np.random.default_rng(0)
+    ijk = np.array([rng.integers(0, s) for s in (30, 31, 32)], dtype=np.float64)
+    v = _fixture_vectors()[0]
+    got = G.project_world_coordinates(G.volume_coords_to_world_coords(ijk, (30, 31, 32)), v[0:3], v[3:6], v[6:9], v[9:12], (31, 32))
+    np.testing.assert_allclose(got, [ijk[1] - 2, ijk[2] - 1], atol=1e-12)
+    with pytest.raises(ValueError):
+        G.convert_to_scico_geometry((4, 4, 4), (4, 4), angles=np.zeros(2), vectors=_fixture_vectors())
+    with pytest.raises(ValueError):
+        G.convert_to_scico_geometry((4, 4, 4), (4, 4))
+
+
+def test_convert_from_scico_geometry_known_answer_and_round_trip():
+    """test_astra_3d.py:210-222 (element 5, the detector centre along the ray, is free)."""
+    from scico_b200 import geometry as G
+
+    M = np.array([[[0.0, 1.0, 0.0, -2.0], [0.0, 0.0, 1.0, -1.0]]])
+    vec = G.convert_from_scico_geometry((30, 31, 32), M, (31, 32))
+    truth = _fixture_vectors()
+    np.testing.assert_allclose(vec[0, :5], truth[0, :5], atol=1e-12)
+    np.testing.assert_allclose(vec[0, 6:], truth[0, 6:], atol=1e-12)
+    # round trip through vectors for a tilted geometry (unit detector spacing: the reference's formula
+    # takes the matrix rows themselves as u and v, which inverts the conversion only for unit steps)
+    from scipy.spatial.transform import Rotation
+
+    ang = np.linspace(0, np.pi, 7, endpoint=False)
+    v0 = G.rotate_vectors(G.angle_to_vector((1.0, 1.0), ang), Rotation.from_euler("x", 0.3))
+    M0 = G.convert_to_scico_geometry((12, 14, 16), (20, 24), vectors=v0)
+    M1 = G.convert_to_scico_geometry((12, 14, 16), (20, 24), vectors=G.convert_from_scico_geometry((12, 14, 16), M0, (20, 24)))
+    np.testing.assert_allclose(M1, M0, atol=1e-10)
+
+
+def test_angle_to_vector_and_rotate_vectors():
+    """test_astra_3d.py:104-118."""
+    from scipy.spatial.transform import Rotation
+
+    from scico_b200 import geometry as G
+
+    assert G.angle_to_vector([0.9, 1.5], np.linspace(0, np.pi, 5)).shape == (5, 12)
+    v0 = G.angle_to_vector([1.0, 1.0], np.linspace(0, np.pi / 2, 4, endpoint=False))
+    v1 = G.angle_to_vector([1.0, 1.0], np.linspace(np.pi / 2, np.pi, 4, endpoint=False))
+    r = Rotation.from_euler("z", np.pi / 2)
+    np.testing.assert_allclose(G.rotate_vectors(v0, r), v1, atol=1e-7)
+    np.testing.assert_allclose(G.rotate_vectors(v0, r.as_matrix()), v1, atol=1e-7)
+
+
+def test_parallel3d_geometry_is_axis0_separable():
+    """ct_3d_tv_padmm.py:49-58: angle_to_vector + convert_to_scico_geometry gives rows that depend on
+    volume axis 0 only -- the geometry the z-slab sharding and the walk kernels are built for."""
+    from scico_b200 import geometry as G
+
+    shape, det = (64, 128, 256), (64, 256)
+    angles = np.linspace(0, np.pi, 10, endpoint=False)
+    M = G.convert_to_scico_geometry(shape, det, vectors=G.angle_to_vector([1.0, 1.0], angles))
+    M2 = G.convert_to_scico_geometry(shape, det, det_spacing=[1.0, 1.0], angles=angles)
+    np.testing.assert_allclose(M, M2, atol=1e-12)
+    assert G.is_axis0_separable(M.astype(np.float32))  # exact zeros: no pseudo-inverse noise left
+    np.testing.assert_allclose(M[:, 0], np.tile([1.0, 0.0, 0.0, 0.0], (10, 1)), atol=1e-12)
