@@ -60,6 +60,7 @@ typedef enum xct_status {
 #define XCT_FLAG_FORCE_GENERAL 0x1u /* skip the separable fast path (testing / comparison) */
 #define XCT_FLAG_NO_WALK 0x2u       /* keep the first-generation plane kernels (testing / comparison) */
 #define XCT_FLAG_NO_HOST_PIPELINE 0x4u /* xct_*_host: one H2D, kernels, one D2H (testing / comparison) */
+#define XCT_FLAG_NO_JOINT 0x8u      /* walk forward: one column per walk for every view (testing / comparison) */
 
 /* kernel families a plan can resolve to (xct_plan_info.path) */
 #define XCT_PATH_2D_PLANE 1   /* 2D, warp-autonomous plane kernels */

@@ -25,6 +25,7 @@ SPLIT_ADMM, SPLIT_LADMM, SPLIT_PADMM = 0, 1, 2
 FLAG_FORCE_GENERAL = 0x1
 FLAG_NO_WALK = 0x2
 FLAG_NO_HOST_PIPELINE = 0x4
+FLAG_NO_JOINT = 0x8
 KERNEL_NAMES = {0: "general", 1: "plane", 2: "walk"}
 
 PATH_NAMES = {1: "2d_plane", 2: "2d_general", 3: "3d_sep", 4: "3d_general"}

@@ -74,6 +74,13 @@ struct xct_plan {
   bool fwd_unit4 = false;  // vector flush possible (unit rows, D1 % 4 == 0, window fits with 4-bin alignment)
   int* d_list4[4] = {nullptr, nullptr, nullptr, nullptr};  // walk forward: [2*major_b + minor_up]
   int n_list4[4] = {0, 0, 0, 0};
+  // joint-column walk forward: views with fjump == 0 by [4*major_b + 2*minor_up + major_positive],
+  // the remaining ("risky") views by [2*major_b + minor_up] for walk_forward_kernel
+  bool fwd_joint = false;
+  int* d_listJ[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_listJ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int* d_listR[4] = {nullptr, nullptr, nullptr, nullptr};
+  int n_listR[4] = {0, 0, 0, 0};
   long long* d_rowoff = nullptr;  // [V][n0] element offset of the (local) sinogram row, or -1
   int n_list[2] = {0, 0};
   // host-buffer staging (xct_*_host)
@@ -126,6 +133,8 @@ struct Envelope {
   int gs = 2;
   std::vector<int> list[2];
   std::vector<int> list4[4];  // [2*major_b + minor_up]: minor-axis coefficient >= 0
+  std::vector<int> listJ[8];  // fjump == 0: [4*major_b + 2*minor_up + major_positive]
+  std::vector<int> listR[4];  // fjump != 0: [2*major_b + minor_up]
 };
 
 Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fwdTN) {
@@ -147,6 +156,12 @@ Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fw
     const float minor = major_b ? views[v].ca : views[v].cb;
     if (minor == 0.f) zero_minor[major_b ? 1 : 0].push_back((int)v);  // no bin movement: either sign class
     else env.list4[(major_b ? 2 : 0) + (minor > 0.f ? 1 : 0)].push_back((int)v);
+    {
+      const float major = major_b ? views[v].cb : views[v].ca;
+      const int up = minor >= 0.f ? 1 : 0;
+      if (views[v].fjump == 0.f) env.listJ[(major_b ? 4 : 0) + 2 * up + (major > 0.f ? 1 : 0)].push_back((int)v);
+      else env.listR[(major_b ? 2 : 0) + up].push_back((int)v);
+    }
     min_major = std::min(min_major, std::max(a, b));
   }
   for (int m = 0; m < 2; ++m) {  // views with a zero minor coefficient join the larger sign class
@@ -186,6 +201,15 @@ int upload_lists(xct_plan* pl, const Envelope& env) {
     XCT_CUDA(cudaMemcpy(pl->d_list4[c], env.list4[c].data(), sizeof(int) * env.list4[c].size(),
                         cudaMemcpyHostToDevice));
   }
+  auto up = [](const std::vector<int>& src, int*& dst, int& n) -> cudaError_t {
+    n = (int)src.size();
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&dst, sizeof(int) * src.size());
+    if (e == cudaSuccess) e = cudaMemcpy(dst, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice);
+    return e;
+  };
+  for (int c = 0; c < 8; ++c) XCT_CUDA(up(env.listJ[c], pl->d_listJ[c], pl->n_listJ[c]));
+  for (int c = 0; c < 4; ++c) XCT_CUDA(up(env.listR[c], pl->d_listR[c], pl->n_listR[c]));
   return XCT_OK;
 }
 
@@ -291,22 +315,9 @@ int launch_plane_forward(const xct_plan* pl, int batch, const float* in, float* 
 }
 
 // walk forward: one launch per (major axis, minor-axis sign) class
-template <class G, bool IS3D, int S, int TN, int GS, bool MAJOR_B, bool MINOR_UP, bool COLD, bool UNIT4>
-int launch_walk_forward_class(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st,
-                              int s_begin, int s_count) {
-  const int cls = (MAJOR_B ? 2 : 0) + (MINOR_UP ? 1 : 0);
-  if (pl->n_list4[cls] == 0) return XCT_OK;
-  xct::Walk2Params wp{};
-  wp.p = plane_params(pl, batch);
-  wp.rowoff = pl->d_rowoff;
-  wp.out_scale = 2.0f;
-  wp.row_stride = wp.p.NS;
-  wp.s_base = s_begin;
-  xct::PlaneParams& p = wp.p;
-  if (s_count >= 0) p.NS = s_count;
-  in += (size_t)s_begin * p.NA * p.NB;
-  p.view_list = pl->d_list4[cls];
-  p.n_list = pl->n_list4[cls];
+// Launch geometry shared by the walk forward kernels (tile = 64 major x TN minor x S slices per warp).
+template <int S, int TN, int GS, bool MAJOR_B>
+dim3 walk_forward_grid(xct::PlaneParams& p) {
   constexpr int TM = 32 * GS;
   p.tilesA = ceil_div(p.NA, MAJOR_B ? TN : TM);
   p.tilesB = ceil_div(p.NB, MAJOR_B ? TM : TN);
@@ -317,8 +328,53 @@ int launch_walk_forward_class(const xct_plan* pl, int batch, const float* in, fl
   if (tasks < target_warps) chunks = (int)std::min<long long>((target_warps + tasks - 1) / tasks, std::max(1, p.n_list / 4));
   p.views_per_chunk = ceil_div(p.n_list, chunks);
   chunks = ceil_div(p.n_list, p.views_per_chunk);
+  return dim3(blocks, chunks);
+}
+
+// joint-column walk forward: one launch per (major axis, minor sign, major sign) class of safe views
+template <bool MAJOR_B, bool MINOR_UP, bool MAJ_POS>
+int launch_walk_forward_joint_class(const xct_plan* pl, const float* in, float* out, cudaStream_t st, int s_begin,
+                                    int s_count) {
+  const int cls = (MAJOR_B ? 4 : 0) + (MINOR_UP ? 2 : 0) + (MAJ_POS ? 1 : 0);
+  if (pl->n_listJ[cls] == 0) return XCT_OK;
+  xct::Walk2Params wp{};
+  wp.p = plane_params(pl, 1);
+  wp.rowoff = pl->d_rowoff;
+  wp.out_scale = 2.0f;
+  wp.row_stride = wp.p.NS;
+  wp.s_base = s_begin;
+  xct::PlaneParams& p = wp.p;
+  if (s_count >= 0) p.NS = s_count;
+  in += (size_t)s_begin * p.NA * p.NB;
+  p.view_list = pl->d_listJ[cls];
+  p.n_list = pl->n_listJ[cls];
+  const dim3 grid = walk_forward_grid<kWFwdS, kWFwdTN, 2, MAJOR_B>(p);
+  const size_t smem = (size_t)kWarps * kWFwdS * kFwdWin * sizeof(float);
+  xct::walk_forward_joint_kernel<xct::Geom3, kWFwdS, kWFwdTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, kWarps>
+      <<<grid, kWarps * 32, smem, st>>>(wp, in, out);
+  return launch_ok("walk_forward_joint_kernel");
+}
+
+template <class G, bool IS3D, int S, int TN, int GS, bool MAJOR_B, bool MINOR_UP, bool COLD, bool UNIT4>
+int launch_walk_forward_class(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st,
+                              int s_begin, int s_count, bool risky_only = false) {
+  const int cls = (MAJOR_B ? 2 : 0) + (MINOR_UP ? 1 : 0);
+  const int* list = risky_only ? pl->d_listR[cls] : pl->d_list4[cls];
+  const int n_list = risky_only ? pl->n_listR[cls] : pl->n_list4[cls];
+  if (n_list == 0) return XCT_OK;
+  xct::Walk2Params wp{};
+  wp.p = plane_params(pl, batch);
+  wp.rowoff = pl->d_rowoff;
+  wp.out_scale = 2.0f;
+  wp.row_stride = wp.p.NS;
+  wp.s_base = s_begin;
+  xct::PlaneParams& p = wp.p;
+  if (s_count >= 0) p.NS = s_count;
+  in += (size_t)s_begin * p.NA * p.NB;
+  p.view_list = list;
+  p.n_list = n_list;
+  const dim3 grid = walk_forward_grid<S, TN, GS, MAJOR_B>(p);
   const size_t smem = (size_t)kWarps * S * kFwdWin * sizeof(float);
-  dim3 grid(blocks, chunks);
   xct::walk_forward_kernel<G, IS3D, S, TN, GS, kFwdWin, MAJOR_B, MINOR_UP, COLD, UNIT4, kWarps>
       <<<grid, kWarps * 32, smem, st>>>(wp, in, out);
   return launch_ok("walk_forward_kernel");
@@ -326,12 +382,24 @@ int launch_walk_forward_class(const xct_plan* pl, int batch, const float* in, fl
 
 template <class G, bool IS3D, int S, int TN, bool COLD, bool UNIT4>
 int launch_walk_forward_v(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st, int s_begin,
-                          int s_count) {
+                          int s_count, bool risky_only = false) {
   int rc;
-  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, true, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count))) return rc;
-  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, false, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count))) return rc;
-  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, false, true, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count))) return rc;
-  return launch_walk_forward_class<G, IS3D, S, TN, 2, false, false, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count);
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, true, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count, risky_only))) return rc;
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, true, false, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count, risky_only))) return rc;
+  if ((rc = launch_walk_forward_class<G, IS3D, S, TN, 2, false, true, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count, risky_only))) return rc;
+  return launch_walk_forward_class<G, IS3D, S, TN, 2, false, false, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count, risky_only);
+}
+
+int launch_walk_forward_joint(const xct_plan* pl, const float* in, float* out, cudaStream_t st, int s_begin, int s_count) {
+  int rc;
+  if ((rc = launch_walk_forward_joint_class<true, true, true>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_joint_class<true, true, false>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_joint_class<true, false, true>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_joint_class<true, false, false>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_joint_class<false, true, true>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_joint_class<false, true, false>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_joint_class<false, false, true>(pl, in, out, st, s_begin, s_count))) return rc;
+  return launch_walk_forward_joint_class<false, false, false>(pl, in, out, st, s_begin, s_count);
 }
 
 // 3D separable forward.  The vector flush needs unit rows, D1 % 4 == 0 and a 16-byte aligned sinogram.
@@ -341,6 +409,12 @@ int launch_walk_forward3(const xct_plan* pl, const float* in, float* out, cudaSt
   const bool unit4 = pl->fwd_unit4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (pl->fwd_cold) {
     return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, true, false>(pl, 1, in, out, st, s_begin, s_count);
+  }
+  if (unit4 && pl->fwd_joint) {
+    // safe views: joint-column kernel; views within rounding distance of a unit coefficient: 2-bin walk
+    int rc = launch_walk_forward_joint(pl, in, out, st, s_begin, s_count);
+    if (rc) return rc;
+    return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, true>(pl, 1, in, out, st, s_begin, s_count, true);
   }
   if (unit4) return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, true>(pl, 1, in, out, st, s_begin, s_count);
   return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, false>(pl, 1, in, out, st, s_begin, s_count);
@@ -495,6 +569,12 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       const float* M = g->matrices + 8 * (size_t)v;
       xct::ViewRec r{};
       r.ca = M[5]; r.cb = M[6]; r.off = M[7]; r.width = 1.f; r.rwidth = 1.f;
+      // walk adjoint: consecutive rows move the coordinate by ca plus at most ~4 ulp of |u| of
+      // rounding (one product, three sums); above 1 the bin can advance by two in one step
+      const float umax = std::fabs(r.ca) * g->n1 + std::fabs(r.cb) * g->n2 + std::fabs(r.off) + 2.f;
+      const float ulp = std::ldexp(1.f, std::ilogb(umax) - 23);
+      r.jump = (std::fabs(r.ca) + 8.f * ulp > 1.f) ? 1.f : 0.f;
+      r.fjump = (std::max(std::fabs(r.ca), std::fabs(r.cb)) + 8.f * ulp > 1.f) ? 1.f : 0.f;
       views[v] = r;
     }
     Envelope env = analyse_views(views, kAdj3TA, kFwd3TN);
@@ -579,6 +659,7 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       pl->fwd_walk = env.fwd_ok && env.gs == 2 && !(g->flags & XCT_FLAG_NO_WALK);
       pl->fwd_cold = env.max_minor > 0.98f;
       pl->fwd_unit4 = env.fwd_unit4_ok && unit && (g->d1 % 4 == 0);
+      pl->fwd_joint = pl->fwd_walk && pl->fwd_unit4 && !pl->fwd_cold && !(g->flags & XCT_FLAG_NO_JOINT);
       pl->adj_walk = env.adj_ok && env.adj_walk_ok && unit && (g->d1 % 4 == 0) && !(g->flags & XCT_FLAG_NO_WALK);
       pl->gs = env.fwd_ok ? env.gs : 0;
       pl->pipe_ok = pl->pipe_ok && pl->fwd_walk && pl->adj_walk && !(g->flags & XCT_FLAG_NO_HOST_PIPELINE);
@@ -599,6 +680,8 @@ void xct_plan_destroy(xct_plan* pl) {
   cudaFree(pl->d_list[1]);
   cudaFree(pl->d_rowoff);
   for (int c = 0; c < 4; ++c) cudaFree(pl->d_list4[c]);
+  for (int c = 0; c < 8; ++c) cudaFree(pl->d_listJ[c]);
+  for (int c = 0; c < 4; ++c) cudaFree(pl->d_listR[c]);
   cudaFree(pl->stage_in);
   cudaFree(pl->stage_out);
   if (pl->hstream) cudaStreamDestroy(pl->hstream);

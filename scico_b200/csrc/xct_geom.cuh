@@ -16,7 +16,9 @@ struct __align__(16) ViewRec {
   float off;     // 3D: M[1,3]                                           2D: Pxmin
   float width;   // 2D: projected pixel width                             3D: unused
   float rwidth;  // 2D: 1/width (correctly rounded)                       3D: unused
-  float pad0, pad1, pad2;
+  float jump;    // walk adjoint: != 0 when rounding can move the bin by two per row step (|ca| ~ 1)
+  float fjump;   // walk forward: != 0 when some coefficient is within rounding distance of 1 (or above)
+  float pad2;
 };
 
 // 3D separable geometry, plane = (voxel axis 1, voxel axis 2) -> detector column.

@@ -42,7 +42,7 @@ __device__ __forceinline__ ViewRec load_view(const ViewRec* p) {
   float4 lo = __ldg(q), hi = __ldg(q + 1);
   ViewRec v;
   v.ca = lo.x; v.cb = lo.y; v.off = lo.z; v.width = lo.w;
-  v.rwidth = hi.x; v.pad0 = hi.y; v.pad1 = hi.z; v.pad2 = hi.w;
+  v.rwidth = hi.x; v.jump = hi.y; v.fjump = hi.z; v.pad2 = hi.w;
   return v;
 }
 __device__ __forceinline__ RowRec load_row(const RowRec* p) {

@@ -77,11 +77,15 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
   const int b = b0 + lane;
   float* ring = smem + (size_t)warp * (STAGES * S * WIN);
 
-  float acc[TA][S];
+  // accumulators as slice PAIRS: the two taps of two slices are one FFMA2 each (fma.rn.f32x2,
+  // sm_100: two IEEE fp32 fmas per issue slot; per element identical to fmaf)
+  static_assert(S % 2 == 0, "slices are processed in pairs");
+  constexpr int H = S / 2;
+  float2 acc[TA][H];
 #pragma unroll
   for (int n = 0; n < TA; ++n)
 #pragma unroll
-    for (int s = 0; s < S; ++s) acc[n][s] = 0.f;
+    for (int h = 0; h < H; ++h) acc[n][h] = make_float2(0.f, 0.f);
 
   // ---- producer: one view's S row segments, global -> shared, asynchronous.
   // Chunk -> (slice, 4-bin group) assignment is fixed per lane; only the row offset and the
@@ -116,11 +120,14 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
     return window_start4<G>(vr, a0, a0 + TA - 1, b0, b0 + 31);
   };
 
-  // ---- consumer: walk down the TA rows of this thread's column, carrying (z[c], z[c+1])
+  // ---- consumer: walk down the TA rows of this thread's column, carrying (z[c], z[c+1]).
+  // COLD (per view, warp-uniform: ViewRec::jump set on the host when |ca| is so close to 1 that
+  // rounding can move the bin by two in one row step) reloads the other tap after such a jump.
   const float xa0 = G::coordA(a0);
-  auto walk = [&](auto up_c, const float* zb, const ViewRec& vr, int c0, float hB) {
+  auto walk = [&](auto up_c, auto cold_c, const float* zb, const ViewRec& vr, int c0, float hB) {
     constexpr bool UP = decltype(up_c)::value;
-    float lo[S], hi[S];
+    constexpr bool COLD = decltype(cold_c)::value;
+    float2 lo[H], hi[H];
     int tp = 0;
 #pragma unroll
     for (int n = 0; n < TA; ++n) {
@@ -132,37 +139,40 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
       const float* z = zb + t;
       if (n == 0) {
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          lo[s] = z[s * WIN];
-          hi[s] = z[s * WIN + 1];
+        for (int h = 0; h < H; ++h) {
+          lo[h] = make_float2(z[(2 * h) * WIN], z[(2 * h + 1) * WIN]);
+          hi[h] = make_float2(z[(2 * h) * WIN + 1], z[(2 * h + 1) * WIN + 1]);
         }
       } else {
         const bool moved = t != tp;
         if (UP) {
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            lo[s] = moved ? hi[s] : lo[s];
-            hi[s] = z[s * WIN + 1];
+          for (int h = 0; h < H; ++h) {
+            lo[h].x = moved ? hi[h].x : lo[h].x;
+            lo[h].y = moved ? hi[h].y : lo[h].y;
+            hi[h] = make_float2(z[(2 * h) * WIN + 1], z[(2 * h + 1) * WIN + 1]);
           }
-          if (moved && t != tp + 1) {  // cold: only when |ca| > 1
+          if (COLD && moved && t != tp + 1) {
 #pragma unroll
-            for (int s = 0; s < S; ++s) lo[s] = z[s * WIN];
+            for (int h = 0; h < H; ++h) lo[h] = make_float2(z[(2 * h) * WIN], z[(2 * h + 1) * WIN]);
           }
         } else {
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            hi[s] = moved ? lo[s] : hi[s];
-            lo[s] = z[s * WIN];
+          for (int h = 0; h < H; ++h) {
+            hi[h].x = moved ? lo[h].x : hi[h].x;
+            hi[h].y = moved ? lo[h].y : hi[h].y;
+            lo[h] = make_float2(z[(2 * h) * WIN], z[(2 * h + 1) * WIN]);
           }
-          if (moved && t != tp - 1) {
+          if (COLD && moved && t != tp - 1) {
 #pragma unroll
-            for (int s = 0; s < S; ++s) hi[s] = z[s * WIN + 1];
+            for (int h = 0; h < H; ++h) hi[h] = make_float2(z[(2 * h) * WIN + 1], z[(2 * h + 1) * WIN + 1]);
           }
         }
       }
       tp = t;
+      const float2 w0p = make_float2(w0, w0), w1p = make_float2(w1, w1);
 #pragma unroll
-      for (int s = 0; s < S; ++s) acc[n][s] = fmaf(hi[s], w1, fmaf(lo[s], w0, acc[n][s]));
+      for (int h = 0; h < H; ++h) acc[n][h] = __ffma2_rn(hi[h], w1p, __ffma2_rn(lo[h], w0p, acc[n][h]));
     }
   };
 
@@ -196,8 +206,14 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
 #pragma unroll
     for (int i = 0; i + 1 < STAGES; ++i) c0q[i] = c0q[i + 1];
     const float hB = G::hoistB(vr, b);
-    if (vr.ca >= 0.f) walk(std::true_type{}, zb, vr, c0, hB);   // bins non-decreasing down the rows
-    else walk(std::false_type{}, zb, vr, c0, hB);
+    if (vr.jump != 0.f) {  // rare (|ca| within rounding distance of 1)
+      if (vr.ca >= 0.f) walk(std::true_type{}, std::true_type{}, zb, vr, c0, hB);
+      else walk(std::false_type{}, std::true_type{}, zb, vr, c0, hB);
+    } else if (vr.ca >= 0.f) {
+      walk(std::true_type{}, std::false_type{}, zb, vr, c0, hB);  // bins non-decreasing down the rows
+    } else {
+      walk(std::false_type{}, std::false_type{}, zb, vr, c0, hB);
+    }
   }
   cp_async_wait<0>();
 
@@ -208,7 +224,8 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
 #pragma unroll
       for (int n = 0; n < TA; ++n) {
         if (a0 + n < p.NA)
-          out[((size_t)(s0 + s) * p.NA + (a0 + n)) * (size_t)p.NB + b] = acc[n][s] * wp.out_scale;
+          out[((size_t)(s0 + s) * p.NA + (a0 + n)) * (size_t)p.NB + b] =
+              ((s & 1) ? acc[n][s / 2].y : acc[n][s / 2].x) * wp.out_scale;
       }
     }
   }
@@ -265,8 +282,10 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
   float* win = smem + (size_t)warp * (WIN * S);
   Vec* winv = reinterpret_cast<Vec*>(win);
 
-  // this thread's voxels, kept for every view of the launch
-  float x[GS][TN][S];
+  // this thread's voxels, kept for every view of the launch, as slice PAIRS: the two bin sums of
+  // two slices advance with one FFMA2 each (fma.rn.f32x2; per element identical to fmaf)
+  constexpr int H = S / 2;
+  float2 x[GS][TN][H];
 #pragma unroll
   for (int d = 0; d < GS; ++d)
 #pragma unroll
@@ -275,23 +294,27 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
       const int b = MAJOR_B ? b0 + GS * lane + d : b0 + n;
       const bool ok = a < p.NA && b < p.NB;
 #pragma unroll
-      for (int s = 0; s < S; ++s)
-        x[d][n][s] = (ok && s0 + s < p.NS) ? __ldg(in + ((size_t)(s0 + s) * p.NA + a) * (size_t)p.NB + b) : 0.f;
+      for (int s = 0; s < S; ++s) {
+        const float val = (ok && s0 + s < p.NS) ? __ldg(in + ((size_t)(s0 + s) * p.NA + a) * (size_t)p.NB + b) : 0.f;
+        if (s & 1) x[d][n][s / 2].y = val;
+        else x[d][n][s / 2].x = val;
+      }
     }
 
   // minor-axis coordinate of walk step 0 (a for MAJOR_B, b otherwise); + n is exact
   const float xmin0 = MAJOR_B ? G::coordA(a0) : G::coordB(b0);
 
-  auto rmw = [&](int t, const float (&v)[S]) {  // win[t][:] += v   (one lane per address)
+  auto rmw = [&](int t, const float2 (&v)[H]) {  // win[t][:] += v   (one lane per address)
     Vec cur = winv[t];
-    float* c = reinterpret_cast<float*>(&cur);
+    float2* c = reinterpret_cast<float2*>(&cur);
 #pragma unroll
-    for (int s = 0; s < S; ++s) c[s] += v[s];
+    for (int h = 0; h < H; ++h) c[h] = __fadd2_rn(c[h], v[h]);
     winv[t] = cur;
   };
   Vec vzero;
 #pragma unroll
   for (int s = 0; s < S; ++s) reinterpret_cast<float*>(&vzero)[s] = 0.f;
+  const float2 zero2 = make_float2(0.f, 0.f);
 
   const int v_begin = blockIdx.y * p.views_per_chunk;
   const int v_end = min(p.n_list, v_begin + p.views_per_chunk);
@@ -308,7 +331,7 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
 #pragma unroll
     for (int d = 0; d < GS; ++d) {
       const float hMaj = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + d) : G::hoistA(vr, a0 + GS * lane + d);
-      float lo[S], hi[S];
+      float2 lo[H], hi[H];
       int tp = 0;
 #pragma unroll
       for (int n = 0; n < TN; ++n) {
@@ -317,12 +340,13 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
         int c;
         float w0, w1;
         G::bins(vr, u, c, w0, w1);
+        const float2 w0p = make_float2(w0, w0), w1p = make_float2(w1, w1);
         const int t = (int)min((unsigned)(c - c0), (unsigned)(WIN - 2));
         if (n == 0) {
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            lo[s] = x[d][n][s] * w0;
-            hi[s] = x[d][n][s] * w1;
+          for (int h = 0; h < H; ++h) {
+            lo[h] = __fmul2_rn(x[d][n][h], w0p);
+            hi[h] = __fmul2_rn(x[d][n][h], w1p);
           }
         } else {
           if (t != tp) {
@@ -331,23 +355,23 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
             else rmw(tp + 1, hi);
             if (!COLD || (MINOR_UP ? (t == tp + 1) : (t == tp - 1))) {
 #pragma unroll
-              for (int s = 0; s < S; ++s) {
-                if (MINOR_UP) { lo[s] = hi[s]; hi[s] = 0.f; }
-                else { hi[s] = lo[s]; lo[s] = 0.f; }
+              for (int h = 0; h < H; ++h) {
+                if (MINOR_UP) { lo[h] = hi[h]; hi[h] = zero2; }
+                else { hi[h] = lo[h]; lo[h] = zero2; }
               }
             } else {  // the bin moved by more than one (|c_minor| > 1): flush the other one too
               if (MINOR_UP) rmw(tp + 1, hi);
               else rmw(tp, lo);
 #pragma unroll
-              for (int s = 0; s < S; ++s) lo[s] = hi[s] = 0.f;
+              for (int h = 0; h < H; ++h) lo[h] = hi[h] = zero2;
             }
           }
           // order this step's stores before the next step's loads of other lanes
           __syncwarp();
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            lo[s] = fmaf(x[d][n][s], w0, lo[s]);
-            hi[s] = fmaf(x[d][n][s], w1, hi[s]);
+          for (int h = 0; h < H; ++h) {
+            lo[h] = __ffma2_rn(x[d][n][h], w0p, lo[h]);
+            hi[h] = __ffma2_rn(x[d][n][h], w1p, hi[h]);
           }
         }
         tp = t;
@@ -413,6 +437,157 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
             }
           }
         }
+      }
+    }
+    __syncwarp();  // all window reads done before the next view zeroes it
+  }
+}
+
+// ------------------------------------------------------------------------ forward, joint columns
+// Same tile and window as walk_forward_kernel, but a lane walks its TWO major-axis columns
+// TOGETHER and carries THREE bin sums in registers: the column with the smaller coordinate (F) sits
+// on bins (t, t+1), its neighbour (G, one voxel further along the major axis, |c_major| <= 1) on
+// (t+e, t+e+1) with e in {0, 1}, so both fit bins t .. t+2.  One shared-memory read-modify-write
+// per bin change then serves both columns: the shared-memory wavefronts that bound
+// walk_forward_kernel (ncu: 14 per walk step, 39 % of them bank-conflict replays) drop by ~45 %.
+// Only for views whose bins provably move by at most one per step in both directions
+// (ViewRec::fjump == 0, decided on the host with a rounding margin); the other views of a plan go
+// through walk_forward_kernel.  3D unit-row geometry with the 16-byte vector flush only.
+// MAJ_POS: the major-axis coefficient is positive (F is the lane's first column).
+template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* __restrict__ sino) {
+  static_assert(WIN % 32 == 0 && S == 4, "float4 window slots, flushed 4 bins per lane");
+  using Vec = float4;
+  constexpr int GS = 2, H = S / 2, Q = WIN / 32, TM = 32 * GS;
+  constexpr int DF = MAJ_POS ? 0 : 1, DG = 1 - DF;
+  const PlaneParams& p = wp.p;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sgroups = (p.NS + S - 1) / S;
+  const long long ntasks = (long long)sgroups * p.tilesA * p.tilesB;
+  long long task = (long long)blockIdx.x * WARPS + warp;
+  if (task >= ntasks) return;
+  const int tb_ = (int)(task % p.tilesB);
+  task /= p.tilesB;
+  const int ta = (int)(task % p.tilesA);
+  const int sg = (int)(task / p.tilesA);
+  const int a0 = ta * (MAJOR_B ? TN : TM), b0 = tb_ * (MAJOR_B ? TM : TN), s0 = sg * S;
+  Vec* winv = reinterpret_cast<Vec*>(smem + (size_t)warp * (WIN * S));
+
+  float2 x[GS][TN][H];
+#pragma unroll
+  for (int d = 0; d < GS; ++d)
+#pragma unroll
+    for (int n = 0; n < TN; ++n) {
+      const int a = MAJOR_B ? a0 + n : a0 + GS * lane + d;
+      const int b = MAJOR_B ? b0 + GS * lane + d : b0 + n;
+      const bool ok = a < p.NA && b < p.NB;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const float val = (ok && s0 + s < p.NS) ? __ldg(in + ((size_t)(s0 + s) * p.NA + a) * (size_t)p.NB + b) : 0.f;
+        if (s & 1) x[d][n][s / 2].y = val;
+        else x[d][n][s / 2].x = val;
+      }
+    }
+  const float xmin0 = MAJOR_B ? G::coordA(a0) : G::coordB(b0);
+
+  auto rmw = [&](int t, const float2 (&v)[H]) {  // win[t][:] += v   (one lane per address)
+    Vec cur = winv[t];
+    float2* c = reinterpret_cast<float2*>(&cur);
+#pragma unroll
+    for (int h = 0; h < H; ++h) c[h] = __fadd2_rn(c[h], v[h]);
+    winv[t] = cur;
+  };
+  const Vec vzero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float2 zero2 = make_float2(0.f, 0.f);
+
+  const int v_begin = blockIdx.y * p.views_per_chunk;
+  const int v_end = min(p.n_list, v_begin + p.views_per_chunk);
+  for (int vi = v_begin; vi < v_end; ++vi) {
+    const int v = p.view_list ? __ldg(p.view_list + vi) : vi;
+    const ViewRec vr = load_view(p.views + v);
+    const int c0 = window_start<G>(vr, a0, a0 + (MAJOR_B ? TN : TM) - 1, b0, b0 + (MAJOR_B ? TM : TN) - 1) & ~3;
+
+#pragma unroll
+    for (int q = 0; q < Q; ++q) winv[lane + 32 * q] = vzero;
+    __syncwarp();
+
+    const float hF = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + DF) : G::hoistA(vr, a0 + GS * lane + DF);
+    const float hG = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + DG) : G::hoistA(vr, a0 + GS * lane + DG);
+    float2 A0[H], A1[H], A2[H];  // sums of bins tb, tb + 1, tb + 2
+    int tb = 0;
+#pragma unroll
+    for (int n = 0; n < TN; ++n) {
+      const float xm = xmin0 + (float)n;
+      const float hm = MAJOR_B ? G::hoistA_x(vr, xm) : G::hoistB_x(vr, xm);
+      const float uF = MAJOR_B ? G::combine(vr, hm, hF) : G::combine(vr, hF, hm);
+      const float uG = MAJOR_B ? G::combine(vr, hm, hG) : G::combine(vr, hG, hm);
+      int cF, cG;
+      float wF0, wF1, wG0, wG1;
+      G::bins(vr, uF, cF, wF0, wF1);
+      G::bins(vr, uG, cG, wG0, wG1);
+      const int tF = (int)min((unsigned)(cF - c0), (unsigned)(WIN - 3));
+      const bool e = cG != cF;  // G one bin further
+      const float wa = e ? 0.f : wG0, wb = e ? wG0 : wG1, wc = e ? wG1 : 0.f;
+      const float2 wF0p = make_float2(wF0, wF0), wF1p = make_float2(wF1, wF1);
+      const float2 wap = make_float2(wa, wa), wbp = make_float2(wb, wb), wcp = make_float2(wc, wc);
+      if (n == 0) {
+        tb = tF;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          A0[h] = __ffma2_rn(x[DG][n][h], wap, __fmul2_rn(x[DF][n][h], wF0p));
+          A1[h] = __ffma2_rn(x[DG][n][h], wbp, __fmul2_rn(x[DF][n][h], wF1p));
+          A2[h] = __fmul2_rn(x[DG][n][h], wcp);
+        }
+      } else {
+        if (tF != tb) {  // F moved by one bin: the bin leaving the carried triple is complete for this walk
+          if (MINOR_UP) {
+            rmw(tb, A0);
+#pragma unroll
+            for (int h = 0; h < H; ++h) { A0[h] = A1[h]; A1[h] = A2[h]; A2[h] = zero2; }
+          } else {
+            rmw(tb + 2, A2);
+#pragma unroll
+            for (int h = 0; h < H; ++h) { A2[h] = A1[h]; A1[h] = A0[h]; A0[h] = zero2; }
+          }
+          tb = tF;
+        }
+        __syncwarp();  // order this step's stores before the next step's loads of other lanes
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          A0[h] = __ffma2_rn(x[DG][n][h], wap, __ffma2_rn(x[DF][n][h], wF0p, A0[h]));
+          A1[h] = __ffma2_rn(x[DG][n][h], wbp, __ffma2_rn(x[DF][n][h], wF1p, A1[h]));
+          A2[h] = __ffma2_rn(x[DG][n][h], wcp, A2[h]);
+        }
+      }
+    }
+    rmw(tb, A0);
+    __syncwarp();
+    rmw(tb + 1, A1);
+    __syncwarp();
+    rmw(tb + 2, A2);
+    __syncwarp();
+
+    // ---- flush the window: lane j owns bins 4j .. 4j+3 (entirely inside or outside [0, D1))
+    const int col = c0 + 4 * lane;
+    if (lane < WIN / 4 && (unsigned)col < (unsigned)p.D1) {
+      float blk[4][S];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const Vec r = winv[4 * lane + k];
+        blk[k][0] = r.x; blk[k][1] = r.y; blk[k][2] = r.z; blk[k][3] = r.w;
+      }
+      const long long* ro = wp.rowoff + (size_t)v * wp.row_stride + wp.s_base;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int sl = s0 + s;
+        if (sl >= p.NS) break;
+        const long long off = __ldg(ro + sl);
+        const bool any = blk[0][s] != 0.f || blk[1][s] != 0.f || blk[2][s] != 0.f || blk[3][s] != 0.f;
+        if (off >= 0 && any)
+          red_add_v4(sino + off + col, wp.out_scale * blk[0][s], wp.out_scale * blk[1][s],
+                     wp.out_scale * blk[2][s], wp.out_scale * blk[3][s]);
       }
     }
     __syncwarp();  // all window reads done before the next view zeroes it

@@ -140,6 +140,31 @@ def test_walk_kernels_selected_and_match_plane_kernels(torch_dev):
     assert O.rel_l2(out.cpu().numpy(), C.project_3d(x, A.matrices, D)) <= TOL
 
 
+def test_joint_forward_matches_single_column_walk_and_oracle(torch_dev):
+    """walk_forward_joint_kernel (two columns per walk, three carried bins) against the one-column
+    walk kernel and the oracle, over a full turn: every (major axis, minor sign, major sign) class,
+    axis-aligned views (which stay on the one-column kernel) and ragged tiles."""
+    torch, dev = torch_dev
+    rng = np.random.default_rng(33)
+    for N, D, angles in (
+        ((12, 150, 140), (12, 216), np.linspace(0, 2 * np.pi, 24, endpoint=False)),
+        ((5, 70, 131), (5, 192), np.linspace(0.01, 2 * np.pi + 0.01, 17, endpoint=False)),
+        ((9, 64, 64), (9, 64), np.array([0.0, np.pi / 2, np.pi / 4, 3 * np.pi / 4, 1e-4, np.pi / 2 - 1e-4, 2.0])),
+    ):
+        M = sb.matrices_from_euler_angles(N, D, "X", np.asarray(angles)[:, None])
+        A = sb.XRayTransform3D(N, M, D)
+        B = sb.XRayTransform3D(N, M, D, _flags=_lib.FLAG_NO_JOINT)
+        assert A.plan_info()["fwd_kernel"] == 2 and B.plan_info()["fwd_kernel"] == 2
+        x = rng.standard_normal(N).astype(np.float32)
+        a, b = _gpu(torch, dev, A, x), _gpu(torch, dev, B, x)
+        ref = C.project_3d(x, A.matrices, D)
+        assert O.rel_l2(a, b) <= 2e-6
+        assert O.rel_l2(a, ref) <= TOL and O.rel_l2(b, ref) <= TOL
+        # per view, so that a wrong class of a few views cannot hide in the norm
+        for v in range(len(M)):
+            assert O.rel_l2(a[v], ref[v]) <= TOL, v
+
+
 def test_3d_paths_selected(torch_dev):
     A = sb.XRayTransform3D((16,) * 3, _x_mats((16,) * 3, (16, 16), 4), (16, 16))
     assert A.plan_info()["path_name"] == "3d_sep" and A.plan_info()["row_aligned"] == 1
