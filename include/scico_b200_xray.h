@@ -60,6 +60,7 @@ typedef enum xct_status {
 #define XCT_FLAG_FORCE_GENERAL 0x1u /* skip the separable fast path (testing / comparison) */
 #define XCT_FLAG_NO_WALK 0x2u       /* keep the first-generation plane kernels (testing / comparison) */
 #define XCT_FLAG_NO_HOST_PIPELINE 0x4u /* xct_*_host: one H2D, kernels, one D2H (testing / comparison) */
+#define XCT_FLAG_NO_TMA 0x10u       /* walk adjoint: stage the sinogram window with cp.async, not TMA (testing / comparison) */
 #define XCT_FLAG_NO_JOINT 0x8u      /* walk forward: one column per walk for every view (testing / comparison) */
 
 /* kernel families a plan can resolve to (xct_plan_info.path) */
@@ -107,6 +108,8 @@ typedef struct xct_plan_info {
   int32_t device;
   int32_t adj_kernel;     /* XCT_KERNEL_*: what xct_adjoint launches (16-byte aligned input assumed) */
   int32_t fwd_kernel;     /* XCT_KERNEL_*: what xct_forward launches */
+  int32_t fwd_joint;      /* walk forward: views that move by at most one bin per step use the joint-column kernel */
+  int32_t adj_tma;        /* walk adjoint: sinogram window staged by TMA (one box per view) */
   int64_t in_elems;       /* elements of one forward input (per batch item) */
   int64_t out_elems;      /* elements of one forward output (per batch item) */
   int64_t updates;        /* voxel-view updates per application = in_elems * num_views */

@@ -26,6 +26,7 @@ FLAG_FORCE_GENERAL = 0x1
 FLAG_NO_WALK = 0x2
 FLAG_NO_HOST_PIPELINE = 0x4
 FLAG_NO_JOINT = 0x8
+FLAG_NO_TMA = 0x10
 KERNEL_NAMES = {0: "general", 1: "plane", 2: "walk"}
 
 PATH_NAMES = {1: "2d_plane", 2: "2d_general", 3: "3d_sep", 4: "3d_general"}
@@ -102,6 +103,8 @@ class PlanInfo(ctypes.Structure):
         ("device", c_int32),
         ("adj_kernel", c_int32),
         ("fwd_kernel", c_int32),
+        ("fwd_joint", c_int32),
+        ("adj_tma", c_int32),
         ("in_elems", c_int64),
         ("out_elems", c_int64),
         ("updates", c_int64),

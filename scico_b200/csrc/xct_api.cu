@@ -69,6 +69,7 @@ struct xct_plan {
   // walk kernels: every (view, slice) lands in exactly one detector row with axis-0 weight 2
   bool rows_unit = false;
   bool adj_walk = false;
+  bool adj_tma = false;    // walk adjoint stages its sinogram window with one TMA box per view (rows = slice + krow)
   bool fwd_walk = false;
   bool fwd_cold = false;   // some view's minor-axis coefficient can move the bin by more than one per step
   bool fwd_unit4 = false;  // vector flush possible (unit rows, D1 % 4 == 0, window fits with 4-bin alignment)
@@ -222,6 +223,25 @@ int launch_check(const char* name) {
 }
 int launch_ok(const char* name) { return launch_check<void>(name); }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda,
+// so the library still loads on a machine without a driver)
+using TensorMapEncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return reinterpret_cast<TensorMapEncodeFn>(f);
+  }();
+  return fn;
+}
+
 int general_grid(size_t n) {
   size_t blocks = (n + 255) / 256;
   return (int)std::min<size_t>(blocks, 148u * 64u);
@@ -274,8 +294,29 @@ int launch_walk_adjoint(const xct_plan* pl, const float* in, float* out, cudaStr
   const long long tasks = (long long)ceil_div(p.NS, kWAdjS) * p.tilesA * p.tilesB;
   const int blocks = ceil_div(tasks, kWarps);
   const size_t smem = (size_t)kWarps * kWAdjStages * kWAdjS * kWAdjWin * sizeof(float);
-  xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps>
-      <<<blocks, kWarps * 32, smem, st>>>(wp, in, out);
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  if (pl->adj_tma) {
+    // (V, d0, d1) fp32 sinogram, box = kWAdjWin bins x kWAdjS rows x 1 view, zero fill out of bounds
+    const cuuint64_t dims[3] = {(cuuint64_t)pl->d1, (cuuint64_t)pl->d0, (cuuint64_t)pl->V};
+    const cuuint64_t strides[2] = {(cuuint64_t)pl->d1 * sizeof(float), (cuuint64_t)pl->d0 * pl->d1 * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)kWAdjWin, (cuuint32_t)kWAdjS, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), dims, strides,
+                                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) {
+      const size_t smem_tma = smem + (size_t)kWarps * kWAdjStages * sizeof(unsigned long long);
+      auto kern = xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps, true>;
+      XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));  // > 48 KB
+      xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps, true>
+          <<<blocks, kWarps * 32, smem_tma, st>>>(wp, in, out, tmap);
+      return launch_ok("walk_adjoint_kernel<tma>");
+    }
+    // encoding refused (e.g. a stride the tensor map cannot express): cp.async staging below
+  }
+  xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps, false>
+      <<<blocks, kWarps * 32, smem, st>>>(wp, in, out, tmap);
   return launch_ok("walk_adjoint_kernel");
 }
 
@@ -623,6 +664,28 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       }
       pl->row_aligned = aligned;
       pl->rows_unit = unit;
+      // TMA staging of the walk adjoint: per view, local row = local slice + krow wherever a row
+      // exists, and slices without a row fall outside [0, d0) under the same rule (zero fill)
+      bool tma_ok = unit;
+      for (int v = 0; v < V && tma_ok; ++v) {
+        bool have = false;
+        long long k = 0;
+        for (int i = 0; i < g->n0; ++i) {
+          const long long off = rowoff[(size_t)v * g->n0 + i];
+          if (off < 0) continue;
+          const long long r = off / g->d1 - (long long)v * g->d0;
+          if (!have) { k = r - i; have = true; }
+          else if (r - i != k) tma_ok = false;
+        }
+        if (!have) k = -(long long)(g->n0 + g->d0 + 64);
+        for (int i = 0; i < g->n0 && tma_ok; ++i)
+          if (rowoff[(size_t)v * g->n0 + i] < 0 && i + k >= 0 && i + k < g->d0) tma_ok = false;
+        if (k < -(1LL << 30) || k > (1LL << 30)) tma_ok = false;
+        views[v].krow = (int)k;
+      }
+      if (!tma_ok)
+        for (auto& vr : views) vr.krow = 0;
+      pl->adj_tma = tma_ok && tensor_map_encoder() != nullptr && !(g->flags & XCT_FLAG_NO_TMA);
       if (unit) {
         // per-slice detector row range over the views, and whether rows never decrease with the slice
         // index (any rotation about axis 0 with a positive axis-0 scale): the host pipeline relies on it
@@ -701,6 +764,8 @@ int xct_plan_get_info(const xct_plan* pl, xct_plan_info* info) {
   info->device = pl->device;
   info->adj_kernel = pl->adj_walk ? XCT_KERNEL_WALK : (pl->adj_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL);
   info->fwd_kernel = pl->fwd_walk ? XCT_KERNEL_WALK : (pl->fwd_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL);
+  info->fwd_joint = pl->fwd_joint ? 1 : 0;
+  info->adj_tma = pl->adj_tma ? 1 : 0;
   info->in_elems = (int64_t)in_elems(pl);
   info->out_elems = (int64_t)out_elems(pl);
   info->updates = info->in_elems * pl->V;

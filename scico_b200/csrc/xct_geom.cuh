@@ -18,7 +18,7 @@ struct __align__(16) ViewRec {
   float rwidth;  // 2D: 1/width (correctly rounded)                       3D: unused
   float jump;    // walk adjoint: != 0 when rounding can move the bin by two per row step (|ca| ~ 1)
   float fjump;   // walk forward: != 0 when some coefficient is within rounding distance of 1 (or above)
-  float pad2;
+  int krow;      // walk adjoint (TMA): local detector row of slice i is i + krow in this view
 };
 
 // 3D separable geometry, plane = (voxel axis 1, voxel axis 2) -> detector column.

@@ -42,7 +42,7 @@ __device__ __forceinline__ ViewRec load_view(const ViewRec* p) {
   float4 lo = __ldg(q), hi = __ldg(q + 1);
   ViewRec v;
   v.ca = lo.x; v.cb = lo.y; v.off = lo.z; v.width = lo.w;
-  v.rwidth = hi.x; v.jump = hi.y; v.fjump = hi.z; v.pad2 = hi.w;
+  v.rwidth = hi.x; v.jump = hi.y; v.fjump = hi.z; v.krow = __float_as_int(hi.w);
   return v;
 }
 __device__ __forceinline__ RowRec load_row(const RowRec* p) {
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __restrict__ out) {
   static_assert(WIN % 32 == 0, "window is staged 32 bins at a time");
   constexpr int Q = WIN / 32;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sgroups = (p.NS + S - 1) / S;
   const long long ntasks = (long long)sgroups * p.tilesA * p.tilesB;
@@ -186,7 +186,7 @@ plane_forward_kernel(PlaneParams p, const float* __restrict__ in, float* __restr
   static_assert(WIN % 32 == 0, "window is flushed 32 bins at a time");
   constexpr int Q = WIN / 32;
   constexpr int TM = 32 * GS;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sgroups = (p.NS + S - 1) / S;
   const long long ntasks = (long long)sgroups * p.tilesA * p.tilesB;

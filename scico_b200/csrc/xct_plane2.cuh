@@ -17,6 +17,8 @@
 // (possible only when |ca| > 1) takes a cold path that reloads both taps, so the kernel is correct
 // for any geometry inside the window envelope checked at plan creation.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is resolved at run time, see xct_api.cu)
+
 #include <type_traits>
 
 #include "xct_plane.cuh"
@@ -46,6 +48,39 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers for the walk adjoint's sinogram window ----
+// (barriers and destinations are passed as 32-bit shared-window addresses, computed once per warp)
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// box (x: WIN bins, y: S rows, z: 1 view) of the (V, D0, D1) sinogram -> shared; out-of-bounds
+// elements (negative bins, bins >= D1, rows outside [0, D0)) arrive as zeros
+__device__ __forceinline__ void tma_load_3d(unsigned smem_dst, const CUtensorMap* tmap, int x, int y, int z, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          smem_dst),
+      "l"(tmap), "r"(bar), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+
 // Window start rounded down to a multiple of 4 bins so that every 16-byte chunk of a staged row is
 // either entirely inside [0, D1) or entirely outside (D1 % 4 == 0 is required by the launcher).
 template <class G>
@@ -55,15 +90,20 @@ __device__ __forceinline__ int window_start4(const ViewRec& vr, int a_lo, int a_
 
 // Tile: TA rows (axis A) x 32 columns (axis B, lane = column) x S slices.
 // smem per warp: STAGES * S * WIN floats.
-template <class G, bool IS3D, int S, int TA, int WIN, int STAGES, int WARPS>
+// TMA: detector rows of consecutive slices are consecutive (row = slice + ViewRec::krow for every
+// view), so the S x WIN window of a view is ONE box of the (V, D0, D1) sinogram: lane 0 issues a
+// single cp.async.bulk.tensor per view that completes on a per-stage mbarrier (hardware zero fill
+// outside the detector) instead of every lane issuing 16-byte cp.async with its own row lookups.
+template <class G, bool IS3D, int S, int TA, int WIN, int STAGES, int WARPS, bool TMA>
 __global__ void __launch_bounds__(WARPS * 32)
-walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __restrict__ out) {
+walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __restrict__ out,
+                    const __grid_constant__ CUtensorMap tmap) {
   static_assert(WIN % 64 == 0 || WIN == 32, "chunk indexing assumes a power-of-two window");
   constexpr int CPR = WIN / 4;                    // 16-byte chunks per staged row
   constexpr int CHUNKS = S * CPR;                 // chunks per view
   constexpr int CPL = (CHUNKS + 31) / 32;         // chunks per lane
   const PlaneParams& p = wp.p;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sgroups = (p.NS + S - 1) / S;
   const long long ntasks = (long long)sgroups * p.tilesA * p.tilesB;
@@ -76,6 +116,18 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
   const int a0 = ta * TA, b0 = tb * 32, s0 = sg * S;
   const int b = b0 + lane;
   float* ring = smem + (size_t)warp * (STAGES * S * WIN);
+  // TMA: one mbarrier per (warp, stage), behind the rings
+  const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring);
+  const unsigned bars_sa =
+      (unsigned)__cvta_generic_to_shared(smem + (size_t)WARPS * (STAGES * S * WIN)) + warp * STAGES * 8u;
+  if (TMA) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < STAGES; ++i) mbar_init(bars_sa + 8u * i, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
 
   // accumulators as slice PAIRS: the two taps of two slices are one FFMA2 each (fma.rn.f32x2,
   // sm_100: two IEEE fp32 fmas per issue slot; per element identical to fmaf)
@@ -118,6 +170,18 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
   auto view_c0 = [&](int v) {
     const ViewRec vr = load_view(p.views + v);
     return window_start4<G>(vr, a0, a0 + TA - 1, b0, b0 + 31);
+  };
+  // TMA producer: the whole S x WIN window of view v in one bulk tensor copy (lane 0)
+  const int row_base = wp.s_base + s0;
+  auto fetch_tma = [&](int v, int stage) {
+    const ViewRec vr = load_view(p.views + v);
+    const int c0 = window_start4<G>(vr, a0, a0 + TA - 1, b0, b0 + 31);
+    if (lane == 0) {
+      const unsigned bar = bars_sa + 8u * stage;
+      mbar_expect_tx(bar, S * WIN * (unsigned)sizeof(float));
+      tma_load_3d(ring_sa + stage * (S * WIN * (unsigned)sizeof(float)), &tmap, c0, row_base + vr.krow, v, bar);
+    }
+    return c0;
   };
 
   // ---- consumer: walk down the TA rows of this thread's column, carrying (z[c], z[c+1]).
@@ -183,24 +247,40 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
 #pragma unroll
   for (int i = 0; i < STAGES - 1; ++i) {
     if (i < p.n_list) {
-      c0q[i] = view_c0(i);
-      fetch(i, c0q[i]);
+      if (TMA) {
+        c0q[i] = fetch_tma(i, i);
+      } else {
+        c0q[i] = view_c0(i);
+        fetch(i, c0q[i]);
+      }
     }
-    cp_async_commit();
+    if (!TMA) cp_async_commit();
   }
 
+  int st_c = 0, st_p = STAGES - 1;  // stage consumed / produced this iteration (v % STAGES, (v + STAGES - 1) % STAGES)
+  unsigned par = 0;                 // mbarrier phase parity of the consumed stage ((v / STAGES) & 1)
   for (int v = 0; v < p.n_list; ++v) {
     // all lanes have finished reading the stage that fetch(v + STAGES - 1) overwrites
     __syncwarp();
     if (v + STAGES - 1 < p.n_list) {
-      c0q[STAGES - 1] = view_c0(v + STAGES - 1);
-      fetch(v + STAGES - 1, c0q[STAGES - 1]);
+      if (TMA) {
+        c0q[STAGES - 1] = fetch_tma(v + STAGES - 1, st_p);
+      } else {
+        c0q[STAGES - 1] = view_c0(v + STAGES - 1);
+        fetch(v + STAGES - 1, c0q[STAGES - 1]);
+      }
     }
-    cp_async_commit();
-    cp_async_wait<STAGES - 1>();
-    __syncwarp();  // every lane's copies of stage v are complete and visible
+    if (TMA) {
+      mbar_wait(bars_sa + 8u * st_c, par);  // stage v has landed (all lanes observe it)
+    } else {
+      cp_async_commit();
+      cp_async_wait<STAGES - 1>();
+      __syncwarp();  // every lane's copies of stage v are complete and visible
+    }
 
-    const float* zb = ring + (v % STAGES) * (S * WIN);
+    const float* zb = ring + st_c * (S * WIN);
+    st_p = st_c;
+    if (++st_c == STAGES) { st_c = 0; par ^= 1u; }
     const ViewRec vr = load_view(p.views + v);
     const int c0 = c0q[0];
 #pragma unroll
@@ -215,7 +295,7 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
       walk(std::false_type{}, std::false_type{}, zb, vr, c0, hB);
     }
   }
-  cp_async_wait<0>();
+  if (!TMA) cp_async_wait<0>();
 
   if (b < p.NB) {
 #pragma unroll
@@ -268,7 +348,7 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
   constexpr int Q = WIN / 32;
   constexpr int TM = 32 * GS;
   const PlaneParams& p = wp.p;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sgroups = (p.NS + S - 1) / S;
   const long long ntasks = (long long)sgroups * p.tilesA * p.tilesB;
@@ -462,7 +542,7 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
   constexpr int GS = 2, H = S / 2, Q = WIN / 32, TM = 32 * GS;
   constexpr int DF = MAJ_POS ? 0 : 1, DG = 1 - DF;
   const PlaneParams& p = wp.p;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sgroups = (p.NS + S - 1) / S;
   const long long ntasks = (long long)sgroups * p.tilesA * p.tilesB;

@@ -155,6 +155,7 @@ def test_joint_forward_matches_single_column_walk_and_oracle(torch_dev):
         A = sb.XRayTransform3D(N, M, D)
         B = sb.XRayTransform3D(N, M, D, _flags=_lib.FLAG_NO_JOINT)
         assert A.plan_info()["fwd_kernel"] == 2 and B.plan_info()["fwd_kernel"] == 2
+        assert A.plan_info()["fwd_joint"] == 1 and B.plan_info()["fwd_joint"] == 0
         x = rng.standard_normal(N).astype(np.float32)
         a, b = _gpu(torch, dev, A, x), _gpu(torch, dev, B, x)
         ref = C.project_3d(x, A.matrices, D)
@@ -163,6 +164,35 @@ def test_joint_forward_matches_single_column_walk_and_oracle(torch_dev):
         # per view, so that a wrong class of a few views cannot hide in the norm
         for v in range(len(M)):
             assert O.rel_l2(a[v], ref[v]) <= TOL, v
+
+
+def test_tma_staged_adjoint_is_bit_identical_to_cp_async_staging(torch_dev):
+    """The walk adjoint stages its sinogram window either with one TMA box per view (rows of
+    consecutive slices consecutive; hardware zero fill at the detector edges) or with per-lane
+    cp.async: same taps, same order, so the results must be bit-identical."""
+    torch, dev = torch_dev
+    rng = np.random.default_rng(5)
+    for name in ("walk_basic", "walk_ragged_tiles", "walk_small_det", "walk_det_rows_offcentre", "walk_many_slices",
+                 "walk_one_view", "walk_two_views"):
+        N, D, mk = CASES_3D[name]
+        M = mk()
+        A = sb.XRayTransform3D(N, M, D)
+        B = sb.XRayTransform3D(N, M, D, _flags=_lib.FLAG_NO_TMA)
+        assert A.plan_info()["adj_tma"] == 1 and B.plan_info()["adj_tma"] == 0
+        y = rng.standard_normal(A.output_shape).astype(np.float32)
+        a, b = _gpu(torch, dev, A, y, adj=True), _gpu(torch, dev, B, y, adj=True)
+        np.testing.assert_array_equal(a, b)
+        assert O.rel_l2(a, C.back_project_3d(y, A.matrices, N)) <= TOL
+    # z-slab plans (slice / detector-row offsets) go through the same box arithmetic
+    N, D = (24, 40, 48), (24, 64)
+    M = _x_mats(N, D, 9)
+    y = rng.standard_normal((9,) + D).astype(np.float32)
+    full = C.back_project_3d(y, M.astype(np.float32), N)
+    for z0, z1 in ((0, 10), (10, 24), (3, 19)):
+        kw = dict(slice_offset=z0, det_row_offset=z0, det_rows_total=D[0])
+        A = sb.XRayTransform3D((z1 - z0,) + N[1:], M, (z1 - z0, D[1]), **kw)
+        got = _gpu(torch, dev, A, np.ascontiguousarray(y[:, z0:z1]), adj=True)
+        assert O.rel_l2(got, full[z0:z1]) <= TOL
 
 
 def test_3d_paths_selected(torch_dev):

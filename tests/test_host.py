@@ -140,7 +140,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.Geom2D) == 32 and ctypes.sizeof(_lib.Geom3D) == 56
-    assert ctypes.sizeof(_lib.PlanInfo) == 56
+    assert ctypes.sizeof(_lib.PlanInfo) == 64
 
 
 def test_invalid_arguments_are_reported_not_fatal():
