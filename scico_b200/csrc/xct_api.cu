@@ -69,6 +69,7 @@ struct xct_plan {
   // walk kernels: every (view, slice) lands in exactly one detector row with axis-0 weight 2
   bool rows_unit = false;
   bool adj_walk = false;
+  bool rows_krow = false;  // local detector row of slice i is i + ViewRec::krow in every view (or none)
   bool adj_tma = false;    // walk adjoint stages its sinogram window with one TMA box per view (rows = slice + krow)
   bool fwd_walk = false;
   bool fwd_cold = false;   // some view's minor-axis coefficient can move the bin by more than one per step
@@ -391,8 +392,12 @@ int launch_walk_forward_joint_class(const xct_plan* pl, const float* in, float* 
   p.n_list = pl->n_listJ[cls];
   const dim3 grid = walk_forward_grid<kWFwdS, kWFwdTN, 2, MAJOR_B>(p);
   const size_t smem = (size_t)kWarps * kWFwdS * kFwdWin * sizeof(float);
-  xct::walk_forward_joint_kernel<xct::Geom3, kWFwdS, kWFwdTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, kWarps>
-      <<<grid, kWarps * 32, smem, st>>>(wp, in, out);
+  if (pl->rows_krow)
+    xct::walk_forward_joint_kernel<xct::Geom3, kWFwdS, kWFwdTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, true, kWarps>
+        <<<grid, kWarps * 32, smem, st>>>(wp, in, out);
+  else
+    xct::walk_forward_joint_kernel<xct::Geom3, kWFwdS, kWFwdTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, false, kWarps>
+        <<<grid, kWarps * 32, smem, st>>>(wp, in, out);
   return launch_ok("walk_forward_joint_kernel");
 }
 
@@ -685,6 +690,7 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       }
       if (!tma_ok)
         for (auto& vr : views) vr.krow = 0;
+      pl->rows_krow = tma_ok;
       pl->adj_tma = tma_ok && tensor_map_encoder() != nullptr && !(g->flags & XCT_FLAG_NO_TMA);
       if (unit) {
         // per-slice detector row range over the views, and whether rows never decrease with the slice

@@ -534,7 +534,20 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
 // (ViewRec::fjump == 0, decided on the host with a rounding margin); the other views of a plan go
 // through walk_forward_kernel.  3D unit-row geometry with the 16-byte vector flush only.
 // MAJ_POS: the major-axis coefficient is positive (F is the lane's first column).
-template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int WARPS>
+// KROW: in every view the local detector row of slice i is i + ViewRec::krow (or outside the
+// detector), so the flush derives its four row pointers from one base instead of four table loads.
+__device__ __forceinline__ void red_add_v4_if(bool pred, float* p, float a, float b, float c, float d) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %0, 0;\n"
+      "@q red.global.add.v4.f32 [%1], {%2, %3, %4, %5};\n"
+      "}\n" ::"r"((int)pred),
+      "l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+      : "memory");
+}
+
+template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, bool KROW, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* __restrict__ sino) {
   static_assert(WIN % 32 == 0 && S == 4, "float4 window slots, flushed 4 bins per lane");
@@ -565,19 +578,25 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
       const bool ok = a < p.NA && b < p.NB;
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        const float val = (ok && s0 + s < p.NS) ? __ldg(in + ((size_t)(s0 + s) * p.NA + a) * (size_t)p.NB + b) : 0.f;
+        // voxels are pre-multiplied by the axis-0 row weight (2, a power of two: bit-identical to
+        // scaling the bin sums afterwards)
+        const float val =
+            (ok && s0 + s < p.NS) ? wp.out_scale * __ldg(in + ((size_t)(s0 + s) * p.NA + a) * (size_t)p.NB + b) : 0.f;
         if (s & 1) x[d][n][s / 2].y = val;
         else x[d][n][s / 2].x = val;
       }
     }
   const float xmin0 = MAJOR_B ? G::coordA(a0) : G::coordB(b0);
 
+  // (An XOR-swizzled slot layout that makes the final read conflict-free was measured: the two extra
+  // address instructions per RMW cost more than the wavefronts saved -- the kernel is issue-bound.)
   auto rmw = [&](int t, const float2 (&v)[H]) {  // win[t][:] += v   (one lane per address)
-    Vec cur = winv[t];
+    Vec* q = winv + t;
+    Vec cur = *q;
     float2* c = reinterpret_cast<float2*>(&cur);
 #pragma unroll
     for (int h = 0; h < H; ++h) c[h] = __fadd2_rn(c[h], v[h]);
-    winv[t] = cur;
+    *q = cur;
   };
   const Vec vzero = make_float4(0.f, 0.f, 0.f, 0.f);
   const float2 zero2 = make_float2(0.f, 0.f);
@@ -649,7 +668,8 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
     rmw(tb + 2, A2);
     __syncwarp();
 
-    // ---- flush the window: lane j owns bins 4j .. 4j+3 (entirely inside or outside [0, D1))
+    // ---- flush the window: lane j owns bins 4j .. 4j+3 (entirely inside or outside [0, D1));
+    // predicated REDs, no branches per slice
     const int col = c0 + 4 * lane;
     if (lane < WIN / 4 && (unsigned)col < (unsigned)p.D1) {
       float blk[4][S];
@@ -658,16 +678,27 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
         const Vec r = winv[4 * lane + k];
         blk[k][0] = r.x; blk[k][1] = r.y; blk[k][2] = r.z; blk[k][3] = r.w;
       }
-      const long long* ro = wp.rowoff + (size_t)v * wp.row_stride + wp.s_base;
+      if (KROW) {
+        const int r0 = wp.s_base + s0 + vr.krow;  // local detector row of the group's first slice
+        float* y = sino + ((long long)v * p.D0 + r0) * (long long)p.D1 + col;
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        const int sl = s0 + s;
-        if (sl >= p.NS) break;
-        const long long off = __ldg(ro + sl);
-        const bool any = blk[0][s] != 0.f || blk[1][s] != 0.f || blk[2][s] != 0.f || blk[3][s] != 0.f;
-        if (off >= 0 && any)
-          red_add_v4(sino + off + col, wp.out_scale * blk[0][s], wp.out_scale * blk[1][s],
-                     wp.out_scale * blk[2][s], wp.out_scale * blk[3][s]);
+        for (int s = 0; s < S; ++s) {
+          const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
+                               __float_as_uint(blk[3][s]);  // all four +0: nothing to add
+          const bool live = s0 + s < p.NS && (unsigned)(r0 + s) < (unsigned)p.D0 && any != 0u;
+          red_add_v4_if(live, y + (long long)s * p.D1, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+        }
+      } else {
+        const long long* ro = wp.rowoff + (size_t)v * wp.row_stride + wp.s_base;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int sl = min(s0 + s, p.NS - 1);
+          const long long off = __ldg(ro + sl);
+          const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
+                               __float_as_uint(blk[3][s]);
+          const bool live = s0 + s < p.NS && off >= 0 && any != 0u;
+          red_add_v4_if(live, sino + (live ? off : 0) + col, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+        }
       }
     }
     __syncwarp();  // all window reads done before the next view zeroes it
