@@ -140,6 +140,52 @@ def ncu_profile():
     return {}
 
 
+def other_configs(torch, sb, dev):
+    """Forward / adjoint timings of BASELINE.json configs[1..3] on one GPU (CUDA events, 3 warm-ups;
+    C2's working set is smaller than L2, so L2 is flushed before every timed call)."""
+
+    def flush_l2():
+        torch.empty(64 * 1024 * 1024, device=dev).fill_(0.0)  # 256 MB > 126 MB L2
+
+    def time_op(A, updates, reps, flush):
+        g = torch.Generator(device=dev).manual_seed(0)
+        x = torch.randn(A.input_shape, device=dev, generator=g)
+        y = torch.randn(A.output_shape, device=dev, generator=g)
+        res = {}
+        for tag, fn, arg in (("fwd", A.__call__, x), ("adj", A.adj, y)):
+            for _ in range(3):
+                fn(arg)
+            ts = []
+            for _ in range(reps):
+                if flush:
+                    flush_l2()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(arg)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            res[tag + "_ms"] = float(np.mean(ts))
+        Ax, ATy = A(x), A.adj(y)
+        gap = abs(torch.sum(Ax.double() * y.double()).item() - torch.sum(x.double() * ATy.double()).item()) / (
+            torch.linalg.vector_norm(Ax.double()).item() * torch.linalg.vector_norm(y.double()).item())
+        info = A.plan_info()
+        res.update({"pair_updates_per_s": 2 * updates / (res["fwd_ms"] + res["adj_ms"]) * 1e3, "adjoint_gap": gap,
+                    "kernel_path": info["path_name"], "l2": "flushed before every call" if flush else "working set > L2"})
+        return res
+
+    out = {}
+    A = sb.XRayTransform2D((512, 512), np.linspace(0, np.pi, 360, endpoint=False))
+    out["C2 2D 512^2 x 360 views, 725 bins"] = time_op(A, 512 * 512 * 360, 10, True)
+    A = sb.XRayTransform2D((4096, 4096), np.linspace(0, np.pi, 2048, endpoint=False))
+    out["C3 2D 4096^2 x 2048 views, 5793 bins (one GPU)"] = time_op(A, 4096 * 4096 * 2048, 3, False)
+    n, V = 512, 720
+    M = sb.matrices_from_euler_angles((n,) * 3, (n, n), "X", np.linspace(0, np.pi, V, endpoint=False)[:, None])
+    A = sb.XRayTransform3D((n,) * 3, M, (n, n))
+    out["C4 3D 512^3 x 720 views, det 512^2 (one GPU)"] = time_op(A, n ** 3 * V, 3, False)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -180,6 +226,7 @@ def main():
     ap.add_argument("--views", type=int, default=1024)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C2 / C3 / C4 timings")
     ap.add_argument("--solver-iters", type=int, default=3, help="TV-PDHG iterations timed after the operator bench (0 = skip)")
     args = ap.parse_args()
 
@@ -285,15 +332,19 @@ def main():
     ach_adj = loc_bytes / (adj_ms * 1e-3) / 1e9
     kname = {0: "gen3d", 1: "plane", 2: "walk"}
     prof = ncu_profile()
+    fwd_name = (f"walk_forward_joint_kernel<Geom3> (+ walk_forward_kernel for the views within rounding distance of a unit "
+                f"coefficient; {n_fwd_launch} class launches per application)" if info.get("fwd_joint")
+                else f"{kname[info['fwd_kernel']]}_forward_kernel<Geom3> ({n_fwd_launch} launches per application, one per view class)")
     roofline = {
-        "bound": "hbm", "kernel": f"{kname[info['fwd_kernel']]}_forward_kernel<Geom3> ({n_fwd_launch} launches per application, one per view class)",
+        "bound": "hbm", "kernel": fwd_name,
         "achieved": ach_fwd, "peak": peak, "unit": "GB/s", "frac": ach_fwd / peak,
         "algorithmic_bytes_per_launch": loc_bytes / n_fwd_launch, "launch_ms": fwd_ms / n_fwd_launch,
         "traffic": prof.get("forward_traffic_bytes_per_launch_at_bench_size"), "peak_source": peak_src + ", of measured",
         "model": "4 B per voxel-view update + 4 B per sinogram element (per-view streaming model the reference executes); "
                  "real DRAM traffic (ncu) is ~1000x lower: the kernels are shared-memory / instruction-issue bound, "
                  "so a fraction above 1 is possible and only says the per-view streaming model is beaten",
-        "adjoint": {"kernel": f"{kname[info['adj_kernel']]}_adjoint_kernel<Geom3> (1 launch per application)", "achieved": ach_adj,
+        "adjoint": {"kernel": f"{kname[info['adj_kernel']]}_adjoint_kernel<Geom3> (1 launch per application"
+                              + (", TMA-staged sinogram window)" if info.get("adj_tma") else ")"), "achieved": ach_adj,
                     "frac": ach_adj / peak, "launch_ms": adj_ms,
                     "traffic": prof.get("adjoint_traffic_bytes_per_launch_at_bench_size")},
     }
@@ -374,6 +425,14 @@ def main():
                                          "host reads one scalar per CG iteration (termination test)", "itstats": "off"}
         del S
 
+    # the other BASELINE.json configurations that fit one GPU (parity for them lives in tests/; these
+    # are timings only): C2 = configs[1], C3 = configs[2] on one GPU, C4 = configs[3] on one GPU
+    others = None
+    if world == 1 and not args.no_configs:
+        x = y = None
+        torch.cuda.empty_cache()
+        others = other_configs(torch, sb, dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = cpu_sample(wl)
@@ -391,7 +450,8 @@ def main():
                        "partition": f"{world} z-slab(s), no collective", "kernel_path": info["path_name"],
                        "l2": "no flush: per-rank volume and sinogram (>= 0.5 GB each at 8 GPUs) exceed the 126 MB L2",
                        "fwd_ms": fwd_ms, "adj_ms": adj_ms},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "solver": solver, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "solver": solver, "other_configs": others,
+            "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -272,8 +272,18 @@ int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* 
   p.tilesB = ceil_div(p.NB, 32);
   const long long tasks = (long long)ceil_div(p.NS, S) * p.tilesA * p.tilesB;
   const int blocks = ceil_div(tasks, kWarps);
+  // small problems: split the views over blockIdx.y (partial sums meet in the zeroed output via RED)
+  const long long target_warps = 148LL * 32;
+  int chunks = 1;
+  if (tasks < target_warps) chunks = (int)std::min<long long>((target_warps + tasks - 1) / tasks, std::max(1, p.n_list / 8));
+  p.views_per_chunk = ceil_div(p.n_list, chunks);
+  chunks = ceil_div(p.n_list, p.views_per_chunk);
+  if (chunks > 1) {
+    const size_t n_out = (size_t)p.NS * p.NA * p.NB;
+    XCT_CUDA(cudaMemsetAsync(out, 0, n_out * sizeof(float), st));
+  }
   const size_t smem = (size_t)kWarps * 2 * S * kAdjWin * sizeof(float);
-  xct::plane_adjoint_kernel<G, IS3D, S, TA, kAdjWin, kWarps><<<blocks, kWarps * 32, smem, st>>>(p, in, out);
+  xct::plane_adjoint_kernel<G, IS3D, S, TA, kAdjWin, kWarps><<<dim3(blocks, chunks), kWarps * 32, smem, st>>>(p, in, out);
   return launch_ok("plane_adjoint_kernel");
 }
 

@@ -124,16 +124,20 @@ plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __res
     }
   };
 
-  if (p.n_list > 0) fetch(0, c0_next);
-  for (int v = 0; v < p.n_list; ++v) {
-    float* zb = zs + (v & 1) * (S * WIN);
+  // small problems: the views are split over blockIdx.y so that the grid fills the SMs; the partial
+  // sums of the chunks then meet in the (pre-zeroed) output through RED.ADD
+  const int v_begin = blockIdx.y * p.views_per_chunk;
+  const int v_end = min(p.n_list, v_begin + p.views_per_chunk);
+  if (v_begin < v_end) fetch(v_begin, c0_next);
+  for (int v = v_begin; v < v_end; ++v) {
+    float* zb = zs + ((v - v_begin) & 1) * (S * WIN);
     const int c0 = c0_next;
 #pragma unroll
     for (int s = 0; s < S; ++s)
 #pragma unroll
       for (int q = 0; q < Q; ++q) zb[s * WIN + lane + 32 * q] = pre[s][q];
     __syncwarp();
-    if (v + 1 < p.n_list) fetch(v + 1, c0_next);
+    if (v + 1 < v_end) fetch(v + 1, c0_next);
 
     const ViewRec vr = load_view(p.views + v);
     const float hB = G::hoistB(vr, b);
@@ -158,7 +162,11 @@ plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __res
       if (s0 + s >= p.NS) break;
 #pragma unroll
       for (int n = 0; n < TA; ++n) {
-        if (a0 + n < p.NA) out[((size_t)(s0 + s) * p.NA + (a0 + n)) * (size_t)p.NB + b] = acc[n][s];
+        if (a0 + n < p.NA) {
+          float* o = out + ((size_t)(s0 + s) * p.NA + (a0 + n)) * (size_t)p.NB + b;
+          if (gridDim.y > 1) atomicAdd(o, acc[n][s]);
+          else *o = acc[n][s];
+        }
       }
     }
   }
