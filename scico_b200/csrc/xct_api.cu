@@ -625,12 +625,13 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       const float* M = g->matrices + 8 * (size_t)v;
       xct::ViewRec r{};
       r.ca = M[5]; r.cb = M[6]; r.off = M[7]; r.width = 1.f; r.rwidth = 1.f;
-      // walk adjoint: consecutive rows move the coordinate by ca plus at most ~4 ulp of |u| of
-      // rounding (one product, three sums); above 1 the bin can advance by two in one step
+      // walk kernels: neighbouring rows / columns move the coordinate by the coefficient plus at most
+      // 4 ulp of |u| of rounding (one product and three sums on each side, half an ulp each); only
+      // when that can exceed 1 can the bin advance by two in one step (margin: 5 ulp)
       const float umax = std::fabs(r.ca) * g->n1 + std::fabs(r.cb) * g->n2 + std::fabs(r.off) + 2.f;
       const float ulp = std::ldexp(1.f, std::ilogb(umax) - 23);
-      r.jump = (std::fabs(r.ca) + 8.f * ulp > 1.f) ? 1.f : 0.f;
-      r.fjump = (std::max(std::fabs(r.ca), std::fabs(r.cb)) + 8.f * ulp > 1.f) ? 1.f : 0.f;
+      r.jump = (std::fabs(r.ca) + 5.f * ulp > 1.f) ? 1.f : 0.f;
+      r.fjump = (std::max(std::fabs(r.ca), std::fabs(r.cb)) + 5.f * ulp > 1.f) ? 1.f : 0.f;
       views[v] = r;
     }
     Envelope env = analyse_views(views, kAdj3TA, kFwd3TN);
