@@ -195,6 +195,36 @@ def test_tma_staged_adjoint_is_bit_identical_to_cp_async_staging(torch_dev):
         assert O.rel_l2(got, full[z0:z1]) <= TOL
 
 
+def test_pair_is_cuda_graph_capturable(torch_dev):
+    """xct_forward / xct_adjoint enqueue everything on the caller's stream without allocation or host
+    synchronisation (the XLA FFI contract): a forward + adjoint pair captured into a CUDA
+    graph replays on new data in the same buffers (3D walk kernels incl. the TMA box, and 2D)."""
+    torch, dev = torch_dev
+    rng = np.random.default_rng(3)
+    N, D, mk = CASES_3D["walk_basic"]
+    A3 = sb.XRayTransform3D(N, mk(), D)
+    A2 = sb.XRayTransform2D((48, 40), np.linspace(0, np.pi, 12, endpoint=False))
+    for A in (A3, A2):
+        x = torch.as_tensor(rng.standard_normal(A.input_shape).astype(np.float32), device=dev)
+        y = torch.empty(A.output_shape, device=dev)
+        xb = torch.empty(A.input_shape, device=dev)
+        A.project(x, out=y)
+        A.back_project(y, out=xb)  # warm-up outside the capture (plans, kernel attributes)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            A.project(x, out=y)
+            A.back_project(y, out=xb)
+        x2 = rng.standard_normal(A.input_shape).astype(np.float32)
+        x.copy_(torch.as_tensor(x2, device=dev))
+        g.replay()
+        torch.cuda.synchronize()
+        want_y = A.project(torch.as_tensor(x2, device=dev))
+        want_x = A.back_project(want_y)
+        assert O.rel_l2(y.cpu().numpy(), want_y.cpu().numpy()) <= 1e-6
+        assert O.rel_l2(xb.cpu().numpy(), want_x.cpu().numpy()) <= 1e-6
+
+
 def test_3d_paths_selected(torch_dev):
     A = sb.XRayTransform3D((16,) * 3, _x_mats((16,) * 3, (16, 16), 4), (16, 16))
     assert A.plan_info()["path_name"] == "3d_sep" and A.plan_info()["row_aligned"] == 1

@@ -81,7 +81,7 @@ out["C3 2D 4096^2 x 2048 views, view blocks"] = {
     "views_per_rank": A.views[1] - A.views[0], "fwd_ms": f_ms, "adj_ms_reduce_scatter": a_scatter,
     "adj_ms_all_reduce": a_allred, "adj_ms_kernels_only": a_local,
     "pair_updates_per_s": 2 * upd / (f_ms + a_scatter) * 1e3,
-    "exchange": "partial images (64 MB per rank) sum-reduced per row block into the owner (NCCL reduce x world)"}
+    "exchange": "partial images (64 MB per rank): one NCCL reduce_scatter over equal row blocks (per-block reduce when the rows do not divide evenly)"}
 del A, x, y
 torch.cuda.empty_cache()
 
