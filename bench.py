@@ -332,6 +332,11 @@ def main():
     ach_adj = loc_bytes / (adj_ms * 1e-3) / 1e9
     kname = {0: "gen3d", 1: "plane", 2: "walk"}
     prof = ncu_profile()
+
+    def ncu_metric(pattern, label):  # mean of a metric over the captured launches of one kernel family
+        vals = [k[label] for k in prof.get("kernels", []) if pattern in k.get("name", "") and isinstance(k.get(label), float)]
+        return float(np.mean(vals)) if vals else None
+
     fwd_name = (f"walk_forward_joint_kernel<Geom3> (+ walk_forward_kernel for the views within rounding distance of a unit "
                 f"coefficient; {n_fwd_launch} class launches per application)" if info.get("fwd_joint")
                 else f"{kname[info['fwd_kernel']]}_forward_kernel<Geom3> ({n_fwd_launch} launches per application, one per view class)")
@@ -343,7 +348,13 @@ def main():
         "model": "4 B per voxel-view update + 4 B per sinogram element (per-view streaming model the reference executes); "
                  "real DRAM traffic (ncu) is ~1000x lower: the kernels are shared-memory / instruction-issue bound, "
                  "so a fraction above 1 is possible and only says the per-view streaming model is beaten",
-        "adjoint": {"kernel": f"{kname[info['adj_kernel']]}_adjoint_kernel<Geom3> (1 launch per application"
+        # the binding resource under the real traffic (committed ncu --set full capture, profiles/ncu_summary.json)
+        "binding_resource": "instruction issue",
+        "issue_active_pct_ncu": ncu_metric("walk_forward_joint", "issue active %"),
+        "dram_throughput_pct_ncu": ncu_metric("walk_forward_joint", "dram throughput %"),
+        "adjoint": {"issue_active_pct_ncu": ncu_metric("walk_adjoint", "issue active %"),
+                    "dram_throughput_pct_ncu": ncu_metric("walk_adjoint", "dram throughput %"),
+                    "kernel": f"{kname[info['adj_kernel']]}_adjoint_kernel<Geom3> (1 launch per application"
                               + (", TMA-staged sinogram window)" if info.get("adj_tma") else ")"), "achieved": ach_adj,
                     "frac": ach_adj / peak, "launch_ms": adj_ms,
                     "traffic": prof.get("adjoint_traffic_bytes_per_launch_at_bench_size")},
