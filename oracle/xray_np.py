@@ -5,9 +5,17 @@ This file is the *oracle*: a CPU restatement of the algorithm in the reference's
 ``__graft_entry__.smoke()`` and the ``cpu_baseline`` leg of ``bench.py`` can check the
 CUDA path.  Nothing under ``scico_b200/`` may import it.
 
-Pinning status.  JAX is not installable in this image, so the reference itself cannot
-be executed.  The oracle is pinned against every known answer the reference's own
-tests hold for this path (``tests/test_oracle_pins.py``):
+Pinning status.  JAX is not installable in this image, so the reference cannot run on
+its own array library.  Two pins instead:
+
+1. The reference's OWN SOURCE FILES (``_xray2d.py``, ``_xray3d.py``, loaded unmodified from
+   /root/reference) are executed over a NumPy stand-in for the few ``jax`` entry points
+   they use (``oracle/jax_standin.py``); their forward / adjoint results, index and weight
+   arrays are committed as ``tests/golden/ref_*.npz`` and this oracle (and the C port)
+   reproduces them BIT FOR BIT (``tests/test_golden_oracle.py``,
+   ``tests/test_reference_source.py``).
+2. Every known answer the reference's own tests hold for this path
+   (``tests/test_oracle_pins.py``):
 
 * ``scico/test/linop/xray/test_xray_3d.py:29-60``  two exact 4x4 projections,
 * ``scico/test/linop/xray/test_xray_3d.py:9-26``   matched adjoint <= 1e-5,
@@ -15,9 +23,9 @@ tests hold for this path (``tests/test_oracle_pins.py``):
 * ``scico/test/linop/xray/test_xray_2d.py:88-102`` FBP PSNR > 28 dB (4 cases),
 * ``scico/test/linop/xray/astra/test_astra_3d.py:200-222`` geometry known answer.
 
-What is NOT pinned (and cannot be here): XLA's choice of fp32 ``cos``/``sin``, FMA
-contraction and scatter order.  The oracle *defines* those as strict IEEE fp32, no
-contraction, NumPy float32 ``cos``/``sin``.
+What is NOT pinned (and cannot be here): what only XLA decides -- its fp32 ``cos``/``sin``,
+FMA contraction and scatter order.  The oracle (like the stand-in) *defines* those as strict
+IEEE fp32, no contraction, NumPy float32 ``cos``/``sin``.
 
 Every fp32 operation below is written as a separate NumPy float32 op so that rounding
 happens exactly where the reference's expression tree rounds.
@@ -218,11 +226,16 @@ def matrices_from_euler_angles(
         voxel_spacing = np.ones(3)
     if det_spacing is None:
         det_spacing = np.ones(2)
-    R = _euler_to_matrices(seq, angles)
-    M = R[:, :2, :] * np.asarray(voxel_spacing, dtype=np.float64)[None, None, :]
-    M = M / np.asarray(det_spacing, dtype=np.float64)[None, :, None]
-    x0 = np.asarray(input_shape, dtype=np.float64) / 2
-    t = -np.einsum("vmn,n->vm", M, x0) + np.asarray(output_shape, dtype=np.float64) / 2
+    try:  # the reference's own call (_xray3d.py:304) when scipy is importable
+        from scipy.spatial.transform import Rotation
+
+        R = np.asarray(Rotation.from_euler(seq, angles).as_matrix()).reshape(-1, 3, 3)
+    except ImportError:
+        R = _euler_to_matrices(seq, angles)
+    M = np.einsum("vmn,nn->vmn", R[:, :2, :], np.diag(np.asarray(voxel_spacing, dtype=np.float64)))  # :308-314
+    M = np.einsum("mm,vmn->vmn", np.diag(1 / np.asarray(det_spacing, dtype=np.float64)), M)
+    x0 = np.array(input_shape) / 2
+    t = -np.einsum("vmn,n->vm", M, x0) + np.array(output_shape) / 2
     return np.concatenate([M, t[..., None]], axis=2)
 
 

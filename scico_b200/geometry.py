@@ -64,6 +64,13 @@ def euler_matrices(seq: str, angles, degrees: bool = False) -> np.ndarray:
     intrinsic = seq.isupper()
     if not (intrinsic or seq.islower()) or any(ch not in "xyz" for ch in seq.lower()):
         raise ValueError(f"Invalid Euler sequence {seq!r}.")
+    try:  # the reference's own call (_xray3d.py:304): bit-identical matrices when scipy is there
+        from scipy.spatial.transform import Rotation
+
+        return np.asarray(Rotation.from_euler(seq, angles, degrees=degrees).as_matrix(),
+                          dtype=np.float64).reshape(-1, 3, 3)
+    except ImportError:
+        pass
     if degrees:
         angles = np.deg2rad(angles)
     R = np.broadcast_to(np.eye(3), (angles.shape[0], 3, 3)).copy()
@@ -81,9 +88,11 @@ def matrices_from_euler_angles(
     voxel_spacing = np.ones(3) if voxel_spacing is None else np.asarray(voxel_spacing, dtype=np.float64)
     det_spacing = np.ones(2) if det_spacing is None else np.asarray(det_spacing, dtype=np.float64)
     M = euler_matrices(seq, angles, degrees)[:, :2, :]
-    M = M * voxel_spacing[None, None, :] / det_spacing[None, :, None]
-    centre = np.asarray(input_shape, dtype=np.float64) / 2
-    t = -(M @ centre) + np.asarray(output_shape, dtype=np.float64) / 2
+    # the reference's own NumPy expressions (_xray3d.py:308-325), so that every entry rounds the same way
+    M = np.einsum("vmn,nn->vmn", M, np.diag(voxel_spacing))
+    M = np.einsum("mm,vmn->vmn", np.diag(1 / det_spacing), M)
+    centre = np.array(input_shape) / 2
+    t = -np.einsum("vmn,n->vm", M, centre) + np.array(output_shape) / 2
     return np.concatenate([M, t[..., None]], axis=2)
 
 

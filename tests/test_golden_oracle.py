@@ -1,4 +1,8 @@
-"""The committed golden fixtures must be reproduced bit-for-bit by both oracles (CPU only)."""
+"""The committed golden fixtures must be reproduced bit-for-bit by both oracles (CPU only).
+
+Two families: ``xray*.npz`` were made from the oracle itself (``make_golden.py``); ``ref*.npz`` were
+made by the REFERENCE'S OWN SOURCE executed over a NumPy stand-in for jax
+(``make_reference_golden.py``, ``oracle/jax_standin.py``) -- those pin the restatement."""
 import glob
 import os
 
@@ -13,17 +17,35 @@ FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
 
 
 def test_fixture_inventory():
-    assert len(FILES) == 8
+    assert len(FILES) == 19
+    assert sum(os.path.basename(f).startswith("ref") for f in FILES) == 11
+
+
+def _table(g):
+    if "table" in g.files:
+        return g["table"]
+    return O.view_table_2d(g["angles"], g["x0"], g["dx"], float(g["y0"]))
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
 def test_oracles_reproduce_golden(path):
     g = np.load(path)
     if str(g["kind"]) == "2d":
-        nx, ny, T = tuple(g["nx"]), int(g["det_count"]), g["table"]
+        nx, ny, T = tuple(g["nx"]), int(g["det_count"]), _table(g)
         for impl in (O, C):
             np.testing.assert_array_equal(impl.project_2d(g["x"], T, ny), g["Ax"])
             np.testing.assert_array_equal(impl.back_project_2d(g["y"], T, nx), g["ATy"])
+        if "inds" in g.files:  # the reference's own _calc_weights arrays (_xray2d.py:308-351)
+            inds, weights = O.calc_weights_2d(T, nx)
+            np.testing.assert_array_equal(inds, g["inds"])
+            np.testing.assert_array_equal(weights, g["weights"])
+            for v in range(len(T)):
+                ci, cw = C.weights_2d(T[v], nx)
+                np.testing.assert_array_equal(ci, g["inds"][v])
+                np.testing.assert_array_equal(cw, g["weights"][v])
+        if "fbp" in g.files:  # _xray2d.py:158-197 (FFT round-off differs between libraries: not bitwise)
+            got = O.fbp_2d(g["y"], T, nx, tuple(g["dx"]))
+            assert O.rel_l2(got, g["fbp"]) <= 1e-5
     else:
         N, D, M = tuple(g["N"]), tuple(g["D"]), g["matrices"].astype(np.float32)
         for impl in (O, C):
