@@ -66,6 +66,27 @@ struct Geom2 {
   static __device__ __forceinline__ float combine(const ViewRec&, float hA, float hB) {
     return __fadd_rn(hA, hB);
   }
+  // Two rows at once with the packed fp32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: each
+  // component is the IEEE round-to-nearest result, bit-identical to the scalar expression below;
+  // fl - u is the exact negation of u - fl, so 1 + (fl - u) == 1 - (u - fl) bit for bit).
+  // CAUTION: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (it does NOT do that to the
+  // scalar .rn forms), so a packed product must never feed a packed sum where the reference rounds
+  // twice: the row term off + ca * a stays scalar.
+  static __device__ __forceinline__ float2 hoistA2(const ViewRec& v, float2 xa) {
+    return make_float2(hoistA_x(v, xa.x), hoistA_x(v, xa.y));
+  }
+  static __device__ __forceinline__ void bins2(const ViewRec& v, float2 u, int& c0, int& c1, float2& w0, float2& w1) {
+    const float2 fl = make_float2(floorf(u.x), floorf(u.y));
+    c0 = __float2int_rd(u.x);
+    c1 = __float2int_rd(u.y);
+    const float2 one = make_float2(1.0f, 1.0f), wd = make_float2(v.width, v.width), rw = make_float2(v.rwidth, v.rwidth);
+    const float2 d = __fadd2_rn(one, __fadd2_rn(fl, make_float2(-u.x, -u.y)));
+    const float2 m = make_float2(fminf(d.x, v.width), fminf(d.y, v.width));
+    const float2 q = __fmul2_rn(m, rw);
+    const float2 e = __ffma2_rn(make_float2(-q.x, -q.y), wd, m);
+    w0 = __ffma2_rn(e, rw, q);
+    w1 = __fadd2_rn(one, make_float2(-w0.x, -w0.y));
+  }
   // inds = floor(Px); weights = min(1 - (Px - inds), width) / width   (_xray2d.py:338,348-349)
   static __device__ __forceinline__ void bins(const ViewRec& v, float u, int& c, float& w0, float& w1) {
     float fl = floorf(u);
