@@ -46,7 +46,8 @@ constexpr int kFwd3S = 2, kFwd3TN = 16;
 constexpr int kFwd2S = 1, kFwd2TN = 16;
 // walk kernels (xct_plane2.cuh)
 constexpr int kWAdjS = 8, kWAdjTA = 8, kWAdjWin = 64, kWAdjStages = 3;
-constexpr int kWFwdS = 4, kWFwdTN = 8;  // walk forward tile: 64 (major) x 8 (minor) x 4 slices
+constexpr int kWFwdS = 4, kWFwdTN = 8;
+constexpr int kW2dTN = 8, kW2dWin = 160;  // 2D joint forward tile: 128 (major) x 8 (minor), one image  // walk forward tile: 64 (major) x 8 (minor) x 4 slices
 
 }  // namespace
 
@@ -79,6 +80,7 @@ struct xct_plan {
   // joint-column walk forward: views with fjump == 0 by [4*major_b + 2*minor_up + major_positive],
   // the remaining ("risky") views by [2*major_b + minor_up] for walk_forward_kernel
   bool fwd_joint = false;
+  bool fwd_joint2d = false;  // 2D: every view inside walk2d_forward_joint_kernel's envelope
   int* d_listJ[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int n_listJ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int* d_listR[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -446,6 +448,41 @@ int launch_walk_forward_v(const xct_plan* pl, int batch, const float* in, float*
   return launch_walk_forward_class<G, IS3D, S, TN, 2, false, false, COLD, UNIT4>(pl, batch, in, out, st, s_begin, s_count, risky_only);
 }
 
+// 2D joint-pair forward: one launch per (major axis, minor sign, major sign) class
+template <bool MAJOR_B, bool MINOR_UP, bool MAJ_POS>
+int launch_walk2d_forward_class(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+  const int cls = (MAJOR_B ? 4 : 0) + (MINOR_UP ? 2 : 0) + (MAJ_POS ? 1 : 0);
+  if (pl->n_listJ[cls] == 0) return XCT_OK;
+  xct::PlaneParams p = plane_params(pl, batch);
+  p.view_list = pl->d_listJ[cls];
+  p.n_list = pl->n_listJ[cls];
+  p.tilesA = ceil_div(p.NA, MAJOR_B ? kW2dTN : 128);
+  p.tilesB = ceil_div(p.NB, MAJOR_B ? 128 : kW2dTN);
+  const long long tasks = (long long)p.NS * p.tilesA * p.tilesB;
+  const int blocks = ceil_div(tasks, kWarps);
+  const long long target_warps = 148LL * 32;
+  int chunks = 1;
+  if (tasks < target_warps) chunks = (int)std::min<long long>((target_warps + tasks - 1) / tasks, std::max(1, p.n_list / 4));
+  p.views_per_chunk = ceil_div(p.n_list, chunks);
+  chunks = ceil_div(p.n_list, p.views_per_chunk);
+  const size_t smem = (size_t)kWarps * kW2dWin * sizeof(float);
+  xct::walk2d_forward_joint_kernel<xct::Geom2, kW2dTN, kW2dWin, MAJOR_B, MINOR_UP, MAJ_POS, kWarps>
+      <<<dim3(blocks, chunks), kWarps * 32, smem, st>>>(p, in, out);
+  return launch_ok("walk2d_forward_joint_kernel");
+}
+
+int launch_walk2d_forward(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+  int rc;
+  if ((rc = launch_walk2d_forward_class<true, true, true>(pl, batch, in, out, st))) return rc;
+  if ((rc = launch_walk2d_forward_class<true, true, false>(pl, batch, in, out, st))) return rc;
+  if ((rc = launch_walk2d_forward_class<true, false, true>(pl, batch, in, out, st))) return rc;
+  if ((rc = launch_walk2d_forward_class<true, false, false>(pl, batch, in, out, st))) return rc;
+  if ((rc = launch_walk2d_forward_class<false, true, true>(pl, batch, in, out, st))) return rc;
+  if ((rc = launch_walk2d_forward_class<false, true, false>(pl, batch, in, out, st))) return rc;
+  if ((rc = launch_walk2d_forward_class<false, false, true>(pl, batch, in, out, st))) return rc;
+  return launch_walk2d_forward_class<false, false, false>(pl, batch, in, out, st);
+}
+
 int launch_walk_forward_joint(const xct_plan* pl, const float* in, float* out, cudaStream_t st, int s_begin, int s_count) {
   int rc;
   if ((rc = launch_walk_forward_joint_class<true, true, true>(pl, in, out, st, s_begin, s_count))) return rc;
@@ -560,6 +597,11 @@ int xct2d_plan_create(xct_plan** out, const xct2d_geom* g) {
     xct::ViewRec r{};
     r.off = t[0]; r.ca = t[1]; r.cb = t[2]; r.width = t[3];
     r.rwidth = 1.0f / t[3];
+    {  // same rounding margin as the 3D walk kernels: the bin may advance by two only above 1 - 5 ulp(u)
+      const float umax = std::fabs(r.ca) * g->n0 + std::fabs(r.cb) * g->n1 + std::fabs(r.off) + 2.f;
+      const float ulp = std::ldexp(1.f, std::ilogb(umax) - 23);
+      r.fjump = (std::max(std::fabs(r.ca), std::fabs(r.cb)) + 5.f * ulp > 1.f) ? 1.f : 0.f;
+    }
     if (!(std::isfinite(t[0]) && std::isfinite(t[1]) && std::isfinite(t[2]) && t[3] > 0.f)) finite = false;
     views[v] = r;
   }
@@ -573,6 +615,15 @@ int xct2d_plan_create(xct_plan** out, const xct2d_geom* g) {
   pl->fwd_plane = env.fwd_ok && !force_general;
   pl->gs = pl->fwd_plane ? env.gs : 0;
   pl->path = (pl->adj_plane && pl->fwd_plane) ? XCT_PATH_2D_PLANE : XCT_PATH_2D_GENERAL;
+  {  // joint-pair forward: lanes 4 voxels apart must land >= 1 bin apart, the window must hold the tile
+    bool ok = pl->fwd_plane && !(g->flags & (XCT_FLAG_NO_WALK | XCT_FLAG_NO_JOINT));
+    for (const auto& vr : views) {
+      const float a = std::fabs(vr.ca), b = std::fabs(vr.cb);
+      const float mj = std::max(a, b), mn = std::min(a, b);
+      if (vr.fjump != 0.f || 4.f * mj < 1.01f || mj * 127.f + mn * (kW2dTN - 1) + 4.f > (float)kW2dWin) ok = false;
+    }
+    pl->fwd_joint2d = ok;
+  }
 
   auto cleanup = [&](int code) { xct_plan_destroy(pl); return code; };
   cudaError_t e = cudaMalloc(&pl->d_views, sizeof(xct::ViewRec) * views.size());
@@ -780,8 +831,8 @@ int xct_plan_get_info(const xct_plan* pl, xct_plan_info* info) {
   info->row_aligned = pl->row_aligned ? 1 : 0;
   info->device = pl->device;
   info->adj_kernel = pl->adj_walk ? XCT_KERNEL_WALK : (pl->adj_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL);
-  info->fwd_kernel = pl->fwd_walk ? XCT_KERNEL_WALK : (pl->fwd_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL);
-  info->fwd_joint = pl->fwd_joint ? 1 : 0;
+  info->fwd_kernel = (pl->fwd_walk || pl->fwd_joint2d) ? XCT_KERNEL_WALK : (pl->fwd_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL);
+  info->fwd_joint = (pl->fwd_joint || pl->fwd_joint2d) ? 1 : 0;
   info->adj_tma = pl->adj_tma ? 1 : 0;
   info->in_elems = (int64_t)in_elems(pl);
   info->out_elems = (int64_t)out_elems(pl);
@@ -802,6 +853,7 @@ int xct_forward(const xct_plan* pl, const float* in, float* out, int32_t batch, 
     xct::gen3d_forward_kernel<<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, out);
     return launch_ok("gen3d_forward_kernel");
   }
+  if (pl->fwd_joint2d) return launch_walk2d_forward(pl, batch, in, out, st);
   if (pl->fwd_plane) return launch_plane_forward<xct::Geom2, false, kFwd2S, kFwd2TN>(pl, batch, in, out, st);
   xct::gen2d_forward_kernel<<<general_grid(in_elems(pl) * batch), 256, 0, st>>>(gen2_params(pl, batch), in, out);
   return launch_ok("gen2d_forward_kernel");

@@ -705,4 +705,114 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
   }
 }
 
+// ----------------------------------------------------------------- 2D forward, joint column pairs
+// The joint-column walk for a single 2D image (S = 1, nothing to amortise coordinates over): a lane
+// owns FOUR major-axis columns, i.e. two adjacent pairs, 4 voxels apart from its neighbour lane
+// (bins >= 2 apart for the reference's default pixel size, |c_major| in [0.5, 0.71]: plain RMW, no
+// atomics).  Each pair is walked along the minor axis with three carried bin sums exactly like
+// walk_forward_joint_kernel (F on bins (t, t+1), G on (t+e, t+e+1), e in {0, 1}), the two columns'
+// coordinates and weights evaluated in packed fp32 (component-wise identical to Geom2's scalar
+// expressions; the row / column products stay scalar, see the CAUTION in xct_geom.cuh).  Against
+// plane_forward_kernel (one RMW of an (A, B) slot pair per voxel, half of its shared wavefronts
+// bank-conflict replays) the shared traffic drops to one RMW per bin change.
+// Window: WIN bins (floats) per warp; flushed with scalar RED (2D rows have no 16-byte alignment).
+// Only for plans whose every view has |coefficients| <= 1 - 5 ulp(u) (ViewRec::fjump == 0).
+template <class G, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+walk2d_forward_joint_kernel(PlaneParams p, const float* __restrict__ in, float* __restrict__ sino) {
+  static_assert(WIN % 32 == 0, "window is flushed 32 bins at a time");
+  constexpr int GS = 4, TM = 32 * GS, Q = WIN / 32;
+  extern __shared__ __align__(128) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long ntasks = (long long)p.NS * p.tilesA * p.tilesB;
+  long long task = (long long)blockIdx.x * WARPS + warp;
+  if (task >= ntasks) return;
+  const int tb_ = (int)(task % p.tilesB);
+  task /= p.tilesB;
+  const int ta = (int)(task % p.tilesA);
+  const int sl = (int)(task / p.tilesA);  // image of the batch
+  const int a0 = ta * (MAJOR_B ? TN : TM), b0 = tb_ * (MAJOR_B ? TM : TN);
+  float* win = smem + (size_t)warp * WIN;
+
+  float x[GS][TN];
+#pragma unroll
+  for (int d = 0; d < GS; ++d)
+#pragma unroll
+    for (int n = 0; n < TN; ++n) {
+      const int a = MAJOR_B ? a0 + n : a0 + GS * lane + d;
+      const int b = MAJOR_B ? b0 + GS * lane + d : b0 + n;
+      x[d][n] = (a < p.NA && b < p.NB) ? __ldg(in + ((size_t)sl * p.NA + a) * (size_t)p.NB + b) : 0.f;
+    }
+  const float xmin0 = MAJOR_B ? G::coordA(a0) : G::coordB(b0);
+
+  auto rmw = [&](int t, float v) { win[t] += v; };  // one lane per address
+
+  const int v_begin = blockIdx.y * p.views_per_chunk;
+  const int v_end = min(p.n_list, v_begin + p.views_per_chunk);
+  for (int vi = v_begin; vi < v_end; ++vi) {
+    const int v = p.view_list ? __ldg(p.view_list + vi) : vi;
+    const ViewRec vr = load_view(p.views + v);
+    const int c0 = window_start<G>(vr, a0, a0 + (MAJOR_B ? TN : TM) - 1, b0, b0 + (MAJOR_B ? TM : TN) - 1);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) win[lane + 32 * q] = 0.f;
+    __syncwarp();
+
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {  // the lane's two column pairs
+      constexpr int DF0 = MAJ_POS ? 0 : 1;
+      const int dF = 2 * pr + DF0, dG = 2 * pr + (1 - DF0);
+      const float hF = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + dF) : G::hoistA(vr, a0 + GS * lane + dF);
+      const float hG = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + dG) : G::hoistA(vr, a0 + GS * lane + dG);
+      const float2 hFG = make_float2(hF, hG);
+      float A0 = 0.f, A1 = 0.f, A2 = 0.f;  // sums of bins tb, tb + 1, tb + 2
+      int tb = 0;
+#pragma unroll
+      for (int n = 0; n < TN; ++n) {
+        const float xm = xmin0 + (float)n;
+        const float hm = MAJOR_B ? G::hoistA_x(vr, xm) : G::hoistB_x(vr, xm);
+        const float2 u = __fadd2_rn(hFG, make_float2(hm, hm));  // Geom2::combine: hA + hB (commutative)
+        int cF, cG;
+        float2 w0, w1;
+        G::bins2(vr, u, cF, cG, w0, w1);
+        const int tF = (int)min((unsigned)(cF - c0), (unsigned)(WIN - 3));
+        const bool e = cG != cF;  // G one bin further
+        const float wa = e ? 0.f : w0.y, wb = e ? w0.y : w1.y, wc = e ? w1.y : 0.f;
+        const float xF = x[dF][n], xG = x[dG][n];
+        if (n == 0) {
+          tb = tF;
+          A0 = fmaf(xG, wa, xF * w0.x);
+          A1 = fmaf(xG, wb, xF * w1.x);
+          A2 = xG * wc;
+        } else {
+          if (tF != tb) {  // F moved by one bin: the bin leaving the carried triple is complete for this walk
+            if (MINOR_UP) { rmw(tb, A0); A0 = A1; A1 = A2; A2 = 0.f; }
+            else { rmw(tb + 2, A2); A2 = A1; A1 = A0; A0 = 0.f; }
+            tb = tF;
+          }
+          __syncwarp();  // order this step's stores before the next step's loads of other lanes
+          A0 = fmaf(xG, wa, fmaf(xF, w0.x, A0));
+          A1 = fmaf(xG, wb, fmaf(xF, w1.x, A1));
+          A2 = fmaf(xG, wc, A2);
+        }
+      }
+      rmw(tb, A0);
+      __syncwarp();
+      rmw(tb + 1, A1);
+      __syncwarp();
+      rmw(tb + 2, A2);
+      __syncwarp();
+    }
+
+    float* y0 = sino + ((size_t)sl * p.V + v) * (size_t)p.D1;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int t = lane + 32 * q;
+      const float val = win[t];
+      const int col = c0 + t;
+      if (val != 0.f && (unsigned)col < (unsigned)p.D1) atomicAdd(y0 + col, val);
+    }
+    __syncwarp();  // all window reads done before the next view zeroes it
+  }
+}
+
 }  // namespace xct

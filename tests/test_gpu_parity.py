@@ -225,6 +225,40 @@ def test_pair_is_cuda_graph_capturable(torch_dev):
         assert O.rel_l2(xb.cpu().numpy(), want_x.cpu().numpy()) <= 1e-6
 
 
+def test_2d_joint_forward_matches_plane_kernel_and_oracle(torch_dev):
+    """walk2d_forward_joint_kernel (a lane walks two column pairs, three carried bins each) against the
+    per-voxel plane kernel and the oracle: a full turn (all eight view classes), ragged tiles, an
+    anisotropic pixel, a short detector, a batch; pixels wider than the envelope fall back."""
+    torch, dev = torch_dev
+    rng = np.random.default_rng(44)
+    for nx, angles, kw in (
+        ((150, 140), np.linspace(0, 2 * np.pi, 24, endpoint=False), {}),
+        ((70, 131), np.linspace(0.01, 2 * np.pi + 0.01, 17, endpoint=False), dict(dx=(0.6, 0.7))),
+        ((64, 64), np.array([0.0, np.pi / 2, np.pi / 4, 3 * np.pi / 4, 1e-4, np.pi / 2 - 1e-4, 2.0]), {}),
+        ((96, 80), np.linspace(0, np.pi, 30, endpoint=False), dict(det_count=90)),
+        ((33, 130), np.linspace(0, np.pi, 9, endpoint=False), dict(dx=0.95)),
+    ):
+        A = sb.XRayTransform2D(nx, angles, **kw)
+        B = sb.XRayTransform2D(nx, angles, _flags=_lib.FLAG_NO_JOINT, **kw)
+        assert A.plan_info()["fwd_joint"] == 1 and B.plan_info()["fwd_joint"] == 0
+        x = rng.standard_normal(nx).astype(np.float32)
+        a, b = _gpu(torch, dev, A, x), _gpu(torch, dev, B, x)
+        ref = C.project_2d(x, A.view_table, A.ny)
+        assert O.rel_l2(a, b) <= 2e-6
+        for v in range(len(angles)):
+            assert O.rel_l2(a[v], ref[v]) <= TOL, v
+    A = sb.XRayTransform2D((40, 150), np.linspace(0, np.pi, 11, endpoint=False))
+    xb = rng.standard_normal((3, 40, 150)).astype(np.float32)
+    got = A.project(torch.as_tensor(xb, device=dev)).cpu().numpy()  # leading batch axis (the reference's vmap use)
+    for k in range(3):
+        assert O.rel_l2(got[k], C.project_2d(xb[k], A.view_table, A.ny)) <= TOL
+    with pytest.warns(UserWarning):  # projected pixel wider than a bin: a coefficient can exceed 1
+        W = sb.XRayTransform2D((48, 48), np.linspace(0, np.pi, 8, endpoint=False), dx=1.2)
+    assert W.plan_info()["fwd_joint"] == 0
+    x = rng.standard_normal((48, 48)).astype(np.float32)
+    assert O.rel_l2(_gpu(torch, dev, W, x), C.project_2d(x, W.view_table, W.ny)) <= TOL
+
+
 def test_3d_paths_selected(torch_dev):
     A = sb.XRayTransform3D((16,) * 3, _x_mats((16,) * 3, (16, 16), 4), (16, 16))
     assert A.plan_info()["path_name"] == "3d_sep" and A.plan_info()["row_aligned"] == 1
