@@ -39,6 +39,18 @@ struct Geom3 {
   static __device__ __forceinline__ float combine(const ViewRec& v, float hA, float hB) {
     return __fadd_rn(__fadd_rn(__fadd_rn(hA, hB), v.off), -0.25f);
   }
+  // Two coordinates at once in packed fp32 (component-wise the IEEE round-to-nearest sums of combine /
+  // bins; the products hA, hB stay scalar: ptxas would contract a packed product into a packed sum)
+  static __device__ __forceinline__ float2 combine2(const ViewRec& v, float2 hA, float2 hB) {
+    return __fadd2_rn(__fadd2_rn(__fadd2_rn(hA, hB), make_float2(v.off, v.off)), make_float2(-0.25f, -0.25f));
+  }
+  static __device__ __forceinline__ void bins2(const ViewRec&, float2 u, int& c0, int& c1, float2& w0, float2& w1) {
+    c0 = __float2int_rd(u.x);
+    c1 = __float2int_rd(u.y);
+    const float2 d = __fadd2_rn(make_float2(ceilf(u.x), ceilf(u.y)), make_float2(-u.x, -u.y));
+    w0 = make_float2(fminf(d.x, 0.5f), fminf(d.y, 0.5f));
+    w1 = __fadd2_rn(make_float2(0.5f, 0.5f), make_float2(-w0.x, -w0.y));
+  }
   // c = floor(left); w0 = to_next = min(ceil(left)-left, 0.5) (0 when left is an integer,
   // _xray3d.py:224); w1 = 0.5 - to_next.  The common factor 1/w^2 = 4 lives in the row weights.
   static __device__ __forceinline__ void bins(const ViewRec&, float u, int& c, float& w0, float& w1) {

@@ -193,12 +193,17 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
     constexpr bool COLD = decltype(cold_c)::value;
     float2 lo[H], hi[H];
     int tp = 0;
+    static_assert(TA % 2 == 0, "rows are evaluated in pairs");
+    int cc[2];
+    float2 ww0, ww1;
 #pragma unroll
     for (int n = 0; n < TA; ++n) {
-      const float u = G::combine(vr, G::hoistA_x(vr, xa0 + (float)n), hB);
-      int c;
-      float w0, w1;
-      G::bins(vr, u, c, w0, w1);
+      if ((n & 1) == 0) {  // coordinates and weights of rows n, n + 1 in packed fp32
+        const float2 hA = make_float2(G::hoistA_x(vr, xa0 + (float)n), G::hoistA_x(vr, xa0 + (float)(n + 1)));
+        G::bins2(vr, G::combine2(vr, hA, make_float2(hB, hB)), cc[0], cc[1], ww0, ww1);
+      }
+      const int c = cc[n & 1];
+      const float w0 = (n & 1) ? ww0.y : ww0.x, w1 = (n & 1) ? ww1.y : ww1.x;
       const int t = (int)min((unsigned)(c - c0), (unsigned)(WIN - 2));
       const float* z = zb + t;
       if (n == 0) {
