@@ -88,9 +88,11 @@ struct Geom2 {
     return make_float2(hoistA_x(v, xa.x), hoistA_x(v, xa.y));
   }
   static __device__ __forceinline__ void bins2(const ViewRec& v, float2 u, int& c0, int& c1, float2& w0, float2& w1) {
-    const float2 fl = make_float2(floorf(u.x), floorf(u.y));
     c0 = __float2int_rd(u.x);
     c1 = __float2int_rd(u.y);
+    // floor(u) as a float from the integer (I2FP, ALU pipe) instead of a second XU-pipe rounding op:
+    // exact for |u| < 2^24, far beyond any detector (the 2D adjoint ran the XU pipe at 71 %)
+    const float2 fl = make_float2(__int2float_rn(c0), __int2float_rn(c1));
     const float2 one = make_float2(1.0f, 1.0f), wd = make_float2(v.width, v.width), rw = make_float2(v.rwidth, v.rwidth);
     const float2 d = __fadd2_rn(one, __fadd2_rn(fl, make_float2(-u.x, -u.y)));
     const float2 m = make_float2(fminf(d.x, v.width), fminf(d.y, v.width));
@@ -101,8 +103,8 @@ struct Geom2 {
   }
   // inds = floor(Px); weights = min(1 - (Px - inds), width) / width   (_xray2d.py:338,348-349)
   static __device__ __forceinline__ void bins(const ViewRec& v, float u, int& c, float& w0, float& w1) {
-    float fl = floorf(u);
     c = __float2int_rd(u);
+    float fl = __int2float_rn(c);  // == floorf(u) for |u| < 2^24 (see bins2)
     float m = fminf(__fadd_rn(1.0f, -__fadd_rn(u, -fl)), v.width);
     // correctly rounded m/width from the host-rounded reciprocal plus one Markstein step
     float q = __fmul_rn(m, v.rwidth);
