@@ -71,6 +71,19 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
         : "memory");
   } while (!done);
 }
+// one elected lane of a converged warp (elect.sync: lets ptxas issue the uniform-datapath TMA
+// instruction directly instead of looping over the lanes that might hold different operands)
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // box (x: WIN bins, y: S rows, z: 1 view) of the (V, D0, D1) sinogram -> shared; out-of-bounds
 // elements (negative bins, bins >= D1, rows outside [0, D0)) arrive as zeros
 __device__ __forceinline__ void tma_load_3d(unsigned smem_dst, const CUtensorMap* tmap, int x, int y, int z, unsigned bar) {
@@ -176,7 +189,7 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
   auto fetch_tma = [&](int v, int stage) {
     const ViewRec vr = load_view(p.views + v);
     const int c0 = window_start4<G>(vr, a0, a0 + TA - 1, b0, b0 + 31);
-    if (lane == 0) {
+    if (elect_one()) {
       const unsigned bar = bars_sa + 8u * stage;
       mbar_expect_tx(bar, S * WIN * (unsigned)sizeof(float));
       tma_load_3d(ring_sa + stage * (S * WIN * (unsigned)sizeof(float)), &tmap, c0, row_base + vr.krow, v, bar);
