@@ -145,6 +145,7 @@ Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fw
   Envelope env;
   float min_major = 1e30f;
   std::vector<int> zero_minor[2];
+  std::vector<int> zero_minor_j[4];  // joint lists: [2*major_b + major_positive]
   for (size_t v = 0; v < views.size(); ++v) {
     const float a = std::fabs(views[v].ca), b = std::fabs(views[v].cb);
     if (!std::isfinite(a) || !std::isfinite(b)) {
@@ -163,14 +164,28 @@ Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fw
     {
       const float major = major_b ? views[v].cb : views[v].ca;
       const int up = minor >= 0.f ? 1 : 0;
-      if (views[v].fjump == 0.f) env.listJ[(major_b ? 4 : 0) + 2 * up + (major > 0.f ? 1 : 0)].push_back((int)v);
-      else env.listR[(major_b ? 2 : 0) + up].push_back((int)v);
+      // joint-column kernel: safe views, and views whose MAJOR coefficient alone is near (or up to 1.5x)
+      // a bin per voxel (per-view E2 variant); a minor coefficient that can reach 1 stays on the 2-bin walk
+      // (fjump: 0 = every bin step is at most one, 1 = only the major coefficient is near / above one bin
+      // per voxel, up to 1.5: the kernel's per-view E2 variant, 2 = the minor coefficient can reach 1 too)
+      if (views[v].fjump < 2.f) {
+        if (minor == 0.f) zero_minor_j[(major_b ? 2 : 0) + (major > 0.f ? 1 : 0)].push_back((int)v);  // either sign class
+        else env.listJ[(major_b ? 4 : 0) + 2 * up + (major > 0.f ? 1 : 0)].push_back((int)v);
+      } else {
+        env.listR[(major_b ? 2 : 0) + up].push_back((int)v);
+      }
     }
     min_major = std::min(min_major, std::max(a, b));
   }
   for (int m = 0; m < 2; ++m) {  // views with a zero minor coefficient join the larger sign class
     auto& dst = env.list4[2 * m + (env.list4[2 * m + 1].size() >= env.list4[2 * m].size() ? 1 : 0)];
     dst.insert(dst.end(), zero_minor[m].begin(), zero_minor[m].end());
+    std::sort(dst.begin(), dst.end());
+  }
+  for (int m = 0; m < 4; ++m) {  // joint lists: a view without bin movement joins the larger sign class (no launch of its own)
+    const int base = (m >> 1) * 4 + (m & 1);  // 4*major_b + major_positive, minor_up adds 2
+    auto& dst = env.listJ[base + (env.listJ[base + 2].size() >= env.listJ[base].size() ? 2 : 0)];
+    dst.insert(dst.end(), zero_minor_j[m].begin(), zero_minor_j[m].end());
     std::sort(dst.begin(), dst.end());
   }
   // lanes GS voxels apart along the major axis must land >= 1 bin apart
@@ -682,7 +697,10 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       const float umax = std::fabs(r.ca) * g->n1 + std::fabs(r.cb) * g->n2 + std::fabs(r.off) + 2.f;
       const float ulp = std::ldexp(1.f, std::ilogb(umax) - 23);
       r.jump = (std::fabs(r.ca) + 5.f * ulp > 1.f) ? 1.f : 0.f;
-      r.fjump = (std::max(std::fabs(r.ca), std::fabs(r.cb)) + 5.f * ulp > 1.f) ? 1.f : 0.f;
+      {
+        const float mj = std::max(std::fabs(r.ca), std::fabs(r.cb)), mn = std::min(std::fabs(r.ca), std::fabs(r.cb));
+        r.fjump = mj + 5.f * ulp <= 1.f ? 0.f : ((mn + 5.f * ulp <= 1.f && mj <= 1.5f) ? 1.f : 2.f);
+      }
       views[v] = r;
     }
     Envelope env = analyse_views(views, kAdj3TA, kFwd3TN);

@@ -17,7 +17,8 @@ struct __align__(16) ViewRec {
   float width;   // 2D: projected pixel width                             3D: unused
   float rwidth;  // 2D: 1/width (correctly rounded)                       3D: unused
   float jump;    // walk adjoint: != 0 when rounding can move the bin by two per row step (|ca| ~ 1)
-  float fjump;   // walk forward: != 0 when some coefficient is within rounding distance of 1 (or above)
+  float fjump;   // walk forward: 0 = bins move by <= 1 per step; 1 = the major coefficient alone is within
+                 // rounding distance of 1 (or up to 1.5): joint kernel's E2 variant; 2 = minor too: 2-bin walk
   int krow;      // walk adjoint (TMA): local detector row of slice i is i + krow in this view
 };
 

@@ -548,9 +548,10 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
 // (t+e, t+e+1) with e in {0, 1}, so both fit bins t .. t+2.  One shared-memory read-modify-write
 // per bin change then serves both columns: the shared-memory wavefronts that bound
 // walk_forward_kernel (ncu: 14 per walk step, 39 % of them bank-conflict replays) drop by ~45 %.
-// Only for views whose bins provably move by at most one per step in both directions
-// (ViewRec::fjump == 0, decided on the host with a rounding margin); the other views of a plan go
-// through walk_forward_kernel.  3D unit-row geometry with the 16-byte vector flush only.
+// Views whose MAJOR coefficient is within rounding distance of 1 (ViewRec::fjump != 0, decided on the
+// host with a rounding margin; up to 1.5) take a per-view variant in which G may land two bins after F.
+// Only views whose MINOR coefficient can reach 1 as well (never the case for a rotation) go through
+// walk_forward_kernel.  3D unit-row geometry with the 16-byte vector flush only.
 // MAJ_POS: the major-axis coefficient is positive (F is the lane's first column).
 // KROW: in every view the local detector row of slice i is i + ViewRec::krow (or outside the
 // detector), so the flush derives its four row pointers from one base instead of four table loads.
@@ -632,59 +633,85 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
 
     const float hF = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + DF) : G::hoistA(vr, a0 + GS * lane + DF);
     const float hG = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + DG) : G::hoistA(vr, a0 + GS * lane + DG);
-    float2 A0[H], A1[H], A2[H];  // sums of bins tb, tb + 1, tb + 2
-    int tb = 0;
+    // E2 (per view, warp-uniform: ViewRec::fjump): the major-axis coefficient is within rounding
+    // distance of 1 (or up to 1.5), so G can land TWO bins after F.  Those rare points bypass the
+    // carried triple and add G's two taps to the window directly (lanes sit >= 1 bin apart, so the
+    // lanes that do it in one instruction still touch distinct bins); everything else is unchanged.
+    auto walk_view = [&](auto e2_c) {
+      constexpr bool E2 = decltype(e2_c)::value;
+      float2 A0[H], A1[H], A2[H];  // sums of bins tb, tb + 1, tb + 2
+      int tb = 0;
 #pragma unroll
-    for (int n = 0; n < TN; ++n) {
-      const float xm = xmin0 + (float)n;
-      const float hm = MAJOR_B ? G::hoistA_x(vr, xm) : G::hoistB_x(vr, xm);
-      const float uF = MAJOR_B ? G::combine(vr, hm, hF) : G::combine(vr, hF, hm);
-      const float uG = MAJOR_B ? G::combine(vr, hm, hG) : G::combine(vr, hG, hm);
-      int cF, cG;
-      float wF0, wF1, wG0, wG1;
-      G::bins(vr, uF, cF, wF0, wF1);
-      G::bins(vr, uG, cG, wG0, wG1);
-      const int tF = (int)min((unsigned)(cF - c0), (unsigned)(WIN - 3));
-      const bool e = cG != cF;  // G one bin further
-      const float wa = e ? 0.f : wG0, wb = e ? wG0 : wG1, wc = e ? wG1 : 0.f;
-      const float2 wF0p = make_float2(wF0, wF0), wF1p = make_float2(wF1, wF1);
-      const float2 wap = make_float2(wa, wa), wbp = make_float2(wb, wb), wcp = make_float2(wc, wc);
-      if (n == 0) {
-        tb = tF;
+      for (int n = 0; n < TN; ++n) {
+        const float xm = xmin0 + (float)n;
+        const float hm = MAJOR_B ? G::hoistA_x(vr, xm) : G::hoistB_x(vr, xm);
+        const float uF = MAJOR_B ? G::combine(vr, hm, hF) : G::combine(vr, hF, hm);
+        const float uG = MAJOR_B ? G::combine(vr, hm, hG) : G::combine(vr, hG, hm);
+        int cF, cG;
+        float wF0, wF1, wG0, wG1;
+        G::bins(vr, uF, cF, wF0, wF1);
+        G::bins(vr, uG, cG, wG0, wG1);
+        const int tF = (int)min((unsigned)(cF - c0), (unsigned)(WIN - (E2 ? 4 : 3)));
+        const bool e = cG != cF;  // G one bin further
+        if (E2) {
+          const bool far = cG - cF >= 2;
+          if (__any_sync(0xffffffffu, far)) {
+            if (far) {
+              float2 g0[H], g1[H];
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-          A0[h] = __ffma2_rn(x[DG][n][h], wap, __fmul2_rn(x[DF][n][h], wF0p));
-          A1[h] = __ffma2_rn(x[DG][n][h], wbp, __fmul2_rn(x[DF][n][h], wF1p));
-          A2[h] = __fmul2_rn(x[DG][n][h], wcp);
-        }
-      } else {
-        if (tF != tb) {  // F moved by one bin: the bin leaving the carried triple is complete for this walk
-          if (MINOR_UP) {
-            rmw(tb, A0);
-#pragma unroll
-            for (int h = 0; h < H; ++h) { A0[h] = A1[h]; A1[h] = A2[h]; A2[h] = zero2; }
-          } else {
-            rmw(tb + 2, A2);
-#pragma unroll
-            for (int h = 0; h < H; ++h) { A2[h] = A1[h]; A1[h] = A0[h]; A0[h] = zero2; }
+              for (int h = 0; h < H; ++h) {
+                g0[h] = __fmul2_rn(x[DG][n][h], make_float2(wG0, wG0));
+                g1[h] = __fmul2_rn(x[DG][n][h], make_float2(wG1, wG1));
+              }
+              rmw(tF + 2, g0);
+              rmw(tF + 3, g1);
+            }
+            __syncwarp();
           }
-          tb = tF;
+          if (far) wG0 = wG1 = 0.f;  // G is accounted for
         }
-        __syncwarp();  // order this step's stores before the next step's loads of other lanes
+        const float wa = e ? 0.f : wG0, wb = e ? wG0 : wG1, wc = e ? wG1 : 0.f;
+        const float2 wF0p = make_float2(wF0, wF0), wF1p = make_float2(wF1, wF1);
+        const float2 wap = make_float2(wa, wa), wbp = make_float2(wb, wb), wcp = make_float2(wc, wc);
+        if (n == 0) {
+          tb = tF;
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-          A0[h] = __ffma2_rn(x[DG][n][h], wap, __ffma2_rn(x[DF][n][h], wF0p, A0[h]));
-          A1[h] = __ffma2_rn(x[DG][n][h], wbp, __ffma2_rn(x[DF][n][h], wF1p, A1[h]));
-          A2[h] = __ffma2_rn(x[DG][n][h], wcp, A2[h]);
+          for (int h = 0; h < H; ++h) {
+            A0[h] = __ffma2_rn(x[DG][n][h], wap, __fmul2_rn(x[DF][n][h], wF0p));
+            A1[h] = __ffma2_rn(x[DG][n][h], wbp, __fmul2_rn(x[DF][n][h], wF1p));
+            A2[h] = __fmul2_rn(x[DG][n][h], wcp);
+          }
+        } else {
+          if (tF != tb) {  // F moved by one bin: the bin leaving the carried triple is complete for this walk
+            if (MINOR_UP) {
+              rmw(tb, A0);
+#pragma unroll
+              for (int h = 0; h < H; ++h) { A0[h] = A1[h]; A1[h] = A2[h]; A2[h] = zero2; }
+            } else {
+              rmw(tb + 2, A2);
+#pragma unroll
+              for (int h = 0; h < H; ++h) { A2[h] = A1[h]; A1[h] = A0[h]; A0[h] = zero2; }
+            }
+            tb = tF;
+          }
+          __syncwarp();  // order this step's stores before the next step's loads of other lanes
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            A0[h] = __ffma2_rn(x[DG][n][h], wap, __ffma2_rn(x[DF][n][h], wF0p, A0[h]));
+            A1[h] = __ffma2_rn(x[DG][n][h], wbp, __ffma2_rn(x[DF][n][h], wF1p, A1[h]));
+            A2[h] = __ffma2_rn(x[DG][n][h], wcp, A2[h]);
+          }
         }
       }
-    }
-    rmw(tb, A0);
-    __syncwarp();
-    rmw(tb + 1, A1);
-    __syncwarp();
-    rmw(tb + 2, A2);
-    __syncwarp();
+      rmw(tb, A0);
+      __syncwarp();
+      rmw(tb + 1, A1);
+      __syncwarp();
+      rmw(tb + 2, A2);
+      __syncwarp();
+    };
+    if (vr.fjump != 0.f) walk_view(std::true_type{});
+    else walk_view(std::false_type{});
 
     // ---- flush the window: lane j owns bins 4j .. 4j+3 (entirely inside or outside [0, D1));
     // predicated REDs, no branches per slice

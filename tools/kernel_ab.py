@@ -30,7 +30,9 @@ z0 = (n - S) // 2
 kw = dict(slice_offset=z0, det_row_offset=z0, det_rows_total=n)
 ops = {
     "default": sb.XRayTransform3D((S, n, n), M, (S, n), **kw),
-    "no_walk": sb.XRayTransform3D((S, n, n), M, (S, n), _flags=_lib.FLAG_NO_WALK, **kw),
+    "no_joint": sb.XRayTransform3D((S, n, n), M, (S, n), _flags=_lib.FLAG_NO_JOINT, **kw),  # one-column walk forward
+    "no_tma": sb.XRayTransform3D((S, n, n), M, (S, n), _flags=_lib.FLAG_NO_TMA, **kw),      # cp.async-staged adjoint
+    "no_walk": sb.XRayTransform3D((S, n, n), M, (S, n), _flags=_lib.FLAG_NO_WALK, **kw),    # first-generation plane kernels
 }
 g = torch.Generator(device=dev).manual_seed(0)
 x = torch.randn((S, n, n), device=dev, generator=g)
@@ -55,6 +57,7 @@ for name, A in ops.items():
         print(f"{name:8s} {tag} [{kern:7s}] {ms:9.3f} ms  {upd / ms / 1e6:8.1f} G updates/s  "
               f"(x{n * n * n / (S * n * n):.0f} -> {ms * n / S * 1024 / V:8.1f} ms at {n}^3 x 1024 views)", flush=True)
 for tag in ("fwd", "adj"):
-    a, b = res[("default", tag)], res[("no_walk", tag)]
-    rel = (torch.linalg.vector_norm((a - b).double()) / torch.linalg.vector_norm(b.double())).item()
-    print(f"{tag}: default vs no_walk rel-L2 {rel:.2e}")
+    for other in ("no_joint", "no_tma", "no_walk"):
+        a, b = res[("default", tag)], res[(other, tag)]
+        rel = (torch.linalg.vector_norm((a - b).double()) / torch.linalg.vector_norm(b.double())).item()
+        print(f"{tag}: default vs {other} rel-L2 {rel:.2e}")
