@@ -312,6 +312,90 @@ def _build_scico_stubs():
 _LOADED = {}
 
 
+def _snp_module(mods):
+    """The slice of ``scico.numpy`` (a jax.numpy wrapper in the reference) that ``solver.cg`` and
+    ``L21Norm`` call, with the stand-in's dtype rules."""
+    snp = mods["scico.numpy"]
+    j = _build_jax()["jax.numpy"]
+    for name in ("zeros", "sum", "abs", "where", "maximum", "minimum", "asarray", "array"):
+        setattr(snp, name, getattr(j, name))
+    snp.sqrt = lambda x: _wrap(np.sqrt(np.asarray(_raw(x))))
+    snp.divide = lambda x, y: _wrap(np.divide(np.asarray(_raw(x)), np.asarray(_raw(y))))
+    snp.count_nonzero = lambda x, **k: _wrap(np.count_nonzero(np.asarray(_raw(x)), **k))
+    snp.BlockArray = type("BlockArray", (), {})
+    snp.Array = object
+    lin = types.ModuleType("scico.numpy.linalg")
+    # jnp.linalg.norm of a real array: sqrt(sum(x * x)) in the array's dtype
+    lin.norm = lambda x, *a, **k: _wrap(np.sqrt(np.sum(np.square(np.asarray(_raw(x))), dtype=np.asarray(_raw(x)).dtype)))
+    snp.linalg = lin
+    mods["scico.numpy.linalg"] = lin
+    util = mods["scico.numpy.util"]
+    util.no_nan_divide = lambda x, y: snp.where(y != 0, snp.divide(x, snp.where(y != 0, y, 1)), 0)  # scico/numpy/util.py:315
+    util.is_complex_dtype = lambda d: np.dtype(d).kind == "c"
+    util.is_real_dtype = lambda d: np.dtype(d).kind == "f"
+    util.is_nested = lambda x: isinstance(x, (list, tuple)) and any(isinstance(v, (list, tuple)) for v in x)
+    return snp
+
+
+def load_reference_solver_pieces():
+    """Returns (cg, L21Norm): ``scico/solver.py::cg`` and ``scico/functional/_norm.py::L21Norm``,
+    loaded unmodified from /root/reference and executed over the stand-in (the other names those two
+    files import are inert placeholders)."""
+    if "cg" in _LOADED:
+        return _LOADED["cg"], _LOADED["L21Norm"]
+    if not available():
+        raise RuntimeError("the reference checkout is not present (this only runs in the build container)")
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.split(".")[0] in ("jax", "scico")}
+    fakes = {**_build_jax(), **_build_scico_stubs()}
+    _snp_module(fakes)
+    jsl = types.ModuleType("jax.scipy.linalg")
+    jsp = types.ModuleType("jax.scipy")
+    jsp.linalg = jsl
+    fakes["jax.scipy"], fakes["jax.scipy.linalg"] = jsp, jsl
+    fakes["jax"].scipy = jsp
+    for n in ("CircularConvolve", "ComposedLinearOperator", "Diagonal", "MatrixOperator", "Sum"):
+        setattr(fakes["scico.linop"], n, type(n, (), {}))
+    fakes["scico.linop"].LinearOperator = fakes["scico.linop._linop"].LinearOperator
+    metric = types.ModuleType("scico.metric")
+    metric.rel_res = lambda *a, **k: None
+    fakes["scico.metric"] = metric
+    fakes["scico.typing"].BlockShape = tuple
+    fakes["scico.typing"].Axes = object
+    fn_pkg = types.ModuleType("scico.functional")
+    fn_pkg.__path__ = []
+    fn_base = types.ModuleType("scico.functional._functional")
+
+    class Functional:  # scico/functional/_functional.py: only the flags the subclasses set
+        has_eval = False
+        has_prox = False
+
+        def __init__(self):
+            pass
+
+    fn_base.Functional = Functional
+    fakes["scico.functional"], fakes["scico.functional._functional"] = fn_pkg, fn_base
+    fakes["scico"].numpy = fakes["scico.numpy"]
+    sys.modules.update(fakes)
+    try:
+        out = {}
+        for tag, rel, name in (("solver", "solver.py", "scico.solver"), ("norm", os.path.join("functional", "_norm.py"), "scico.functional._norm")):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE_ROOT, "scico", rel))
+            mod = importlib.util.module_from_spec(spec)
+            mod.__package__ = name.rsplit(".", 1)[0]
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+            out[tag] = mod
+        _LOADED["cg"], _LOADED["L21Norm"] = out["solver"].cg, out["norm"].L21Norm
+    finally:
+        for k in list(sys.modules):
+            if k in fakes or k in ("scico.solver", "scico.functional._norm"):
+                if saved.get(k) is not None:
+                    sys.modules[k] = saved[k]
+                else:
+                    sys.modules.pop(k, None)
+    return _LOADED["cg"], _LOADED["L21Norm"]
+
+
 def available() -> bool:
     return os.path.exists(os.path.join(REFERENCE_ROOT, "scico", "linop", "xray", "_xray3d.py"))
 

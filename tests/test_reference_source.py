@@ -58,3 +58,27 @@ def test_drop_in_geometry_equals_the_reference_helper():
             ref = np.asarray(R3.matrices_from_euler_angles((9, 10, 11), (12, 13), seq, ang, **kw))
             got = sb.matrices_from_euler_angles((9, 10, 11), (12, 13), seq, ang, **kw)
             np.testing.assert_array_equal(got.astype(np.float32), ref)  # the reference returns float32 (x64 off)
+
+
+@needs_reference
+def test_tv_oracle_pieces_equal_the_reference_source():
+    """``scico/solver.py::cg`` (:367-405) and ``L21Norm.prox`` (``functional/_norm.py:254-263``) executed
+    from the reference's files over the stand-in against the TV oracle's restatements, bit for bit."""
+    from oracle import tv_np as T
+
+    cg, L21Norm = J.load_reference_solver_pieces()
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal((3, 6, 7, 8)).astype(np.float32)
+    v[:, 0, 0, 0] = 0  # a zero-length group: no_nan_divide
+    for lam in (0.3, 1.5):
+        np.testing.assert_array_equal(np.asarray(L21Norm(l2_axis=0).prox(J._wrap(v), lam)), T.l21_prox(v, lam))
+    n = 40
+    Q = rng.standard_normal((n, n)).astype(np.float32)
+    Amat = (Q @ Q.T + n * np.eye(n, dtype=np.float32)).astype(np.float32)
+    b, x0 = rng.standard_normal(n).astype(np.float32), np.zeros(n, np.float32)
+    for tol, maxiter in ((1e-4, 25), (1e-7, 100), (1e-30, 7)):
+        xr, info = cg(lambda x: J._wrap((Amat @ np.asarray(x)).astype(np.float32)), J._wrap(b), J._wrap(x0), tol=tol, maxiter=maxiter)
+        xo, io = T.cg(lambda x: (Amat @ x).astype(np.float32), b, x0, tol=tol, maxiter=maxiter)
+        assert info["num_iter"] == io["num_iter"]
+        np.testing.assert_array_equal(np.asarray(xr), xo)
+        assert abs(float(info["rel_res"]) - io["rel_res"]) <= 1e-6 * max(io["rel_res"], 1e-30)
