@@ -145,3 +145,36 @@ def test_pdhg_itstats_and_parameter_estimate(cuda_device):
     # the first iteration starts from zero duals and leaves x unchanged: compare with the second
     assert S.history[0]["prml_rsdl"] == 0.0 and S.history[-1]["prml_rsdl"] < S.history[1]["prml_rsdl"]
     assert O.rel_l2(S.x.cpu().numpy(), x_gt) < 0.15
+
+
+@pytest.mark.gpu
+def test_solve_replays_a_cuda_graph_and_matches_plain_stepping(cuda_device):
+    """solve() captures one iteration in a CUDA graph when nothing in it needs the host (PDHG and the
+    split ADMM variants, single GPU, statistics off) and replays it: same iterates as stepping."""
+    import torch
+
+    import scico_b200 as sb
+    from scico_b200.optimize import TVADMM, TVPDHG, TVProximalADMM
+
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(3)
+    A2 = sb.XRayTransform2D((64, 56), np.linspace(0, np.pi, 20, endpoint=False))
+    N, D = (16, 40, 48), (16, 64)
+    A3 = sb.XRayTransform3D(N, sb.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, 9, endpoint=False)[:, None]), D)
+    for A in (A2, A3):
+        x_gt = torch.rand(A.input_shape, device=dev, generator=g)
+        y = A(x_gt)
+        for make in (lambda: TVPDHG(A, y, 0.1, 0.02, 0.02, maxiter=12),
+                     lambda: TVProximalADMM(A, y, lam=0.5, rho=0.1, mu=2e3, nu=1.01, alpha=2.0, maxiter=12)):
+            S, R = make(), make()
+            S.solve(use_graph=True)
+            for _ in range(12):
+                R.step()
+            assert S.itnum == R.itnum == 12
+            rel = (torch.linalg.vector_norm(S.x - R.x) / torch.linalg.vector_norm(R.x)).item()
+            assert rel <= 1e-5, rel
+            E = make()
+            E.solve()  # default: plain stepping
+            assert (torch.linalg.vector_norm(E.x - R.x) / torch.linalg.vector_norm(R.x)).item() <= 1e-5
+    with pytest.raises(ValueError):
+        TVADMM(A2, A2(torch.rand(A2.input_shape, device=dev)), 0.5, 5.0, maxiter=3).solve(use_graph=True)
