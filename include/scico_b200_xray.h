@@ -115,6 +115,16 @@ typedef struct xct_plan_info {
   int64_t updates;        /* voxel-view updates per application = in_elems * num_views */
 } xct_plan_info;
 
+/* View classes and row structure a plan derived from its geometry (xct_plan_get_classes, xct*_plan_analyse). */
+typedef struct xct_plan_classes {
+  int32_t joint_views[8];   /* joint-column forward: views per class [4*major_is_axis_b + 2*minor_up + major_positive] */
+  int32_t two_bin_views[4]; /* one-column walk forward: views per class [2*major_is_axis_b + minor_up] */
+  int32_t adj_jump_views;   /* views whose |ca| is within rounding distance of 1 (walk adjoint's jump-by-two variant) */
+  int32_t rows_unit;        /* 3D sep: every (view, slice) lands in one detector row with weight 2 */
+  int32_t rows_consecutive; /* 3D sep: local row = local slice + const per view (TMA box / krow flush) */
+  int32_t fwd_cold;         /* some minor coefficient can move the bin by two per step */
+} xct_plan_classes;
+
 XCT_API int xct_version(void);
 XCT_API const char *xct_last_error(void);
 XCT_API int xct_device_count(void);
@@ -123,6 +133,13 @@ XCT_API int xct2d_plan_create(xct_plan **plan, const xct2d_geom *geom);
 XCT_API int xct3d_plan_create(xct_plan **plan, const xct3d_geom *geom);
 XCT_API void xct_plan_destroy(xct_plan *plan);
 XCT_API int xct_plan_get_info(const xct_plan *plan, xct_plan_info *info);
+XCT_API int xct_plan_get_classes(const xct_plan *plan, xct_plan_classes *classes);
+/* Analysis only: the decisions xct*_plan_create would take for this geometry (kernel families, view
+ * classes, joint / TMA eligibility), computed on the host without touching a CUDA device; `device` of the
+ * geometry is ignored, either output may be NULL.  adj_tma reports eligibility (the driver's tensor-map
+ * encoder is looked up only by a real plan). */
+XCT_API int xct2d_plan_analyse(const xct2d_geom *geom, xct_plan_info *info, xct_plan_classes *classes);
+XCT_API int xct3d_plan_analyse(const xct3d_geom *geom, xct_plan_info *info, xct_plan_classes *classes);
 
 /* Forward projection.  in: (batch, *input_shape)  out: (batch, *output_shape), DEVICE pointers.
  * `batch` must be 1 for 3D plans.  `out` is fully overwritten (it may be uninitialised). */

@@ -40,6 +40,9 @@ EXPORTED_SYMBOLS = (
     "xct3d_plan_create",
     "xct_plan_destroy",
     "xct_plan_get_info",
+    "xct_plan_get_classes",
+    "xct2d_plan_analyse",
+    "xct3d_plan_analyse",
     "xct_forward",
     "xct_adjoint",
     "xct_forward_host",
@@ -111,6 +114,17 @@ class PlanInfo(ctypes.Structure):
     ]
 
 
+class PlanClasses(ctypes.Structure):
+    _fields_ = [
+        ("joint_views", c_int32 * 8),
+        ("two_bin_views", c_int32 * 4),
+        ("adj_jump_views", c_int32),
+        ("rows_unit", c_int32),
+        ("rows_consecutive", c_int32),
+        ("fwd_cold", c_int32),
+    ]
+
+
 class TvBlock(ctypes.Structure):
     _fields_ = [("n0", c_int32), ("n1", c_int32), ("n2", c_int32), ("is_first", c_int32), ("is_last", c_int32)]
 
@@ -145,6 +159,9 @@ def lib() -> ctypes.CDLL:
     L.xct_plan_destroy.argtypes = [c_void_p]
     L.xct_plan_destroy.restype = None
     L.xct_plan_get_info.argtypes = [c_void_p, POINTER(PlanInfo)]
+    L.xct_plan_get_classes.argtypes = [c_void_p, POINTER(PlanClasses)]
+    L.xct2d_plan_analyse.argtypes = [POINTER(Geom2D), POINTER(PlanInfo), POINTER(PlanClasses)]
+    L.xct3d_plan_analyse.argtypes = [POINTER(Geom3D), POINTER(PlanInfo), POINTER(PlanClasses)]
     for name in ("xct_forward", "xct_adjoint"):
         getattr(L, name).argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
     for name in ("xct_forward_host", "xct_adjoint_host"):

@@ -52,6 +52,8 @@ constexpr int kW2dTN = 8, kW2dWin = 160;  // 2D joint forward tile: 128 (major) 
 }  // namespace
 
 struct xct_plan {
+  bool dry = false;  // analysis only (xct*_plan_analyse): every decision is made, nothing is uploaded
+  int adj_jump_views = 0;  // views that take the walk adjoint's jump-by-two variant
   int ndim = 0;
   int path = 0;          // XCT_PATH_*
   bool fwd_plane = false;  // forward uses the plane kernel (else general)
@@ -108,6 +110,7 @@ struct DeviceGuard {
   int prev = -1;
   bool ok = true;
   explicit DeviceGuard(int dev) {
+    if (dev < 0) return;  // analysis-only plan: no CUDA call at all
     if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
     if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
   }
@@ -205,28 +208,22 @@ Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fw
   return env;
 }
 
+// device copy of a host table; a dry plan (analysis only, possibly without any CUDA device) skips it
+template <class T>
+cudaError_t dev_upload(const xct_plan* pl, T*& dst, const T* src, size_t count) {
+  if (pl->dry || count == 0) return cudaSuccess;
+  cudaError_t e = cudaMalloc(&dst, sizeof(T) * count);
+  if (e == cudaSuccess) e = cudaMemcpy(dst, src, sizeof(T) * count, cudaMemcpyHostToDevice);
+  return e;
+}
+
 int upload_lists(xct_plan* pl, const Envelope& env) {
-  for (int c = 0; c < 2; ++c) {
-    pl->n_list[c] = (int)env.list[c].size();
-    if (pl->n_list[c] == 0) continue;
-    XCT_CUDA(cudaMalloc(&pl->d_list[c], sizeof(int) * env.list[c].size()));
-    XCT_CUDA(cudaMemcpy(pl->d_list[c], env.list[c].data(), sizeof(int) * env.list[c].size(),
-                        cudaMemcpyHostToDevice));
-  }
-  for (int c = 0; c < 4; ++c) {
-    pl->n_list4[c] = (int)env.list4[c].size();
-    if (pl->n_list4[c] == 0) continue;
-    XCT_CUDA(cudaMalloc(&pl->d_list4[c], sizeof(int) * env.list4[c].size()));
-    XCT_CUDA(cudaMemcpy(pl->d_list4[c], env.list4[c].data(), sizeof(int) * env.list4[c].size(),
-                        cudaMemcpyHostToDevice));
-  }
-  auto up = [](const std::vector<int>& src, int*& dst, int& n) -> cudaError_t {
+  auto up = [&](const std::vector<int>& src, int*& dst, int& n) -> cudaError_t {
     n = (int)src.size();
-    if (n == 0) return cudaSuccess;
-    cudaError_t e = cudaMalloc(&dst, sizeof(int) * src.size());
-    if (e == cudaSuccess) e = cudaMemcpy(dst, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice);
-    return e;
+    return dev_upload(pl, dst, src.data(), src.size());
   };
+  for (int c = 0; c < 2; ++c) XCT_CUDA(up(env.list[c], pl->d_list[c], pl->n_list[c]));
+  for (int c = 0; c < 4; ++c) XCT_CUDA(up(env.list4[c], pl->d_list4[c], pl->n_list4[c]));
   for (int c = 0; c < 8; ++c) XCT_CUDA(up(env.listJ[c], pl->d_listJ[c], pl->n_listJ[c]));
   for (int c = 0; c < 4; ++c) XCT_CUDA(up(env.listR[c], pl->d_listR[c], pl->n_listR[c]));
   return XCT_OK;
@@ -589,19 +586,20 @@ int xct_device_count(void) {
   return n;
 }
 
-int xct2d_plan_create(xct_plan** out, const xct2d_geom* g) {
+static int plan2d_create_impl(xct_plan** out, const xct2d_geom* g, bool dry) {
   if (!out || !g) return fail(XCT_ERR_INVALID, "null argument");
   *out = nullptr;
   if (g->n0 < 1 || g->n1 < 1 || g->num_views < 1 || g->det_count < 1 || !g->view_table)
     return fail(XCT_ERR_INVALID, "xct2d_plan_create: bad shape or null view_table");
   if ((long long)g->n0 * g->n1 > (1LL << 40)) return fail(XCT_ERR_INVALID, "image too large");
-  int rc = check_device(g->device);
+  int rc = dry ? XCT_OK : check_device(g->device);
   if (rc) return rc;
-  DeviceGuard guard(g->device);
+  DeviceGuard guard(dry ? -1 : g->device);
   if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
 
   xct_plan* pl = new (std::nothrow) xct_plan();
   if (!pl) return fail(XCT_ERR_INVALID, "out of host memory");
+  pl->dry = dry;
   pl->ndim = 2; pl->device = g->device; pl->V = g->num_views;
   pl->n0 = g->n0; pl->n1 = g->n1; pl->n2 = 1; pl->d0 = 1; pl->d1 = g->det_count;
 
@@ -641,29 +639,28 @@ int xct2d_plan_create(xct_plan** out, const xct2d_geom* g) {
   }
 
   auto cleanup = [&](int code) { xct_plan_destroy(pl); return code; };
-  cudaError_t e = cudaMalloc(&pl->d_views, sizeof(xct::ViewRec) * views.size());
-  if (e == cudaSuccess)
-    e = cudaMemcpy(pl->d_views, views.data(), sizeof(xct::ViewRec) * views.size(), cudaMemcpyHostToDevice);
+  cudaError_t e = dev_upload(pl, pl->d_views, views.data(), views.size());
   if (e != cudaSuccess) return cleanup(fail(XCT_ERR_CUDA, std::string("view table upload: ") + cudaGetErrorString(e)));
   if ((rc = upload_lists(pl, env))) return cleanup(rc);
   *out = pl;
   return XCT_OK;
 }
 
-int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
+static int plan3d_create_impl(xct_plan** out, const xct3d_geom* g, bool dry) {
   if (!out || !g) return fail(XCT_ERR_INVALID, "null argument");
   *out = nullptr;
   if (g->n0 < 1 || g->n1 < 1 || g->n2 < 1 || g->d0 < 1 || g->d1 < 1 || g->num_views < 1 || !g->matrices)
     return fail(XCT_ERR_INVALID, "xct3d_plan_create: bad shape or null matrices");
   if ((long long)g->d0 * g->d1 >= (1LL << 31))
     return fail(XCT_ERR_INVALID, "detector too large for int32 row*col offsets");
-  int rc = check_device(g->device);
+  int rc = dry ? XCT_OK : check_device(g->device);
   if (rc) return rc;
-  DeviceGuard guard(g->device);
+  DeviceGuard guard(dry ? -1 : g->device);
   if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
 
   xct_plan* pl = new (std::nothrow) xct_plan();
   if (!pl) return fail(XCT_ERR_INVALID, "out of host memory");
+  pl->dry = dry;
   pl->ndim = 3; pl->device = g->device; pl->V = g->num_views;
   pl->n0 = g->n0; pl->n1 = g->n1; pl->n2 = g->n2; pl->d0 = g->d0; pl->d1 = g->d1;
   pl->slice_offset = g->slice_offset; pl->row_off = g->det_row_offset;
@@ -680,8 +677,7 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
   }
   if (!finite) return cleanup(fail(XCT_ERR_INVALID, "xct3d_plan_create: non-finite matrix entry"));
 
-  cudaError_t e = cudaMalloc(&pl->d_mats, sizeof(float) * 8 * (size_t)V);
-  if (e == cudaSuccess) e = cudaMemcpy(pl->d_mats, g->matrices, sizeof(float) * 8 * (size_t)V, cudaMemcpyHostToDevice);
+  cudaError_t e = dev_upload(pl, pl->d_mats, g->matrices, 8 * (size_t)V);
   if (e != cudaSuccess) return cleanup(fail(XCT_ERR_CUDA, std::string("matrix upload: ") + cudaGetErrorString(e)));
 
   pl->path = XCT_PATH_3D_GENERAL;
@@ -771,7 +767,7 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       if (!tma_ok)
         for (auto& vr : views) vr.krow = 0;
       pl->rows_krow = tma_ok;
-      pl->adj_tma = tma_ok && tensor_map_encoder() != nullptr && !(g->flags & XCT_FLAG_NO_TMA);
+      pl->adj_tma = tma_ok && (dry || tensor_map_encoder() != nullptr) && !(g->flags & XCT_FLAG_NO_TMA);
       if (unit) {
         // per-slice detector row range over the views, and whether rows never decrease with the slice
         // index (any rotation about axis 0 with a positive axis-0 scale): the host pipeline relies on it
@@ -793,14 +789,12 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
         pl->pipe_ok = mono;
       }
       if (unit) {
-        e = cudaMalloc(&pl->d_rowoff, sizeof(long long) * rowoff.size());
-        if (e == cudaSuccess) e = cudaMemcpy(pl->d_rowoff, rowoff.data(), sizeof(long long) * rowoff.size(), cudaMemcpyHostToDevice);
+        e = dev_upload(pl, pl->d_rowoff, rowoff.data(), rowoff.size());
         if (e != cudaSuccess) return cleanup(fail(XCT_ERR_CUDA, std::string("row index upload: ") + cudaGetErrorString(e)));
       }
-      e = cudaMalloc(&pl->d_views, sizeof(xct::ViewRec) * views.size());
-      if (e == cudaSuccess) e = cudaMemcpy(pl->d_views, views.data(), sizeof(xct::ViewRec) * views.size(), cudaMemcpyHostToDevice);
-      if (e == cudaSuccess) e = cudaMalloc(&pl->d_rows, sizeof(xct::RowRec) * rows.size());
-      if (e == cudaSuccess) e = cudaMemcpy(pl->d_rows, rows.data(), sizeof(xct::RowRec) * rows.size(), cudaMemcpyHostToDevice);
+      e = dev_upload(pl, pl->d_views, views.data(), views.size());
+      if (e == cudaSuccess) e = dev_upload(pl, pl->d_rows, rows.data(), rows.size());
+      for (const auto& vr : views) pl->adj_jump_views += vr.jump != 0.f ? 1 : 0;
       if (e != cudaSuccess) return cleanup(fail(XCT_ERR_CUDA, std::string("table upload: ") + cudaGetErrorString(e)));
       if ((rc = upload_lists(pl, env))) return cleanup(rc);
       pl->adj_plane = env.adj_ok;
@@ -810,6 +804,7 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
       pl->fwd_unit4 = env.fwd_unit4_ok && unit && (g->d1 % 4 == 0);
       pl->fwd_joint = pl->fwd_walk && pl->fwd_unit4 && !pl->fwd_cold && !(g->flags & XCT_FLAG_NO_JOINT);
       pl->adj_walk = env.adj_ok && env.adj_walk_ok && unit && (g->d1 % 4 == 0) && !(g->flags & XCT_FLAG_NO_WALK);
+      pl->adj_tma = pl->adj_tma && pl->adj_walk;  // the TMA box is the walk adjoint's staging
       pl->gs = env.fwd_ok ? env.gs : 0;
       pl->pipe_ok = pl->pipe_ok && pl->fwd_walk && pl->adj_walk && !(g->flags & XCT_FLAG_NO_HOST_PIPELINE);
       if (pl->adj_plane && pl->fwd_plane) pl->path = XCT_PATH_3D_SEP;
@@ -819,8 +814,49 @@ int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) {
   return XCT_OK;
 }
 
+int xct2d_plan_create(xct_plan** out, const xct2d_geom* g) { return plan2d_create_impl(out, g, false); }
+int xct3d_plan_create(xct_plan** out, const xct3d_geom* g) { return plan3d_create_impl(out, g, false); }
+
+// Analysis only: every plan decision (kernel family, view classes, TMA / joint eligibility) from the
+// geometry alone, without touching a CUDA device -- what the CPU-only tests exercise.
+static void fill_classes(const xct_plan* pl, xct_plan_classes* c) {
+  for (int k = 0; k < 8; ++k) c->joint_views[k] = pl->n_listJ[k];
+  for (int k = 0; k < 4; ++k) c->two_bin_views[k] = (pl->fwd_joint || pl->fwd_joint2d) ? pl->n_listR[k] : pl->n_list4[k];
+  c->adj_jump_views = pl->adj_jump_views;
+  c->rows_unit = pl->rows_unit ? 1 : 0;
+  c->rows_consecutive = pl->rows_krow ? 1 : 0;
+  c->fwd_cold = pl->fwd_cold ? 1 : 0;
+}
+int xct_plan_get_classes(const xct_plan* pl, xct_plan_classes* classes) {
+  if (!pl || !classes) return fail(XCT_ERR_INVALID, "null argument");
+  fill_classes(pl, classes);
+  return XCT_OK;
+}
+int xct2d_plan_analyse(const xct2d_geom* g, xct_plan_info* info, xct_plan_classes* classes) {
+  xct_plan* pl = nullptr;
+  int rc = plan2d_create_impl(&pl, g, true);
+  if (rc) return rc;
+  if (info) rc = xct_plan_get_info(pl, info);
+  if (!rc && classes) fill_classes(pl, classes);
+  xct_plan_destroy(pl);
+  return rc;
+}
+int xct3d_plan_analyse(const xct3d_geom* g, xct_plan_info* info, xct_plan_classes* classes) {
+  xct_plan* pl = nullptr;
+  int rc = plan3d_create_impl(&pl, g, true);
+  if (rc) return rc;
+  if (info) rc = xct_plan_get_info(pl, info);
+  if (!rc && classes) fill_classes(pl, classes);
+  xct_plan_destroy(pl);
+  return rc;
+}
+
 void xct_plan_destroy(xct_plan* pl) {
   if (!pl) return;
+  if (pl->dry) {
+    delete pl;
+    return;
+  }
   DeviceGuard guard(pl->device);
   cudaFree(pl->d_views);
   cudaFree(pl->d_rows);

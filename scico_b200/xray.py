@@ -121,6 +121,18 @@ def _apply(plans: _Plans, x, out_shape, forward: bool, batch: int, default_devic
     return torch.from_numpy(out) if was_torch else out
 
 
+def _analyse(fn, geom) -> dict:
+    info, cls = _lib.PlanInfo(), _lib.PlanClasses()
+    _lib.check(fn(ctypes.byref(geom), ctypes.byref(info), ctypes.byref(cls)))
+    d = {name: getattr(info, name) for name, _ in info._fields_}
+    d["path_name"] = _lib.PATH_NAMES.get(info.path, "?")
+    d["joint_views"] = list(cls.joint_views)
+    d["two_bin_views"] = list(cls.two_bin_views)
+    for name in ("adj_jump_views", "rows_unit", "rows_consecutive", "fwd_cold"):
+        d[name] = getattr(cls, name)
+    return d
+
+
 class XRayTransform2D(LinearOperator):
     r"""Parallel ray, single axis, 2D X-ray projector (``_xray2d.py:29-136``).
 
@@ -169,7 +181,7 @@ class XRayTransform2D(LinearOperator):
                          output_shape=self.output_shape, output_dtype=np.float32,
                          eval_fn=self.project, adj_fn=self.back_project)
 
-    def _make_plan(self, device: int):
+    def _geom(self, device: int):
         g = _lib.Geom2D()
         g.n0, g.n1 = int(self.nx[0]), int(self.nx[1])
         g.num_views = int(self.view_table.shape[0])
@@ -177,9 +189,18 @@ class XRayTransform2D(LinearOperator):
         g.view_table = self.view_table.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
         g.device = device
         g.flags = self._flags
+        return g
+
+    def _make_plan(self, device: int):
+        g = self._geom(device)
         pl = ctypes.c_void_p()
         _lib.check(_lib.lib().xct2d_plan_create(ctypes.byref(pl), ctypes.byref(g)))
         return pl
+
+    def analyse(self) -> dict:
+        """The native plan's decisions for this geometry (kernel families, view classes), computed on the
+        host without a CUDA device (``xct2d_plan_analyse``)."""
+        return _analyse(_lib.lib().xct2d_plan_analyse, self._geom(0))
 
     def plan_info(self, device: int = 0) -> dict:
         return self._plans.info(device)
@@ -266,7 +287,7 @@ class XRayTransform3D(LinearOperator):
                          eval_fn=self.project, adj_fn=self.back_project,
                          input_dtype=input_dtype, output_dtype=input_dtype)
 
-    def _make_plan(self, device: int):
+    def _geom(self, device: int):
         g = _lib.Geom3D()
         g.n0, g.n1, g.n2 = (int(s) for s in self.input_shape)
         g.d0, g.d1 = (int(s) for s in self.det_shape)
@@ -277,9 +298,18 @@ class XRayTransform3D(LinearOperator):
         g.det_rows_total = self.det_rows_total
         g.device = device
         g.flags = self._flags
+        return g
+
+    def _make_plan(self, device: int):
+        g = self._geom(device)
         pl = ctypes.c_void_p()
         _lib.check(_lib.lib().xct3d_plan_create(ctypes.byref(pl), ctypes.byref(g)))
         return pl
+
+    def analyse(self) -> dict:
+        """The native plan's decisions for this geometry (kernel families, view classes, TMA / joint
+        eligibility), computed on the host without a CUDA device (``xct3d_plan_analyse``)."""
+        return _analyse(_lib.lib().xct3d_plan_analyse, self._geom(0))
 
     def plan_info(self, device: int = 0) -> dict:
         return self._plans.info(device)
