@@ -587,24 +587,52 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
   const int a0 = ta * (MAJOR_B ? TN : TM), b0 = tb_ * (MAJOR_B ? TM : TN), s0 = sg * S;
   Vec* winv = reinterpret_cast<Vec*>(smem + (size_t)warp * (WIN * S));
 
+  // voxels are pre-multiplied by the axis-0 row weight (2, a power of two: bit-identical to scaling
+  // the bin sums afterwards)
   float2 x[GS][TN][H];
+  auto put = [&](int d, int n, int s, float val) {
+    if (s & 1) x[d][n][s / 2].y = wp.out_scale * val;
+    else x[d][n][s / 2].x = wp.out_scale * val;
+  };
+  // interior tiles of 16-byte aligned volumes are loaded with vector loads: the lane's 8 consecutive
+  // columns as two LDG.128 (major axis A) or its two adjacent columns as one LDG.64 (major axis B)
+  const bool interior = a0 + (MAJOR_B ? TN : TM) <= p.NA && b0 + (MAJOR_B ? TM : TN) <= p.NB && s0 + S <= p.NS &&
+                        (p.NB & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  if (interior) {
+    static_assert(TN == 8 && GS == 2, "vector tile load is written for 8 minor points and column pairs");
 #pragma unroll
-  for (int d = 0; d < GS; ++d)
+    for (int s = 0; s < S; ++s) {
+      const float* slice = in + (size_t)(s0 + s) * p.NA * (size_t)p.NB;
+      if (MAJOR_B) {
 #pragma unroll
-    for (int n = 0; n < TN; ++n) {
-      const int a = MAJOR_B ? a0 + n : a0 + GS * lane + d;
-      const int b = MAJOR_B ? b0 + GS * lane + d : b0 + n;
-      const bool ok = a < p.NA && b < p.NB;
+        for (int n = 0; n < TN; ++n) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(slice + (size_t)(a0 + n) * p.NB + b0 + GS * lane));
+          put(0, n, s, v.x);
+          put(1, n, s, v.y);
+        }
+      } else {
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        // voxels are pre-multiplied by the axis-0 row weight (2, a power of two: bit-identical to
-        // scaling the bin sums afterwards)
-        const float val =
-            (ok && s0 + s < p.NS) ? wp.out_scale * __ldg(in + ((size_t)(s0 + s) * p.NA + a) * (size_t)p.NB + b) : 0.f;
-        if (s & 1) x[d][n][s / 2].y = val;
-        else x[d][n][s / 2].x = val;
+        for (int d = 0; d < GS; ++d) {
+          const float4* row = reinterpret_cast<const float4*>(slice + (size_t)(a0 + GS * lane + d) * p.NB + b0);
+          const float4 v0 = __ldg(row), v1 = __ldg(row + 1);
+          put(d, 0, s, v0.x); put(d, 1, s, v0.y); put(d, 2, s, v0.z); put(d, 3, s, v0.w);
+          put(d, 4, s, v1.x); put(d, 5, s, v1.y); put(d, 6, s, v1.z); put(d, 7, s, v1.w);
+        }
       }
     }
+  } else {
+#pragma unroll
+    for (int d = 0; d < GS; ++d)
+#pragma unroll
+      for (int n = 0; n < TN; ++n) {
+        const int a = MAJOR_B ? a0 + n : a0 + GS * lane + d;
+        const int b = MAJOR_B ? b0 + GS * lane + d : b0 + n;
+        const bool ok = a < p.NA && b < p.NB;
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          put(d, n, s, (ok && s0 + s < p.NS) ? __ldg(in + ((size_t)(s0 + s) * p.NA + a) * (size_t)p.NB + b) : 0.f);
+      }
+  }
   const float xmin0 = MAJOR_B ? G::coordA(a0) : G::coordB(b0);
 
   // (An XOR-swizzled slot layout that makes the final read conflict-free was measured: the two extra
