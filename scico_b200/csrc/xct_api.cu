@@ -77,6 +77,7 @@ struct xct_plan {
   bool fwd_walk = false;
   bool fwd_cold = false;   // some view's minor-axis coefficient can move the bin by more than one per step
   bool fwd_unit4 = false;  // vector flush possible (unit rows, D1 % 4 == 0, window fits with 4-bin alignment)
+  bool fwd_mix4 = false;   // same window / alignment conditions, rows mix two detector rows (joint kernel, ROWS_MIX)
   int* d_list4[4] = {nullptr, nullptr, nullptr, nullptr};  // walk forward: [2*major_b + minor_up]
   int n_list4[4] = {0, 0, 0, 0};
   // joint-column walk forward: views with fjump == 0 by [4*major_b + 2*minor_up + major_positive],
@@ -406,7 +407,7 @@ int launch_walk_forward_joint_class(const xct_plan* pl, const float* in, float* 
   xct::Walk2Params wp{};
   wp.p = plane_params(pl, 1);
   wp.rowoff = pl->d_rowoff;
-  wp.out_scale = 2.0f;
+  wp.out_scale = pl->rows_unit ? 2.0f : 1.0f;  // unit rows: the row weight 2 is folded into the voxels
   wp.row_stride = wp.p.NS;
   wp.s_base = s_begin;
   xct::PlaneParams& p = wp.p;
@@ -416,11 +417,14 @@ int launch_walk_forward_joint_class(const xct_plan* pl, const float* in, float* 
   p.n_list = pl->n_listJ[cls];
   const dim3 grid = walk_forward_grid<kWFwdS, kWFwdTN, 2, MAJOR_B>(p);
   const size_t smem = (size_t)kWarps * kWFwdS * kFwdWin * sizeof(float);
-  if (pl->rows_krow)
-    xct::walk_forward_joint_kernel<xct::Geom3, kWFwdS, kWFwdTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, true, kWarps>
+  if (!pl->rows_unit)
+    xct::walk_forward_joint_kernel<xct::Geom3, kWFwdS, kWFwdTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_MIX, kWarps>
+        <<<grid, kWarps * 32, smem, st>>>(wp, in, out);
+  else if (pl->rows_krow)
+    xct::walk_forward_joint_kernel<xct::Geom3, kWFwdS, kWFwdTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_KROW, kWarps>
         <<<grid, kWarps * 32, smem, st>>>(wp, in, out);
   else
-    xct::walk_forward_joint_kernel<xct::Geom3, kWFwdS, kWFwdTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, false, kWarps>
+    xct::walk_forward_joint_kernel<xct::Geom3, kWFwdS, kWFwdTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_TABLE, kWarps>
         <<<grid, kWarps * 32, smem, st>>>(wp, in, out);
   return launch_ok("walk_forward_joint_kernel");
 }
@@ -511,15 +515,18 @@ int launch_walk_forward_joint(const xct_plan* pl, const float* in, float* out, c
 // Slices [s_begin, s_begin + s_count) of the plan only (s_count < 0: all); `in` is the full volume.
 int launch_walk_forward3(const xct_plan* pl, const float* in, float* out, cudaStream_t st, int s_begin = 0,
                          int s_count = -1) {
-  const bool unit4 = pl->fwd_unit4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const bool unit4 = pl->fwd_unit4 && aligned16;
   if (pl->fwd_cold) {
     return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, true, false>(pl, 1, in, out, st, s_begin, s_count);
   }
-  if (unit4 && pl->fwd_joint) {
-    // safe views: joint-column kernel; views within rounding distance of a unit coefficient: 2-bin walk
+  if (pl->fwd_joint && aligned16 && (pl->fwd_unit4 || pl->fwd_mix4)) {
+    // joint-column kernel; views whose minor coefficient can reach one bin per voxel: 2-bin walk
     int rc = launch_walk_forward_joint(pl, in, out, st, s_begin, s_count);
     if (rc) return rc;
-    return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, true>(pl, 1, in, out, st, s_begin, s_count, true);
+    if (pl->fwd_unit4)
+      return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, true>(pl, 1, in, out, st, s_begin, s_count, true);
+    return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, false>(pl, 1, in, out, st, s_begin, s_count, true);
   }
   if (unit4) return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, true>(pl, 1, in, out, st, s_begin, s_count);
   return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, false>(pl, 1, in, out, st, s_begin, s_count);
@@ -802,7 +809,8 @@ static int plan3d_create_impl(xct_plan** out, const xct3d_geom* g, bool dry) {
       pl->fwd_walk = env.fwd_ok && env.gs == 2 && !(g->flags & XCT_FLAG_NO_WALK);
       pl->fwd_cold = env.max_minor > 0.98f;
       pl->fwd_unit4 = env.fwd_unit4_ok && unit && (g->d1 % 4 == 0);
-      pl->fwd_joint = pl->fwd_walk && pl->fwd_unit4 && !pl->fwd_cold && !(g->flags & XCT_FLAG_NO_JOINT);
+      pl->fwd_mix4 = env.fwd_unit4_ok && !unit && (g->d1 % 4 == 0);
+      pl->fwd_joint = pl->fwd_walk && (pl->fwd_unit4 || pl->fwd_mix4) && !pl->fwd_cold && !(g->flags & XCT_FLAG_NO_JOINT);
       pl->adj_walk = env.adj_ok && env.adj_walk_ok && unit && (g->d1 % 4 == 0) && !(g->flags & XCT_FLAG_NO_WALK);
       pl->adj_tma = pl->adj_tma && pl->adj_walk;  // the TMA box is the walk adjoint's staging
       pl->gs = env.fwd_ok ? env.gs : 0;

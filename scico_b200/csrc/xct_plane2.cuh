@@ -542,6 +542,7 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
 }
 
 // ------------------------------------------------------------------------ forward, joint columns
+enum { ROWS_TABLE = 0, ROWS_KROW = 1, ROWS_MIX = 2 };
 // Same tile and window as walk_forward_kernel, but a lane walks its TWO major-axis columns
 // TOGETHER and carries THREE bin sums in registers: the column with the smaller coordinate (F) sits
 // on bins (t, t+1), its neighbour (G, one voxel further along the major axis, |c_major| <= 1) on
@@ -553,8 +554,12 @@ walk_forward_kernel(Walk2Params wp, const float* __restrict__ in, float* __restr
 // Only views whose MINOR coefficient can reach 1 as well (never the case for a rotation) go through
 // walk_forward_kernel.  3D unit-row geometry with the 16-byte vector flush only.
 // MAJ_POS: the major-axis coefficient is positive (F is the lane's first column).
-// KROW: in every view the local detector row of slice i is i + ViewRec::krow (or outside the
-// detector), so the flush derives its four row pointers from one base instead of four table loads.
+// ROWS selects how a slice finds its detector row(s) at the flush:
+//   ROWS_KROW   in every view the local row of slice i is i + ViewRec::krow (or outside the detector): the
+//               four row pointers come from one base instead of four table loads;
+//   ROWS_TABLE  unit rows looked up in the per-(view, slice) offset table;
+//   ROWS_MIX    a slice spreads over rows r0 and r0 + 1 with the masked axis-0 weights of its RowRec
+//               (detector row pitch != voxel pitch along axis 0); voxels are then not pre-scaled.
 __device__ __forceinline__ void red_add_v4_if(bool pred, float* p, float a, float b, float c, float d) {
   asm volatile(
       "{\n"
@@ -566,8 +571,8 @@ __device__ __forceinline__ void red_add_v4_if(bool pred, float* p, float a, floa
       : "memory");
 }
 
-template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, bool KROW, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int ROWS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)  // two CTAs (16 warps) per SM: at most 128 registers
 walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* __restrict__ sino) {
   static_assert(WIN % 32 == 0 && S == 4, "float4 window slots, flushed 4 bins per lane");
   using Vec = float4;
@@ -751,7 +756,7 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
         const Vec r = winv[4 * lane + k];
         blk[k][0] = r.x; blk[k][1] = r.y; blk[k][2] = r.z; blk[k][3] = r.w;
       }
-      if (KROW) {
+      if (ROWS == ROWS_KROW) {
         const int r0 = wp.s_base + s0 + vr.krow;  // local detector row of the group's first slice
         float* y = sino + ((long long)v * p.D0 + r0) * (long long)p.D1 + col;
 #pragma unroll
@@ -761,7 +766,7 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
           const bool live = s0 + s < p.NS && (unsigned)(r0 + s) < (unsigned)p.D0 && any != 0u;
           red_add_v4_if(live, y + (long long)s * p.D1, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
         }
-      } else {
+      } else if (ROWS == ROWS_TABLE) {
         const long long* ro = wp.rowoff + (size_t)v * wp.row_stride + wp.s_base;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -771,6 +776,20 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
                                __float_as_uint(blk[3][s]);
           const bool live = s0 + s < p.NS && off >= 0 && any != 0u;
           red_add_v4_if(live, sino + (live ? off : 0) + col, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int sl = min(s0 + s, p.NS - 1);
+          const RowRec rr = load_row(p.rows + (size_t)v * wp.row_stride + wp.s_base + sl);
+          const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
+                               __float_as_uint(blk[3][s]);
+          const bool live = s0 + s < p.NS && any != 0u;
+          // the masked weights are zero for rows outside the detector: r0 may then be -1 or D0 - 1
+          float* y = sino + ((long long)v * p.D0 + rr.r0) * (long long)p.D1 + col;
+          red_add_v4_if(live && rr.w0 != 0.f, y, rr.w0 * blk[0][s], rr.w0 * blk[1][s], rr.w0 * blk[2][s], rr.w0 * blk[3][s]);
+          red_add_v4_if(live && rr.w1 != 0.f, y + p.D1, rr.w1 * blk[0][s], rr.w1 * blk[1][s], rr.w1 * blk[2][s],
+                        rr.w1 * blk[3][s]);
         }
       }
     }

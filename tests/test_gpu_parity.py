@@ -68,6 +68,11 @@ CASES_3D.update({
     # in-plane voxel spacing 1.4: minor-axis coefficient reaches 0.99 -> bins can jump by two (cold path)
     "walk_cold_spacing": ((6, 40, 44), (6, 96), lambda: _x_mats((6, 40, 44), (6, 96), 16, voxel_spacing=[1.0, 1.4, 1.4])),
     "walk_many_slices": ((70, 24, 20), (70, 36), lambda: _x_mats((70, 24, 20), (70, 36), 6)),
+    # detector rows finer than the slices: every slice mixes two rows (joint forward, ROWS_MIX flush)
+    "walk_row_mixing": ((12, 40, 44), (18, 96), lambda: _x_mats((12, 40, 44), (18, 96), 16, det_spacing=[0.75, 1.0])),
+    "walk_row_mixing_full_turn": ((9, 70, 66), (8, 120),
+                                  lambda: sb.matrices_from_euler_angles((9, 70, 66), (8, 120), "X", np.linspace(0, 2 * np.pi, 12, endpoint=False)[:, None],
+                                                                        det_spacing=[1.3, 1.0])),
 })
 
 

@@ -47,7 +47,7 @@ def test_slab_geometry_keeps_consecutive_rows():
     ("tilt", dict(path_name="3d_general", fwd_kernel=0, adj_kernel=0, fwd_joint=0, adj_tma=0)),
     ("odd_columns", dict(path_name="3d_sep", fwd_kernel=2, adj_kernel=1, fwd_joint=0, adj_tma=0)),
     ("wide_voxels", dict(path_name="3d_sep", fwd_cold=1, fwd_joint=0)),
-    ("row_mixing", dict(path_name="3d_sep", rows_unit=0, fwd_joint=0, adj_kernel=1, adj_tma=0)),
+    ("row_mixing", dict(path_name="3d_sep", rows_unit=0, fwd_kernel=2, fwd_joint=1, adj_kernel=1, adj_tma=0)),
 ])
 def test_geometries_outside_the_envelope_fall_back(case, expect):
     N, D, V = (12, 40, 44), (12, 96), 16
