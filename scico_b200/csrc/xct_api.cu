@@ -45,7 +45,7 @@ constexpr int kFwdWin = 96;
 constexpr int kFwd3S = 2, kFwd3TN = 16;
 constexpr int kFwd2S = 1, kFwd2TN = 16;
 // walk kernels (xct_plane2.cuh)
-constexpr int kWAdjS = 8, kWAdjTA = 8, kWAdjWin = 64, kWAdjStages = 3;
+constexpr int kWAdjS = 8, kWAdjTA = 8, kWAdjWin = 64, kWAdjStages = 4;
 constexpr int kWFwdS = 4, kWFwdTN = 8;
 constexpr int kW2dTN = 8, kW2dWin = 160;  // 2D joint forward tile: 128 (major) x 8 (minor), one image  // walk forward tile: 64 (major) x 8 (minor) x 4 slices
 
@@ -330,7 +330,7 @@ int launch_walk_adjoint(const xct_plan* pl, const float* in, float* out, cudaStr
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUresult r = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), dims, strides,
                                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS) {
       const size_t smem_tma = smem + (size_t)kWarps * kWAdjStages * sizeof(unsigned long long);
       auto kern = xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps, true>;
@@ -340,6 +340,10 @@ int launch_walk_adjoint(const xct_plan* pl, const float* in, float* out, cudaStr
       return launch_ok("walk_adjoint_kernel<tma>");
     }
     // encoding refused (e.g. a stride the tensor map cannot express): cp.async staging below
+  }
+  {
+    auto kern = xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps, false>;
+    if (smem > 48 * 1024) XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps, false>
       <<<blocks, kWarps * 32, smem, st>>>(wp, in, out, tmap);
