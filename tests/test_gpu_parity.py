@@ -334,6 +334,9 @@ def test_golden_fixtures(torch_dev, path):
         assert np.abs(w - g["w_mid"]).max() <= 2.4e-7
     assert O.rel_l2(_gpu(torch, dev, A, g["x"]), g["Ax"]) <= TOL
     assert O.rel_l2(_gpu(torch, dev, A, g["y"], adj=True), g["ATy"]) <= TOL
+    if "fbp" in g.files:  # the reference source's own filtered back projection (_xray2d.py:158-197)
+        got = A.fbp(torch.as_tensor(g["y"], device=dev)).cpu().numpy()
+        assert O.rel_l2(got, g["fbp"]) <= 1e-4  # FFT round-off differs between libraries
 
 
 def test_known_answers_exact(torch_dev):
