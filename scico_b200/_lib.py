@@ -49,6 +49,13 @@ EXPORTED_SYMBOLS = (
     "xct_adjoint_host",
     "xct3d_debug_weights",
     "xct2d_debug_weights",
+    "xct_adjoint_scatter",
+    "xct_peer_alloc",
+    "xct_peer_open",
+    "xct_peer_zero",
+    "xct_peer_copy_out",
+    "xct_peer_close",
+    "xct_peer_free",
     "xct_launch_count",
     "xct_launch_count_reset",
     "xct_tv_primal_step",
@@ -125,6 +132,21 @@ class PlanClasses(ctypes.Structure):
     ]
 
 
+MAX_ROUTE_PARTS = 16
+
+
+class OutRoute(ctypes.Structure):
+    _fields_ = [
+        ("nparts", c_int32),
+        ("row_begin", c_int32 * (MAX_ROUTE_PARTS + 1)),
+        ("ptr", c_void_p * MAX_ROUTE_PARTS),
+    ]
+
+
+class IpcHandle(ctypes.Structure):
+    _fields_ = [("bytes", ctypes.c_ubyte * 64)]
+
+
 class TvBlock(ctypes.Structure):
     _fields_ = [("n0", c_int32), ("n1", c_int32), ("n2", c_int32), ("is_first", c_int32), ("is_last", c_int32)]
 
@@ -166,6 +188,13 @@ def lib() -> ctypes.CDLL:
         getattr(L, name).argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
     for name in ("xct_forward_host", "xct_adjoint_host"):
         getattr(L, name).argtypes = [c_void_p, c_void_p, c_void_p, c_int32]
+    L.xct_adjoint_scatter.argtypes = [c_void_p, c_void_p, POINTER(OutRoute), c_void_p]
+    L.xct_peer_alloc.argtypes = [c_int32, ctypes.c_size_t, POINTER(c_void_p), POINTER(IpcHandle)]
+    L.xct_peer_open.argtypes = [c_int32, POINTER(IpcHandle), POINTER(c_void_p)]
+    L.xct_peer_zero.argtypes = [c_int32, c_void_p, ctypes.c_size_t, c_void_p]
+    L.xct_peer_copy_out.argtypes = [c_int32, c_void_p, c_void_p, ctypes.c_size_t, c_void_p]
+    L.xct_peer_close.argtypes = [c_int32, c_void_p]
+    L.xct_peer_free.argtypes = [c_int32, c_void_p]
     L.xct3d_debug_weights.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
     L.xct2d_debug_weights.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
     cf = ctypes.c_float

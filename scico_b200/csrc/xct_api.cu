@@ -281,7 +281,8 @@ xct::PlaneParams plane_params(const xct_plan* pl, int batch) {
 
 // ------------------------------------------------------------------ plane launches
 template <class G, bool IS3D, int S, int TA>
-int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st,
+                         const xct::OutRoute* route = nullptr) {
   xct::PlaneParams p = plane_params(pl, batch);
   p.tilesA = ceil_div(p.NA, TA);
   p.tilesB = ceil_div(p.NB, 32);
@@ -293,12 +294,17 @@ int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* 
   if (tasks < target_warps) chunks = (int)std::min<long long>((target_warps + tasks - 1) / tasks, std::max(1, p.n_list / 8));
   p.views_per_chunk = ceil_div(p.n_list, chunks);
   chunks = ceil_div(p.n_list, p.views_per_chunk);
+  const size_t smem = (size_t)kWarps * 2 * S * kAdjWin * sizeof(float);
+  if (route) {  // routed: every value is added into its row block's owner (the caller zeroed the blocks)
+    xct::plane_adjoint_kernel<G, IS3D, S, TA, kAdjWin, kWarps, true>
+        <<<dim3(blocks, chunks), kWarps * 32, smem, st>>>(p, in, nullptr, *route);
+    return launch_ok("plane_adjoint_kernel<route>");
+  }
   if (chunks > 1) {
     const size_t n_out = (size_t)p.NS * p.NA * p.NB;
     XCT_CUDA(cudaMemsetAsync(out, 0, n_out * sizeof(float), st));
   }
-  const size_t smem = (size_t)kWarps * 2 * S * kAdjWin * sizeof(float);
-  xct::plane_adjoint_kernel<G, IS3D, S, TA, kAdjWin, kWarps><<<dim3(blocks, chunks), kWarps * 32, smem, st>>>(p, in, out);
+  xct::plane_adjoint_kernel<G, IS3D, S, TA, kAdjWin, kWarps><<<dim3(blocks, chunks), kWarps * 32, smem, st>>>(p, in, out, xct::OutRoute{});
   return launch_ok("plane_adjoint_kernel");
 }
 
@@ -933,12 +939,102 @@ int xct_adjoint(const xct_plan* pl, const float* in, float* out, int32_t batch, 
   if (pl->ndim == 3) {
     if (pl->adj_walk && (reinterpret_cast<uintptr_t>(in) & 15) == 0) return launch_walk_adjoint(pl, in, out, st);
     if (pl->adj_plane) return launch_plane_adjoint<xct::Geom3, true, kAdj3S, kAdj3TA>(pl, 1, in, out, st);
-    xct::gen3d_adjoint_kernel<<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, out);
+    xct::gen3d_adjoint_kernel<false><<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, out, xct::OutRoute{});
     return launch_ok("gen3d_adjoint_kernel");
   }
   if (pl->adj_plane) return launch_plane_adjoint<xct::Geom2, false, kAdj2S, kAdj2TA>(pl, batch, in, out, st);
-  xct::gen2d_adjoint_kernel<<<general_grid(in_elems(pl) * batch), 256, 0, st>>>(gen2_params(pl, batch), in, out);
+  xct::gen2d_adjoint_kernel<false><<<general_grid(in_elems(pl) * batch), 256, 0, st>>>(gen2_params(pl, batch), in, out, xct::OutRoute{});
   return launch_ok("gen2d_adjoint_kernel");
+}
+
+// Back projection of a view block whose result rows go straight to their owners (view-block sharding):
+// the kernels' epilogue adds each value into the row block that holds it, across NVLink for a peer's
+// block, instead of writing a partial volume for a reduce-scatter.  The walk adjoint has no routed
+// variant: separable 3D plans use the plane adjoint here (z-slab sharding is the mode for them).
+int xct_adjoint_scatter(const xct_plan* pl, const float* in, const xct_out_route* r, void* stream) {
+  if (!pl || !in || !r) return fail(XCT_ERR_INVALID, "null argument");
+  if (pl->dry) return fail(XCT_ERR_INVALID, "analysis-only plan");
+  const int rows = pl->n0;
+  if (r->nparts < 1 || r->nparts > XCT_MAX_ROUTE_PARTS) return fail(XCT_ERR_INVALID, "route: nparts outside [1, XCT_MAX_ROUTE_PARTS]");
+  if (r->row_begin[0] != 0 || r->row_begin[r->nparts] != rows)
+    return fail(XCT_ERR_INVALID, "route: row blocks must cover [0, n0) of the adjoint's result");
+  xct::OutRoute route{};
+  static_assert(XCT_MAX_ROUTE_PARTS == xct::kMaxRouteParts, "header and kernels disagree");
+  route.nparts = r->nparts;
+  route.inner = pl->ndim == 3 ? (long long)pl->n1 * pl->n2 : (long long)pl->n1;
+  for (int k = 0; k < r->nparts; ++k) {
+    if (r->row_begin[k + 1] < r->row_begin[k]) return fail(XCT_ERR_INVALID, "route: row_begin must be non-decreasing");
+    if (r->row_begin[k + 1] > r->row_begin[k] && !r->ptr[k]) return fail(XCT_ERR_INVALID, "route: null pointer for a non-empty block");
+    route.ptr[k] = r->ptr[k];
+    route.row_begin[k] = r->row_begin[k];
+  }
+  for (int k = r->nparts; k <= xct::kMaxRouteParts; ++k) route.row_begin[k] = rows;
+  DeviceGuard guard(pl->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pl->ndim == 3) {
+    if (pl->adj_plane) return launch_plane_adjoint<xct::Geom3, true, kAdj3S, kAdj3TA>(pl, 1, in, nullptr, st, &route);
+    xct::gen3d_adjoint_kernel<true><<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, nullptr, route);
+    return launch_ok("gen3d_adjoint_kernel<route>");
+  }
+  if (pl->adj_plane) return launch_plane_adjoint<xct::Geom2, false, kAdj2S, kAdj2TA>(pl, 1, in, nullptr, st, &route);
+  xct::gen2d_adjoint_kernel<true><<<general_grid(in_elems(pl)), 256, 0, st>>>(gen2_params(pl, 1), in, nullptr, route);
+  return launch_ok("gen2d_adjoint_kernel<route>");
+}
+
+// ---- device buffers other processes of the node can map (CUDA IPC over NVLink / NVSwitch) ----
+int xct_peer_alloc(int32_t device, size_t bytes, void** ptr, xct_ipc_handle* handle) {
+  if (!ptr || !handle || bytes == 0) return fail(XCT_ERR_INVALID, "null argument or empty buffer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(handle->bytes), "xct_ipc_handle must hold a cudaIpcMemHandle_t");
+  int rc = check_device(device);
+  if (rc) return rc;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
+  void* p = nullptr;
+  XCT_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(XCT_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  std::memcpy(handle->bytes, &h, sizeof(h));
+  *ptr = p;
+  return XCT_OK;
+}
+int xct_peer_open(int32_t device, const xct_ipc_handle* handle, void** ptr) {
+  if (!ptr || !handle) return fail(XCT_ERR_INVALID, "null argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle->bytes, sizeof(h));
+  XCT_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return XCT_OK;
+}
+int xct_peer_zero(int32_t device, void* ptr, size_t bytes, void* stream) {
+  if (!ptr) return fail(XCT_ERR_INVALID, "null argument");
+  DeviceGuard guard(device);
+  XCT_CUDA(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream));
+  return XCT_OK;
+}
+int xct_peer_copy_out(int32_t device, void* dst, const void* src, size_t bytes, void* stream) {
+  if (!dst || !src) return fail(XCT_ERR_INVALID, "null argument");
+  DeviceGuard guard(device);
+  XCT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return XCT_OK;
+}
+int xct_peer_close(int32_t device, void* ptr) {
+  if (!ptr) return XCT_OK;
+  DeviceGuard guard(device);
+  XCT_CUDA(cudaIpcCloseMemHandle(ptr));
+  return XCT_OK;
+}
+int xct_peer_free(int32_t device, void* ptr) {
+  if (!ptr) return XCT_OK;
+  DeviceGuard guard(device);
+  XCT_CUDA(cudaFree(ptr));
+  return XCT_OK;
 }
 
 // Pipelined host path for 3D separable plans with unit, monotone rows: the volume is cut into

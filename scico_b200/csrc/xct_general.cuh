@@ -54,8 +54,11 @@ __device__ __forceinline__ float voxel_coord(int idx, int offset) {
 }
 
 // thread = one voxel (k fastest); views in ascending order, taps in the reference's order.
+// ROUTE: add into the slab owners' memory (OutRoute, xct_geom.cuh) instead of storing to `vol`.
+template <bool ROUTE = false>
 __global__ void __launch_bounds__(256)
-gen3d_adjoint_kernel(Gen3Params p, const float* __restrict__ sino, float* __restrict__ vol) {
+gen3d_adjoint_kernel(Gen3Params p, const float* __restrict__ sino, float* __restrict__ vol,
+                     const __grid_constant__ OutRoute route) {
   const size_t n = (size_t)p.N0 * p.N1 * p.N2;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -74,7 +77,8 @@ gen3d_adjoint_kernel(Gen3Params p, const float* __restrict__ sino, float* __rest
       if (t.w[2] != 0.f) acc = fmaf(__ldg(y + base + 1), t.w[2], acc);
       if (t.w[3] != 0.f) acc = fmaf(__ldg(y + base + p.D1 + 1), t.w[3], acc);
     }
-    vol[idx] = acc;
+    if constexpr (ROUTE) route_add(route, i, (long long)j * p.N2 + k, acc);
+    else vol[idx] = acc;
   }
 }
 
@@ -128,8 +132,10 @@ struct Gen2Params {
 };
 
 // thread = one pixel of one batch item; gathers both taps for every view.
+template <bool ROUTE = false>  // ROUTE: one image, rows added into the row-block owners' memory
 __global__ void __launch_bounds__(256)
-gen2d_adjoint_kernel(Gen2Params p, const float* __restrict__ sino, float* __restrict__ im) {
+gen2d_adjoint_kernel(Gen2Params p, const float* __restrict__ sino, float* __restrict__ im,
+                     const __grid_constant__ OutRoute route) {
   const size_t npix = (size_t)p.N0 * p.N1, n = npix * p.batch;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -147,7 +153,8 @@ gen2d_adjoint_kernel(Gen2Params p, const float* __restrict__ sino, float* __rest
       if (c >= 0 && c < p.ny) s0 = fmaf(__ldg(y + c), w0, s0);
       if (c + 1 >= 0 && c + 1 < p.ny) s1 = fmaf(__ldg(y + c + 1), w1, s1);
     }
-    im[idx] = s0 + s1;
+    if constexpr (ROUTE) route_add(route, i, j, s0 + s1);
+    else im[idx] = s0 + s1;
   }
 }
 

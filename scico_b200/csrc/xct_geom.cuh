@@ -124,4 +124,25 @@ struct __align__(16) RowRec {
   int32_t pad;
 };
 
+// ---- routed output of the adjoint (view-block sharding, xct_adjoint_scatter) --------------------
+// The adjoint's result is cut along its axis 0 into `nparts` row blocks; block k lives in the memory
+// behind ptr[k] -- the buffer of the GPU that owns that block, reached through a CUDA-IPC mapping over
+// NVLink when it is not the local one.  Every kernel that takes a route ADDS its values (RED.ADD.F32,
+// fire-and-forget, also across NVLink) instead of storing them: the partial back projections of all
+// view blocks meet in the owner's memory and no partial volume is written, sent and summed afterwards.
+constexpr int kMaxRouteParts = 16;
+struct OutRoute {
+  float* ptr[kMaxRouteParts];
+  int row_begin[kMaxRouteParts + 1];  // block k holds rows [row_begin[k], row_begin[k + 1])
+  int nparts;
+  long long inner;  // elements per row (product of the trailing dims)
+};
+// out[row][rest] += val, in the memory of the part that owns `row`
+__device__ __forceinline__ void route_add(const OutRoute& r, int row, long long rest, float val) {
+  int k = 0;
+  for (int q = 1; q < r.nparts; ++q) k += row >= r.row_begin[q] ? 1 : 0;
+  // system scope: the other GPUs of the node add to the same block at the same time
+  atomicAdd_system(r.ptr[k] + (long long)(row - r.row_begin[k]) * r.inner + rest, val);
+}
+
 }  // namespace xct

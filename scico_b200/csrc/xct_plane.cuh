@@ -64,9 +64,12 @@ __device__ __forceinline__ int window_start(const ViewRec& vr, int a_lo, int a_h
 
 // ------------------------------------------------------------------------------------ adjoint
 // Tile: TA rows (axis A) x 32 columns (axis B, lane = column) x S slices.  WIN = staged bins.
-template <class G, bool IS3D, int S, int TA, int WIN, int WARPS>
+// ROUTE: the result is ADDED into the row blocks of `route` (the owners' memory, possibly across NVLink)
+// instead of being stored to `out`; 2D: one image, row = image axis 0; 3D: row = slice.
+template <class G, bool IS3D, int S, int TA, int WIN, int WARPS, bool ROUTE = false>
 __global__ void __launch_bounds__(WARPS * 32)
-plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __restrict__ out) {
+plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __restrict__ out,
+                     const __grid_constant__ OutRoute route) {
   static_assert(WIN % 32 == 0, "window is staged 32 bins at a time");
   constexpr int Q = WIN / 32;
   extern __shared__ __align__(128) float smem[];
@@ -184,6 +187,11 @@ plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __res
 #pragma unroll
       for (int n = 0; n < TA; ++n) {
         if (a0 + n < p.NA) {
+          if constexpr (ROUTE) {
+            if (IS3D) route_add(route, s0 + s, (long long)(a0 + n) * p.NB + b, acc[n][s]);
+            else route_add(route, a0 + n, b, acc[n][s]);
+            continue;
+          }
           float* o = out + ((size_t)(s0 + s) * p.NA + (a0 + n)) * (size_t)p.NB + b;
           if (gridDim.y > 1) atomicAdd(o, acc[n][s]);
           else *o = acc[n][s];

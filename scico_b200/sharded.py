@@ -151,8 +151,135 @@ class SlabShardedXRayTransform3D:
     adj = back_project
 
 
+class PeerBlocks:
+    """Row blocks of a view-sharded back projection, held in device memory that every GPU of the node can
+    add into (``xct_peer_alloc`` + CUDA IPC: one process per GPU, the blocks of the other ranks are mapped
+    through NVLink / NVSwitch peer access).
+
+    ``exchange(launch, out)`` runs one fused back projection + exchange step:
+
+    1. ``launch(ptrs, row_begin)`` enqueues this rank's ``xct_adjoint_scatter``: the kernel's epilogue adds
+       every result row into the block of the rank that owns it (``RED.ADD.F32``, system scope);
+    2. one stream-ordered rendezvous (a one-element NCCL all-reduce): when it completes on this rank's
+       stream, every rank's kernel has finished, so this rank's block holds the complete sum;
+    3. the block is copied to ``out`` and zeroed again for its next use.
+
+    Two copies of every block alternate between calls, which is what makes ONE rendezvous per call enough:
+    a peer can only add into copy ``c`` again two calls later, i.e. after a rendezvous that this rank joined
+    after zeroing ``c``.  No partial volume is written, sent or summed by a separate collective."""
+
+    COPIES = 2
+
+    def __init__(self, slabs: Sequence[tuple[int, int]], inner_shape: Sequence[int], group=None,
+                 rank: Optional[int] = None, world_size: Optional[int] = None, device: Optional[int] = None):
+        import ctypes
+
+        from . import _lib
+
+        if torch is None or not torch.cuda.is_available():
+            raise RuntimeError("PeerBlocks needs CUDA devices (there is no CPU path)")
+        self._lib, self._L = _lib, _lib.lib()
+        self.group = group
+        r, w = _world(group)
+        self.rank = r if rank is None else rank
+        self.world_size = w if world_size is None else world_size
+        if len(slabs) != self.world_size or self.world_size > _lib.MAX_ROUTE_PARTS:
+            raise ValueError(f"need one row block per rank and at most {_lib.MAX_ROUTE_PARTS} ranks")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.slabs = [tuple(sl) for sl in slabs]
+        self.row_begin = [self.slabs[0][0]] + [b for _, b in self.slabs]
+        self.inner_shape = tuple(int(n) for n in inner_shape)
+        rows = self.slabs[self.rank][1] - self.slabs[self.rank][0]
+        self.local_shape = (rows,) + self.inner_shape
+        self.nbytes = 4 * rows * int(np.prod(self.inner_shape))
+        alloc = max(self.nbytes, 256)  # an empty block still needs a valid pointer
+        self._own: list[int] = []
+        self._mapped: list[int] = []
+        handles = []
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for _ in range(self.COPIES):
+            ptr, h = ctypes.c_void_p(), _lib.IpcHandle()
+            _lib.check(self._L.xct_peer_alloc(self.device, alloc, ctypes.byref(ptr), ctypes.byref(h)))
+            _lib.check(self._L.xct_peer_zero(self.device, ptr, alloc, stream))
+            self._own.append(ptr.value)
+            handles.append(bytes(h.bytes))
+        torch.cuda.synchronize(self.device)
+        gathered = [None] * self.world_size
+        if self.world_size > 1:
+            dist.all_gather_object(gathered, handles, group=group)
+        else:
+            gathered[0] = handles
+        self.ptrs: list[list[int]] = []
+        for c in range(self.COPIES):
+            row = []
+            for k in range(self.world_size):
+                if k == self.rank:
+                    row.append(self._own[c])
+                    continue
+                h = _lib.IpcHandle()
+                ctypes.memmove(h.bytes, gathered[k][c], 64)
+                q = ctypes.c_void_p()
+                _lib.check(self._L.xct_peer_open(self.device, ctypes.byref(h), ctypes.byref(q)))
+                self._mapped.append(q.value)
+                row.append(q.value)
+            self.ptrs.append(row)
+        self._token = torch.zeros(1, dtype=torch.float32, device=f"cuda:{self.device}")
+        self._turn = 0
+        if self.world_size > 1:
+            dist.barrier(group=group)  # every block is zeroed and mapped before anybody adds into it
+
+    def exchange(self, launch: Callable[[list, list], None], out):
+        if tuple(out.shape) != self.local_shape or not out.is_contiguous() or out.dtype != torch.float32:
+            raise ValueError(f"'out' must be a contiguous float32 tensor of shape {self.local_shape}")
+        c = self._turn
+        self._turn = (c + 1) % self.COPIES
+        launch(self.ptrs[c], self.row_begin)
+        if self.world_size > 1:
+            dist.all_reduce(self._token, group=self.group)  # stream-ordered: no host synchronisation
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if self.nbytes:
+            self._lib.check(self._L.xct_peer_copy_out(self.device, out.data_ptr(), self._own[c], self.nbytes, stream))
+            self._lib.check(self._L.xct_peer_zero(self.device, self._own[c], self.nbytes, stream))
+        return out
+
+    def close(self, collective: bool = True):
+        """Unmap the peers' blocks and free this rank's (``collective``: rendezvous first, so that no peer is
+        still adding into them)."""
+        if self._L is None:
+            return
+        if collective and self.world_size > 1 and dist.is_initialized():
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+        for q in self._mapped:
+            self._L.xct_peer_close(self.device, q)
+        if collective and self.world_size > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+        for q in self._own:
+            self._L.xct_peer_free(self.device, q)
+        self._mapped, self._own, self._L = [], [], None
+
+    def __del__(self):
+        try:
+            self.close(collective=False)
+        except Exception:  # interpreter shutdown
+            pass
+
+
 class _ViewSharded:
     """Shared machinery of the view-block partitions (volume / image rows sharded on axis 0)."""
+
+    def _setup_exchange(self, exchange, inner_shape):
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        self.exchange = exchange
+        self.peer = None
+        if exchange == "peer" and self.world_size > 1:
+            self.peer = PeerBlocks(self.slabs, inner_shape, group=self.group, rank=self.rank, world_size=self.world_size)
+
+    def close(self):
+        if getattr(self, "peer", None) is not None:
+            self.peer.close()
+            self.peer = None
 
     def _setup(self, n_views, axis0, group, rank, world_size):
         self.group = group
@@ -203,14 +330,17 @@ class ViewShardedXRayTransform3D(_ViewSharded):
     ``project(x_slab)``: all-gathers the slab-sharded volume and projects it onto this rank's views
     ``(v1-v0, D0, D1)``.  ``back_project(y_views)``: back-projects the local views slab by slab
     (one plan per destination slab, ``slice_offset`` = slab start) and sum-reduces each slab into
-    its owner; returns this rank's slab ``(z1-z0, N1, N2)``."""
+    its owner; returns this rank's slab ``(z1-z0, N1, N2)``.  ``exchange="peer"``: ONE back projection
+    kernel whose epilogue adds every slice into its owner's slab through NVLink peer memory
+    (:class:`PeerBlocks`, ``xct_adjoint_scatter``) instead of the per-slab NCCL reductions."""
 
     def __init__(self, input_shape, matrices, det_shape, group=None, op_factory: Optional[Callable] = None,
-                 rank: Optional[int] = None, world_size: Optional[int] = None):
+                 rank: Optional[int] = None, world_size: Optional[int] = None, exchange: str = "nccl"):
         self.input_shape = tuple(int(s) for s in input_shape)
         self.det_shape = tuple(int(s) for s in det_shape)
         self.matrices = np.asarray(matrices, dtype=np.float32)
         self._setup(len(self.matrices), self.input_shape[0], group, rank, world_size)
+        self._setup_exchange(exchange, self.input_shape[1:])
         v0, v1 = self.views
         self.local_output_shape = (v1 - v0,) + self.det_shape
         z0, z1 = self.slab
@@ -235,6 +365,12 @@ class ViewShardedXRayTransform3D(_ViewSharded):
         if tuple(y_views.shape) != self.local_output_shape:
             raise ValueError(f"local views of shape {tuple(y_views.shape)} do not match {self.local_output_shape}")
 
+        if self.peer is not None:  # fused: the kernel adds every slice into its owner's slab over NVLink
+            out = y_views.new_empty(self.local_input_shape)
+            launch = (lambda ptrs, rb: self.full.back_project_scatter(y_views, ptrs, rb)) if self.full is not None \
+                else (lambda ptrs, rb: None)
+            return self.peer.exchange(launch, out)
+
         def part(j):
             a, b = self.slabs[j]
             if self.per_slab[j] is None:
@@ -253,13 +389,16 @@ class ViewShardedXRayTransform2D(_ViewSharded):
     The image is small next to the sinogram, so it is kept replicated: ``project(x)`` maps the
     full image to this rank's views ``(v1-v0, ny)``; ``back_project(y_views)`` returns either the
     row block this rank owns (``scatter=True``, reduce per row block) or the full image on every
-    rank (``scatter=False``, all-reduce)."""
+    rank (``scatter=False``, all-reduce).  ``exchange="peer"``: the scatter case runs ONE kernel whose
+    epilogue adds every image row into its owner's block through NVLink peer memory
+    (:class:`PeerBlocks`, ``xct_adjoint_scatter``) instead of back projection + NCCL reduce-scatter."""
 
     def __init__(self, input_shape, angles, group=None, op_factory: Optional[Callable] = None,
-                 rank: Optional[int] = None, world_size: Optional[int] = None, **kw):
+                 rank: Optional[int] = None, world_size: Optional[int] = None, exchange: str = "nccl", **kw):
         self.input_shape = tuple(int(s) for s in input_shape)
         self.angles = np.asarray(angles, dtype=np.float64)
         self._setup(len(self.angles), self.input_shape[0], group, rank, world_size)
+        self._setup_exchange(exchange, self.input_shape[1:])
         v0, v1 = self.views
         if kw.get("det_count") is None:  # the default depends on the image only, not on the views
             kw["det_count"] = int(np.ceil(np.linalg.norm(self.input_shape)))
@@ -278,6 +417,11 @@ class ViewShardedXRayTransform2D(_ViewSharded):
     def back_project(self, y_views, scatter: bool = True):
         if tuple(y_views.shape) != self.local_output_shape:
             raise ValueError(f"local views of shape {tuple(y_views.shape)} do not match {self.local_output_shape}")
+        if self.peer is not None and scatter:  # fused: image rows are added into their owners over NVLink
+            out = y_views.new_empty((self.slab[1] - self.slab[0],) + self.input_shape[1:])
+            launch = (lambda ptrs, rb: self.local.back_project_scatter(y_views, ptrs, rb)) if self.local is not None \
+                else (lambda ptrs, rb: None)
+            return self.peer.exchange(launch, out)
         full = self.local.back_project(y_views) if self.local is not None else y_views.new_zeros(self.input_shape)
         if self.world_size == 1:
             return full

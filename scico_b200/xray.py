@@ -133,6 +133,30 @@ def _analyse(fn, geom) -> dict:
     return d
 
 
+def _apply_scatter(plans: _Plans, y, ptrs, row_begin):
+    """Back projection of the CUDA tensor ``y`` whose result rows are ADDED into the row blocks behind
+    ``ptrs`` (device pointers, local or peer-mapped; block ``k`` = rows ``[row_begin[k], row_begin[k+1])``
+    of axis 0): ``xct_adjoint_scatter``.  Asynchronous on the current stream."""
+    if not (torch is not None and isinstance(y, torch.Tensor) and y.is_cuda):
+        raise ValueError("back_project_scatter needs a CUDA tensor")
+    if len(ptrs) + 1 != len(row_begin) or not 1 <= len(ptrs) <= _lib.MAX_ROUTE_PARTS:
+        raise ValueError(f"need 1..{_lib.MAX_ROUTE_PARTS} row blocks and one more row boundary than blocks")
+    route = _lib.OutRoute()
+    route.nparts = len(ptrs)
+    for k, b in enumerate(row_begin):
+        route.row_begin[k] = int(b)
+    for k, q in enumerate(ptrs):
+        route.ptr[k] = int(q) if q else None
+    dev = y.device.index
+    yin = y.detach()
+    if yin.dtype != torch.float32:
+        yin = yin.to(torch.float32)
+    yin = yin.contiguous()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.lib().xct_adjoint_scatter(plans.get(dev), yin.data_ptr(), ctypes.byref(route), stream))
+
+
 class XRayTransform2D(LinearOperator):
     r"""Parallel ray, single axis, 2D X-ray projector (``_xray2d.py:29-136``).
 
@@ -216,6 +240,14 @@ class XRayTransform2D(LinearOperator):
         """X-ray back projection, ``H.T @ y`` (exact adjoint of :meth:`project`)."""
         batch, lead = self._batch(y, self.output_shape)
         return _apply(self._plans, y, lead + self.nx, False, batch, _device_index(self.input_device), out)
+
+    def back_project_scatter(self, y, ptrs, row_begin) -> None:
+        """Back projection fused with the view-block exchange: image row ``i`` is ADDED into the row
+        block that owns it (``ptrs[k]``: device pointer of rows ``[row_begin[k], row_begin[k+1])``, local or a
+        peer GPU's, see :class:`scico_b200.sharded.PeerBlocks`).  One image, CUDA tensors only."""
+        if tuple(y.shape) != self.output_shape:
+            raise ValueError(f"array of shape {tuple(y.shape)} does not match {self.output_shape}")
+        _apply_scatter(self._plans, y, ptrs, row_begin)
 
     @staticmethod
     def _batch(a, core):
@@ -325,6 +357,14 @@ class XRayTransform3D(LinearOperator):
         if tuple(proj.shape) != self.output_shape:
             raise ValueError(f"array of shape {tuple(proj.shape)} does not match {self.output_shape}")
         return _apply(self._plans, proj, self.input_shape, False, 1, _device_index(self.input_device), out)
+
+    def back_project_scatter(self, proj, ptrs, row_begin) -> None:
+        """Back projection fused with the view-block exchange: slice ``i`` of the result is ADDED into the
+        slab that owns it (``ptrs[k]``: device pointer of slices ``[row_begin[k], row_begin[k+1])``, local or a
+        peer GPU's, see :class:`scico_b200.sharded.PeerBlocks`).  CUDA tensors only."""
+        if tuple(proj.shape) != self.output_shape:
+            raise ValueError(f"array of shape {tuple(proj.shape)} does not match {self.output_shape}")
+        _apply_scatter(self._plans, proj, ptrs, row_begin)
 
     matrices_from_euler_angles = staticmethod(matrices_from_euler_angles)
 

@@ -75,6 +75,38 @@ def _worker(rank, world, port, case):
             assert O.rel_l2(got, C.project_2d(x, T, op.ny)[v0:v1]) <= 1e-5
             back = op.back_project(torch.as_tensor(np.ascontiguousarray(y[v0:v1]), device=dev)).cpu().numpy()
             assert O.rel_l2(back, C.back_project_2d(y, T, nx)[z0:z1]) <= 1e-5
+        elif case == "view2d_peer":
+            # back projection fused with the exchange: rows added into their owners over NVLink peer memory
+            nx, V = (200, 168), 48
+            angles = np.linspace(0, np.pi, V, endpoint=False)
+            op = sharded.ViewShardedXRayTransform2D(nx, angles, exchange="peer")
+            nccl = sharded.ViewShardedXRayTransform2D(nx, angles)
+            T = sb.XRayTransform2D(nx, angles).view_table
+            (z0, z1), (v0, v1) = op.slab, op.views
+            assert op.peer is not None
+            for it in range(4):  # both block copies are reused
+                y = rng.standard_normal((V, op.ny)).astype(np.float32)
+                yv = torch.as_tensor(np.ascontiguousarray(y[v0:v1]), device=dev)
+                back = op.back_project(yv)
+                assert tuple(back.shape) == (z1 - z0, nx[1])
+                assert O.rel_l2(back.cpu().numpy(), C.back_project_2d(y, T, nx)[z0:z1]) <= 1e-5, it
+                ref = nccl.back_project(yv)
+                assert (torch.linalg.vector_norm(back - ref) / torch.linalg.vector_norm(ref)).item() <= 1e-6
+            op.close()
+        elif case == "view3d_peer":
+            N, D, V = (20, 24, 28), (30, 36), 10
+            ang = np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, 0.5)], 1)
+            M = sb.matrices_from_euler_angles(N, D, "XY", ang)
+            op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange="peer")
+            (z0, z1), (v0, v1) = op.slab, op.views
+            for it in range(3):
+                y = rng.standard_normal((V,) + D).astype(np.float32)
+                back = op.back_project(torch.as_tensor(np.ascontiguousarray(y[v0:v1]), device=dev)).cpu().numpy()
+                assert O.rel_l2(back, C.back_project_3d(y, op.matrices, N)[z0:z1]) <= 1e-5, it
+            x = rng.standard_normal(N).astype(np.float32)
+            got = op.project(torch.as_tensor(x[z0:z1], device=dev)).cpu().numpy()
+            assert O.rel_l2(got, C.project_3d(x, op.matrices, D)[v0:v1]) <= 1e-5
+            op.close()
         elif case == "pdhg_slab":
             from scico_b200.optimize import TVPDHG
 
@@ -128,7 +160,7 @@ def _worker(rank, world, port, case):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["slab", "slab_halo", "view3d", "view2d", "pdhg_slab", "admm_slab", "ladmm_slab", "padmm_slab"])
+@pytest.mark.parametrize("case", ["slab", "slab_halo", "view3d", "view2d", "view2d_peer", "view3d_peer", "pdhg_slab", "admm_slab", "ladmm_slab", "padmm_slab"])
 def test_sharded_operators_nccl(case):
     import torch
     import torch.multiprocessing as mp
