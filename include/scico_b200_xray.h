@@ -153,10 +153,11 @@ XCT_API int xct_adjoint(const xct_plan *plan, const float *in_dev, float *out_de
  * With the views split over the GPUs of a node (BASELINE.json configs[2]; general 3D matrices) every GPU
  * back-projects its view block onto the WHOLE image / volume, and the partial results have to be summed
  * into the row block (axis 0) each GPU owns -- the reduce-scatter of SURVEY.md 8e.  xct_adjoint_scatter
- * does both in one kernel: its epilogue adds every value straight into the owner's block (RED.ADD.F32
- * through a CUDA-IPC mapping, i.e. over NVLink / NVSwitch for a peer's block), so no partial volume is
- * written, sent and summed afterwards.  Protocol (see scico_b200/sharded.py): every rank zeroes its block,
- * all ranks synchronise, every rank calls xct_adjoint_scatter, all ranks synchronise again.
+ * does both in one kernel: its epilogue writes every value straight into the owner's memory (through a
+ * CUDA-IPC mapping, i.e. over NVLink / NVSwitch for a peer's block), so no partial volume is written, sent
+ * and summed by a separate collective.  Protocol (scico_b200/sharded.py::PeerBlocks): every rank calls
+ * xct_adjoint_scatter on one of two alternating copies of the blocks, all ranks meet once (stream-ordered),
+ * every owner sums the slots it received (store mode) or copies its block out and re-zeroes it (add mode).
  * Replaces, for this mode, XRayTransform*._back_project (_xray2d.py:267-306, _xray3d.py:161-204) followed
  * by the cross-device sum the reference leaves to jax.Array sharding. */
 #define XCT_MAX_ROUTE_PARTS 16
@@ -164,9 +165,13 @@ typedef struct xct_out_route {
   int32_t nparts;                             /* row blocks = GPUs of the node */
   int32_t row_begin[XCT_MAX_ROUTE_PARTS + 1]; /* block k holds rows [row_begin[k], row_begin[k+1]) of axis 0 */
   float *ptr[XCT_MAX_ROUTE_PARTS];            /* DEVICE pointer (local or peer-mapped) of block k: (rows_k, *trailing dims) */
+  int32_t store; /* 0: values are ADDED to the blocks (RED.ADD.F32, system scope; zero them first, every rank
+                  *    targets the same block).  1: values are STORED (each element exactly once per call):
+                  *    ptr[k] is then this rank's own slot in the owner's staging area and the owner sums the
+                  *    slots afterwards with xct_sum_slots (posted NVLink writes, deterministic sum order). */
 } xct_out_route;
-/* in: (*output_shape) of the plan, DEVICE pointer.  The blocks are ADDED to (zero them first).  One image /
- * volume per call (no batch).  Asynchronous on `stream`, no allocation, no host synchronisation. */
+/* in: (*output_shape) of the plan, DEVICE pointer.  One image / volume per call (no batch).  Asynchronous on
+ * `stream`, no allocation, no host synchronisation. */
 XCT_API int xct_adjoint_scatter(const xct_plan *plan, const float *in_dev, const xct_out_route *route, void *stream);
 
 /* Device buffers the other processes of the node can map (cudaMalloc + CUDA IPC; one process per GPU). */
@@ -175,6 +180,9 @@ XCT_API int xct_peer_alloc(int32_t device, size_t bytes, void **ptr, xct_ipc_han
 XCT_API int xct_peer_open(int32_t device, const xct_ipc_handle *handle, void **ptr); /* another process's buffer */
 XCT_API int xct_peer_zero(int32_t device, void *ptr, size_t bytes, void *stream);                       /* async memset 0 */
 XCT_API int xct_peer_copy_out(int32_t device, void *dst_dev, const void *src, size_t bytes, void *stream); /* async D2D copy */
+/* dst[i] = ((slot_0[i] + slot_1[i]) + ...) for i < n; slot s starts at slots + s * pitch (elements). */
+XCT_API int xct_sum_slots(int32_t device, float *dst_dev, const float *slots_dev, int32_t nslots, size_t n, size_t pitch,
+                          void *stream);
 XCT_API int xct_peer_close(int32_t device, void *ptr); /* unmap (xct_peer_open) */
 XCT_API int xct_peer_free(int32_t device, void *ptr);  /* release (xct_peer_alloc) */
 

@@ -54,6 +54,7 @@ EXPORTED_SYMBOLS = (
     "xct_peer_open",
     "xct_peer_zero",
     "xct_peer_copy_out",
+    "xct_sum_slots",
     "xct_peer_close",
     "xct_peer_free",
     "xct_launch_count",
@@ -140,6 +141,7 @@ class OutRoute(ctypes.Structure):
         ("nparts", c_int32),
         ("row_begin", c_int32 * (MAX_ROUTE_PARTS + 1)),
         ("ptr", c_void_p * MAX_ROUTE_PARTS),
+        ("store", c_int32),
     ]
 
 
@@ -193,6 +195,7 @@ def lib() -> ctypes.CDLL:
     L.xct_peer_open.argtypes = [c_int32, POINTER(IpcHandle), POINTER(c_void_p)]
     L.xct_peer_zero.argtypes = [c_int32, c_void_p, ctypes.c_size_t, c_void_p]
     L.xct_peer_copy_out.argtypes = [c_int32, c_void_p, c_void_p, ctypes.c_size_t, c_void_p]
+    L.xct_sum_slots.argtypes = [c_int32, c_void_p, c_void_p, c_int32, ctypes.c_size_t, ctypes.c_size_t, c_void_p]
     L.xct_peer_close.argtypes = [c_int32, c_void_p]
     L.xct_peer_free.argtypes = [c_int32, c_void_p]
     L.xct3d_debug_weights.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]

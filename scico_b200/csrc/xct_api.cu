@@ -295,7 +295,11 @@ int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* 
   p.views_per_chunk = ceil_div(p.n_list, chunks);
   chunks = ceil_div(p.n_list, p.views_per_chunk);
   const size_t smem = (size_t)kWarps * 2 * S * kAdjWin * sizeof(float);
-  if (route) {  // routed: every value is added into its row block's owner (the caller zeroed the blocks)
+  if (route && route->store) {  // plain stores: every element must be written exactly once, so no view split
+    chunks = 1;
+    p.views_per_chunk = p.n_list;
+  }
+  if (route) {  // routed: every value goes to its row block's owner (add mode: the caller zeroed the blocks)
     xct::plane_adjoint_kernel<G, IS3D, S, TA, kAdjWin, kWarps, true>
         <<<dim3(blocks, chunks), kWarps * 32, smem, st>>>(p, in, nullptr, *route);
     return launch_ok("plane_adjoint_kernel<route>");
@@ -961,6 +965,7 @@ int xct_adjoint_scatter(const xct_plan* pl, const float* in, const xct_out_route
   xct::OutRoute route{};
   static_assert(XCT_MAX_ROUTE_PARTS == xct::kMaxRouteParts, "header and kernels disagree");
   route.nparts = r->nparts;
+  route.store = r->store ? 1 : 0;
   route.inner = pl->ndim == 3 ? (long long)pl->n1 * pl->n2 : (long long)pl->n1;
   for (int k = 0; k < r->nparts; ++k) {
     if (r->row_begin[k + 1] < r->row_begin[k]) return fail(XCT_ERR_INVALID, "route: row_begin must be non-decreasing");
@@ -1023,6 +1028,13 @@ int xct_peer_copy_out(int32_t device, void* dst, const void* src, size_t bytes, 
   DeviceGuard guard(device);
   XCT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return XCT_OK;
+}
+int xct_sum_slots(int32_t device, float* dst, const float* slots, int32_t nslots, size_t n, size_t pitch, void* stream) {
+  if (!dst || !slots || nslots < 1 || pitch < n) return fail(XCT_ERR_INVALID, "xct_sum_slots: bad argument");
+  if (n == 0) return XCT_OK;
+  DeviceGuard guard(device);
+  xct::sum_slots_kernel<<<general_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(dst, slots, nslots, n, pitch);
+  return launch_ok("sum_slots_kernel");
 }
 int xct_peer_close(int32_t device, void* ptr) {
   if (!ptr) return XCT_OK;

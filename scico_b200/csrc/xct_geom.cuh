@@ -126,23 +126,68 @@ struct __align__(16) RowRec {
 
 // ---- routed output of the adjoint (view-block sharding, xct_adjoint_scatter) --------------------
 // The adjoint's result is cut along its axis 0 into `nparts` row blocks; block k lives in the memory
-// behind ptr[k] -- the buffer of the GPU that owns that block, reached through a CUDA-IPC mapping over
-// NVLink when it is not the local one.  Every kernel that takes a route ADDS its values (RED.ADD.F32,
-// fire-and-forget, also across NVLink) instead of storing them: the partial back projections of all
-// view blocks meet in the owner's memory and no partial volume is written, sent and summed afterwards.
+// behind ptr[k] -- a buffer of the GPU that owns that block, reached through a CUDA-IPC mapping over
+// NVLink when it is not the local one.  Two ways for the partial back projections of all view blocks
+// to meet in the owner's memory, neither of which writes a partial volume for a later collective:
+//   store (default of sharded.PeerBlocks): ptr[k] is THIS rank's slot in the owner's staging area; plain
+//          posted stores (full NVLink write bandwidth); the owner sums the slots in rank order afterwards
+//          (sum_slots_kernel: deterministic);
+//   add:   ptr[k] is the block itself and every rank adds into it (RED.ADD.F32, system scope).
 constexpr int kMaxRouteParts = 16;
 struct OutRoute {
   float* ptr[kMaxRouteParts];
   int row_begin[kMaxRouteParts + 1];  // block k holds rows [row_begin[k], row_begin[k + 1])
   int nparts;
+  int store;        // 1: plain stores (each element is written exactly once per launch); 0: RED.ADD
   long long inner;  // elements per row (product of the trailing dims)
 };
-// out[row][rest] += val, in the memory of the part that owns `row`
+// out[row][rest] (+)= val, in the memory of the part that owns `row`
 __device__ __forceinline__ void route_add(const OutRoute& r, int row, long long rest, float val) {
   int k = 0;
+#pragma unroll 1
   for (int q = 1; q < r.nparts; ++q) k += row >= r.row_begin[q] ? 1 : 0;
-  // system scope: the other GPUs of the node add to the same block at the same time
-  atomicAdd_system(r.ptr[k] + (long long)(row - r.row_begin[k]) * r.inner + rest, val);
+  float* q = r.ptr[k] + (long long)(row - r.row_begin[k]) * r.inner + rest;
+  if (r.store) *q = val;
+  else atomicAdd_system(q, val);  // system scope: the other GPUs of the node add to the same block
+}
+
+// Owner lookup done once for a run of rows that share it (see the routed epilogue of plane_adjoint_kernel).
+struct RouteCursor {
+  float* q;  // address of (row, rest) in the owner's memory
+  int next;  // first row of the next block
+  __device__ __forceinline__ void seek(const OutRoute& r, int row, long long rest) {
+    int k = 0;
+#pragma unroll 1
+    for (int j = 1; j < r.nparts; ++j) k += row >= r.row_begin[j] ? 1 : 0;
+    next = r.row_begin[k + 1];
+    q = r.ptr[k] + (long long)(row - r.row_begin[k]) * r.inner + rest;
+  }
+};
+
+// dst[i] = ((slot_0[i] + slot_1[i]) + slot_2[i]) + ... : the owner's side of the store-mode exchange.
+__global__ void __launch_bounds__(256)
+sum_slots_kernel(float* __restrict__ dst, const float* __restrict__ slots, int nslots, size_t n, size_t pitch) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((n & 3) == 0 && (pitch & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(slots)) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(slots);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const size_t n4 = n >> 2, p4 = pitch >> 2;
+    for (; i < n4; i += stride) {
+      float4 a = s4[i];
+      for (int s = 1; s < nslots; ++s) {
+        const float4 b = s4[(size_t)s * p4 + i];
+        a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+      }
+      d4[i] = a;
+    }
+    return;
+  }
+  for (; i < n; i += stride) {
+    float a = slots[i];
+    for (int s = 1; s < nslots; ++s) a = __fadd_rn(a, slots[(size_t)s * pitch + i]);
+    dst[i] = a;
+  }
 }
 
 }  // namespace xct

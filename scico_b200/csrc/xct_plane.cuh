@@ -67,7 +67,7 @@ __device__ __forceinline__ int window_start(const ViewRec& vr, int a_lo, int a_h
 // ROUTE: the result is ADDED into the row blocks of `route` (the owners' memory, possibly across NVLink)
 // instead of being stored to `out`; 2D: one image, row = image axis 0; 3D: row = slice.
 template <class G, bool IS3D, int S, int TA, int WIN, int WARPS, bool ROUTE = false>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, ROUTE ? (IS3D ? 2 : 4) : 0)  // routed: the plain kernel's occupancy (0 = unspecified)
 plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __restrict__ out,
                      const __grid_constant__ OutRoute route) {
   static_assert(WIN % 32 == 0, "window is staged 32 bins at a time");
@@ -180,6 +180,53 @@ plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __res
     }
   }
 
+  if constexpr (ROUTE) {
+    // Routed epilogue.  It is kept SMALL on purpose: an owner search inlined into every one of the TA (x S)
+    // unrolled writes made this kernel 9 % slower than the plain one although the epilogue runs once per warp
+    // (its ~100 KB of straight-line code went through the instruction cache of every SM 16 000 times and
+    // evicted the view loop of the other warps).  So: one owner lookup per column (2D) or per slice (3D),
+    // then plain pointer steps; a tile that straddles two row blocks takes the per-row lookup (rare).
+    if (b >= p.NB) return;
+    if constexpr (!IS3D) {
+      RouteCursor cur;
+      cur.seek(route, a0, b);
+      if (a0 + TA <= cur.next) {  // the whole tile belongs to one row block (warp-uniform)
+        float* q = cur.q;
+        const long long step = route.inner;
+        if (route.store) {
+#pragma unroll
+          for (int n = 0; n < TA; ++n)
+            if (a0 + n < p.NA) q[n * step] = acc[n][0];
+        } else {
+#pragma unroll
+          for (int n = 0; n < TA; ++n)
+            if (a0 + n < p.NA) atomicAdd_system(q + n * step, acc[n][0]);
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < TA; ++n)
+          if (a0 + n < p.NA) route_add(route, a0 + n, b, acc[n][0]);
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (s0 + s >= p.NS) break;
+        RouteCursor cur;
+        cur.seek(route, s0 + s, (long long)a0 * p.NB + b);  // the slice picks the owner
+        float* q = cur.q;
+        if (route.store) {
+#pragma unroll
+          for (int n = 0; n < TA; ++n)
+            if (a0 + n < p.NA) q[(size_t)n * p.NB] = acc[n][s];
+        } else {
+#pragma unroll
+          for (int n = 0; n < TA; ++n)
+            if (a0 + n < p.NA) atomicAdd_system(q + (size_t)n * p.NB, acc[n][s]);
+        }
+      }
+    }
+    return;
+  }
   if (b < p.NB) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -187,11 +234,6 @@ plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __res
 #pragma unroll
       for (int n = 0; n < TA; ++n) {
         if (a0 + n < p.NA) {
-          if constexpr (ROUTE) {
-            if (IS3D) route_add(route, s0 + s, (long long)(a0 + n) * p.NB + b, acc[n][s]);
-            else route_add(route, a0 + n, b, acc[n][s]);
-            continue;
-          }
           float* o = out + ((size_t)(s0 + s) * p.NA + (a0 + n)) * (size_t)p.NB + b;
           if (gridDim.y > 1) atomicAdd(o, acc[n][s]);
           else *o = acc[n][s];

@@ -153,31 +153,38 @@ class SlabShardedXRayTransform3D:
 
 class PeerBlocks:
     """Row blocks of a view-sharded back projection, held in device memory that every GPU of the node can
-    add into (``xct_peer_alloc`` + CUDA IPC: one process per GPU, the blocks of the other ranks are mapped
+    write into (``xct_peer_alloc`` + CUDA IPC: one process per GPU, the buffers of the other ranks are mapped
     through NVLink / NVSwitch peer access).
 
     ``exchange(launch, out)`` runs one fused back projection + exchange step:
 
-    1. ``launch(ptrs, row_begin)`` enqueues this rank's ``xct_adjoint_scatter``: the kernel's epilogue adds
-       every result row into the block of the rank that owns it (``RED.ADD.F32``, system scope);
+    1. ``launch(ptrs, row_begin, store)`` enqueues this rank's ``xct_adjoint_scatter``: the kernel's epilogue
+       sends every result row to the rank that owns it --
+       ``mode="store"`` (default): plain posted stores into THIS rank's slot of the owner's staging area
+       ``(world, rows, *inner)``; ``mode="add"``: ``RED.ADD.F32`` (system scope) into the owner's block;
     2. one stream-ordered rendezvous (a one-element NCCL all-reduce): when it completes on this rank's
-       stream, every rank's kernel has finished, so this rank's block holds the complete sum;
-    3. the block is copied to ``out`` and zeroed again for its next use.
+       stream, every rank's kernel has finished;
+    3. store: the owner sums its slots in rank order into ``out`` (``xct_sum_slots``: deterministic, unlike
+       a sum of atomics); add: the block is copied to ``out`` and zeroed again for its next use.
 
-    Two copies of every block alternate between calls, which is what makes ONE rendezvous per call enough:
-    a peer can only add into copy ``c`` again two calls later, i.e. after a rendezvous that this rank joined
-    after zeroing ``c``.  No partial volume is written, sent or summed by a separate collective."""
+    Two copies of every buffer alternate between calls, which is what makes ONE rendezvous per call enough:
+    a peer can only write copy ``c`` again two calls later, i.e. after a rendezvous that this rank joined
+    after it had consumed ``c``.  No partial volume is written, sent and summed by a separate collective."""
 
     COPIES = 2
 
     def __init__(self, slabs: Sequence[tuple[int, int]], inner_shape: Sequence[int], group=None,
-                 rank: Optional[int] = None, world_size: Optional[int] = None, device: Optional[int] = None):
+                 rank: Optional[int] = None, world_size: Optional[int] = None, device: Optional[int] = None,
+                 mode: str = "store"):
         import ctypes
 
         from . import _lib
 
         if torch is None or not torch.cuda.is_available():
             raise RuntimeError("PeerBlocks needs CUDA devices (there is no CPU path)")
+        if mode not in ("store", "add"):
+            raise ValueError("mode must be 'store' or 'add'")
+        self.mode = mode
         self._lib, self._L = _lib, _lib.lib()
         self.group = group
         r, w = _world(group)
@@ -189,10 +196,12 @@ class PeerBlocks:
         self.slabs = [tuple(sl) for sl in slabs]
         self.row_begin = [self.slabs[0][0]] + [b for _, b in self.slabs]
         self.inner_shape = tuple(int(n) for n in inner_shape)
-        rows = self.slabs[self.rank][1] - self.slabs[self.rank][0]
-        self.local_shape = (rows,) + self.inner_shape
-        self.nbytes = 4 * rows * int(np.prod(self.inner_shape))
-        alloc = max(self.nbytes, 256)  # an empty block still needs a valid pointer
+        inner = int(np.prod(self.inner_shape))
+        self._block_elems = [(b - a) * inner for a, b in self.slabs]
+        self.local_shape = (self.slabs[self.rank][1] - self.slabs[self.rank][0],) + self.inner_shape
+        self.nelems = self._block_elems[self.rank]
+        slots = self.world_size if mode == "store" else 1
+        alloc = max(4 * self.nelems * slots, 256)  # an empty block still needs a valid pointer
         self._own: list[int] = []
         self._mapped: list[int] = []
         handles = []
@@ -200,6 +209,7 @@ class PeerBlocks:
         for _ in range(self.COPIES):
             ptr, h = ctypes.c_void_p(), _lib.IpcHandle()
             _lib.check(self._L.xct_peer_alloc(self.device, alloc, ctypes.byref(ptr), ctypes.byref(h)))
+            # add: blocks start at zero; store: the slot of a rank without views is never written and stays zero
             _lib.check(self._L.xct_peer_zero(self.device, ptr, alloc, stream))
             self._own.append(ptr.value)
             handles.append(bytes(h.bytes))
@@ -209,42 +219,50 @@ class PeerBlocks:
             dist.all_gather_object(gathered, handles, group=group)
         else:
             gathered[0] = handles
-        self.ptrs: list[list[int]] = []
+        self.ptrs: list[list[int]] = []  # [copy][owner] -> where this rank writes the owner's rows
         for c in range(self.COPIES):
             row = []
             for k in range(self.world_size):
                 if k == self.rank:
-                    row.append(self._own[c])
-                    continue
-                h = _lib.IpcHandle()
-                ctypes.memmove(h.bytes, gathered[k][c], 64)
-                q = ctypes.c_void_p()
-                _lib.check(self._L.xct_peer_open(self.device, ctypes.byref(h), ctypes.byref(q)))
-                self._mapped.append(q.value)
-                row.append(q.value)
+                    base = self._own[c]
+                else:
+                    h = _lib.IpcHandle()
+                    ctypes.memmove(h.bytes, gathered[k][c], 64)
+                    q = ctypes.c_void_p()
+                    _lib.check(self._L.xct_peer_open(self.device, ctypes.byref(h), ctypes.byref(q)))
+                    self._mapped.append(q.value)
+                    base = q.value
+                if mode == "store":  # this rank's slot in owner k's staging area
+                    base += 4 * self.rank * self._block_elems[k]
+                row.append(base)
             self.ptrs.append(row)
         self._token = torch.zeros(1, dtype=torch.float32, device=f"cuda:{self.device}")
         self._turn = 0
         if self.world_size > 1:
-            dist.barrier(group=group)  # every block is zeroed and mapped before anybody adds into it
+            dist.barrier(group=group)  # every buffer is zeroed and mapped before anybody writes into it
 
-    def exchange(self, launch: Callable[[list, list], None], out):
+    def exchange(self, launch: Callable[[list, list, bool], None], out):
         if tuple(out.shape) != self.local_shape or not out.is_contiguous() or out.dtype != torch.float32:
             raise ValueError(f"'out' must be a contiguous float32 tensor of shape {self.local_shape}")
         c = self._turn
         self._turn = (c + 1) % self.COPIES
-        launch(self.ptrs[c], self.row_begin)
+        launch(self.ptrs[c], self.row_begin, self.mode == "store")
         if self.world_size > 1:
             dist.all_reduce(self._token, group=self.group)  # stream-ordered: no host synchronisation
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        if self.nbytes:
-            self._lib.check(self._L.xct_peer_copy_out(self.device, out.data_ptr(), self._own[c], self.nbytes, stream))
-            self._lib.check(self._L.xct_peer_zero(self.device, self._own[c], self.nbytes, stream))
+        if self.nelems == 0:
+            return out
+        if self.mode == "store":
+            self._lib.check(self._L.xct_sum_slots(self.device, out.data_ptr(), self._own[c], self.world_size,
+                                                  self.nelems, self.nelems, stream))
+        else:
+            self._lib.check(self._L.xct_peer_copy_out(self.device, out.data_ptr(), self._own[c], 4 * self.nelems, stream))
+            self._lib.check(self._L.xct_peer_zero(self.device, self._own[c], 4 * self.nelems, stream))
         return out
 
     def close(self, collective: bool = True):
-        """Unmap the peers' blocks and free this rank's (``collective``: rendezvous first, so that no peer is
-        still adding into them)."""
+        """Unmap the peers' buffers and free this rank's (``collective``: rendezvous first, so that no peer is
+        still writing into them)."""
         if self._L is None:
             return
         if collective and self.world_size > 1 and dist.is_initialized():
@@ -269,12 +287,13 @@ class _ViewSharded:
     """Shared machinery of the view-block partitions (volume / image rows sharded on axis 0)."""
 
     def _setup_exchange(self, exchange, inner_shape):
-        if exchange not in ("nccl", "peer"):
-            raise ValueError("exchange must be 'nccl' or 'peer'")
+        if exchange not in ("nccl", "peer", "peer_add"):
+            raise ValueError("exchange must be 'nccl', 'peer' (stores into per-rank slots) or 'peer_add' (atomics)")
         self.exchange = exchange
         self.peer = None
-        if exchange == "peer" and self.world_size > 1:
-            self.peer = PeerBlocks(self.slabs, inner_shape, group=self.group, rank=self.rank, world_size=self.world_size)
+        if exchange != "nccl" and self.world_size > 1:
+            self.peer = PeerBlocks(self.slabs, inner_shape, group=self.group, rank=self.rank, world_size=self.world_size,
+                                   mode="store" if exchange == "peer" else "add")
 
     def close(self):
         if getattr(self, "peer", None) is not None:
@@ -331,8 +350,9 @@ class ViewShardedXRayTransform3D(_ViewSharded):
     ``(v1-v0, D0, D1)``.  ``back_project(y_views)``: back-projects the local views slab by slab
     (one plan per destination slab, ``slice_offset`` = slab start) and sum-reduces each slab into
     its owner; returns this rank's slab ``(z1-z0, N1, N2)``.  ``exchange="peer"``: ONE back projection
-    kernel whose epilogue adds every slice into its owner's slab through NVLink peer memory
-    (:class:`PeerBlocks`, ``xct_adjoint_scatter``) instead of the per-slab NCCL reductions."""
+    kernel whose epilogue writes every slice into its owner's memory through NVLink peer access
+    (:class:`PeerBlocks`, ``xct_adjoint_scatter``; ``"peer_add"``: atomics instead of per-rank slots) instead
+    of the per-slab NCCL reductions."""
 
     def __init__(self, input_shape, matrices, det_shape, group=None, op_factory: Optional[Callable] = None,
                  rank: Optional[int] = None, world_size: Optional[int] = None, exchange: str = "nccl"):
@@ -367,8 +387,8 @@ class ViewShardedXRayTransform3D(_ViewSharded):
 
         if self.peer is not None:  # fused: the kernel adds every slice into its owner's slab over NVLink
             out = y_views.new_empty(self.local_input_shape)
-            launch = (lambda ptrs, rb: self.full.back_project_scatter(y_views, ptrs, rb)) if self.full is not None \
-                else (lambda ptrs, rb: None)
+            launch = (lambda ptrs, rb, st: self.full.back_project_scatter(y_views, ptrs, rb, st)) if self.full is not None \
+                else (lambda ptrs, rb, st: None)
             return self.peer.exchange(launch, out)
 
         def part(j):
@@ -390,8 +410,9 @@ class ViewShardedXRayTransform2D(_ViewSharded):
     full image to this rank's views ``(v1-v0, ny)``; ``back_project(y_views)`` returns either the
     row block this rank owns (``scatter=True``, reduce per row block) or the full image on every
     rank (``scatter=False``, all-reduce).  ``exchange="peer"``: the scatter case runs ONE kernel whose
-    epilogue adds every image row into its owner's block through NVLink peer memory
-    (:class:`PeerBlocks`, ``xct_adjoint_scatter``) instead of back projection + NCCL reduce-scatter."""
+    epilogue writes every image row into its owner's memory through NVLink peer access
+    (:class:`PeerBlocks`, ``xct_adjoint_scatter``; ``"peer_add"``: atomics instead of per-rank slots) instead of
+    back projection + NCCL reduce-scatter."""
 
     def __init__(self, input_shape, angles, group=None, op_factory: Optional[Callable] = None,
                  rank: Optional[int] = None, world_size: Optional[int] = None, exchange: str = "nccl", **kw):
@@ -419,8 +440,8 @@ class ViewShardedXRayTransform2D(_ViewSharded):
             raise ValueError(f"local views of shape {tuple(y_views.shape)} do not match {self.local_output_shape}")
         if self.peer is not None and scatter:  # fused: image rows are added into their owners over NVLink
             out = y_views.new_empty((self.slab[1] - self.slab[0],) + self.input_shape[1:])
-            launch = (lambda ptrs, rb: self.local.back_project_scatter(y_views, ptrs, rb)) if self.local is not None \
-                else (lambda ptrs, rb: None)
+            launch = (lambda ptrs, rb, st: self.local.back_project_scatter(y_views, ptrs, rb, st)) if self.local is not None \
+                else (lambda ptrs, rb, st: None)
             return self.peer.exchange(launch, out)
         full = self.local.back_project(y_views) if self.local is not None else y_views.new_zeros(self.input_shape)
         if self.world_size == 1:

@@ -133,16 +133,18 @@ def _analyse(fn, geom) -> dict:
     return d
 
 
-def _apply_scatter(plans: _Plans, y, ptrs, row_begin):
-    """Back projection of the CUDA tensor ``y`` whose result rows are ADDED into the row blocks behind
-    ``ptrs`` (device pointers, local or peer-mapped; block ``k`` = rows ``[row_begin[k], row_begin[k+1])``
-    of axis 0): ``xct_adjoint_scatter``.  Asynchronous on the current stream."""
+def _apply_scatter(plans: _Plans, y, ptrs, row_begin, store: bool = False):
+    """Back projection of the CUDA tensor ``y`` whose result rows go to the row blocks behind ``ptrs``
+    (device pointers, local or peer-mapped; block ``k`` = rows ``[row_begin[k], row_begin[k+1])`` of axis 0):
+    ``xct_adjoint_scatter``.  ``store=False``: the values are ADDED (system-scope RED); ``store=True``: they
+    are stored, each element exactly once.  Asynchronous on the current stream."""
     if not (torch is not None and isinstance(y, torch.Tensor) and y.is_cuda):
         raise ValueError("back_project_scatter needs a CUDA tensor")
     if len(ptrs) + 1 != len(row_begin) or not 1 <= len(ptrs) <= _lib.MAX_ROUTE_PARTS:
         raise ValueError(f"need 1..{_lib.MAX_ROUTE_PARTS} row blocks and one more row boundary than blocks")
     route = _lib.OutRoute()
     route.nparts = len(ptrs)
+    route.store = 1 if store else 0
     for k, b in enumerate(row_begin):
         route.row_begin[k] = int(b)
     for k, q in enumerate(ptrs):
@@ -241,13 +243,14 @@ class XRayTransform2D(LinearOperator):
         batch, lead = self._batch(y, self.output_shape)
         return _apply(self._plans, y, lead + self.nx, False, batch, _device_index(self.input_device), out)
 
-    def back_project_scatter(self, y, ptrs, row_begin) -> None:
-        """Back projection fused with the view-block exchange: image row ``i`` is ADDED into the row
-        block that owns it (``ptrs[k]``: device pointer of rows ``[row_begin[k], row_begin[k+1])``, local or a
-        peer GPU's, see :class:`scico_b200.sharded.PeerBlocks`).  One image, CUDA tensors only."""
+    def back_project_scatter(self, y, ptrs, row_begin, store: bool = False) -> None:
+        """Back projection fused with the view-block exchange: image row ``i`` is added into (or, with
+        ``store``, written to) the row block that owns it (``ptrs[k]``: device pointer of rows
+        ``[row_begin[k], row_begin[k+1])``, local or a peer GPU's, see :class:`scico_b200.sharded.PeerBlocks`).
+        One image, CUDA tensors only."""
         if tuple(y.shape) != self.output_shape:
             raise ValueError(f"array of shape {tuple(y.shape)} does not match {self.output_shape}")
-        _apply_scatter(self._plans, y, ptrs, row_begin)
+        _apply_scatter(self._plans, y, ptrs, row_begin, store)
 
     @staticmethod
     def _batch(a, core):
@@ -358,13 +361,14 @@ class XRayTransform3D(LinearOperator):
             raise ValueError(f"array of shape {tuple(proj.shape)} does not match {self.output_shape}")
         return _apply(self._plans, proj, self.input_shape, False, 1, _device_index(self.input_device), out)
 
-    def back_project_scatter(self, proj, ptrs, row_begin) -> None:
-        """Back projection fused with the view-block exchange: slice ``i`` of the result is ADDED into the
-        slab that owns it (``ptrs[k]``: device pointer of slices ``[row_begin[k], row_begin[k+1])``, local or a
-        peer GPU's, see :class:`scico_b200.sharded.PeerBlocks`).  CUDA tensors only."""
+    def back_project_scatter(self, proj, ptrs, row_begin, store: bool = False) -> None:
+        """Back projection fused with the view-block exchange: slice ``i`` of the result is added into (or,
+        with ``store``, written to) the slab that owns it (``ptrs[k]``: device pointer of slices
+        ``[row_begin[k], row_begin[k+1])``, local or a peer GPU's, see :class:`scico_b200.sharded.PeerBlocks`).
+        CUDA tensors only."""
         if tuple(proj.shape) != self.output_shape:
             raise ValueError(f"array of shape {tuple(proj.shape)} does not match {self.output_shape}")
-        _apply_scatter(self._plans, proj, ptrs, row_begin)
+        _apply_scatter(self._plans, proj, ptrs, row_begin, store)
 
     matrices_from_euler_angles = staticmethod(matrices_from_euler_angles)
 

@@ -75,11 +75,11 @@ def _worker(rank, world, port, case):
             assert O.rel_l2(got, C.project_2d(x, T, op.ny)[v0:v1]) <= 1e-5
             back = op.back_project(torch.as_tensor(np.ascontiguousarray(y[v0:v1]), device=dev)).cpu().numpy()
             assert O.rel_l2(back, C.back_project_2d(y, T, nx)[z0:z1]) <= 1e-5
-        elif case == "view2d_peer":
+        elif case in ("view2d_peer", "view2d_peer_add"):
             # back projection fused with the exchange: rows added into their owners over NVLink peer memory
             nx, V = (200, 168), 48
             angles = np.linspace(0, np.pi, V, endpoint=False)
-            op = sharded.ViewShardedXRayTransform2D(nx, angles, exchange="peer")
+            op = sharded.ViewShardedXRayTransform2D(nx, angles, exchange="peer" if case == "view2d_peer" else "peer_add")
             nccl = sharded.ViewShardedXRayTransform2D(nx, angles)
             T = sb.XRayTransform2D(nx, angles).view_table
             (z0, z1), (v0, v1) = op.slab, op.views
@@ -93,11 +93,11 @@ def _worker(rank, world, port, case):
                 ref = nccl.back_project(yv)
                 assert (torch.linalg.vector_norm(back - ref) / torch.linalg.vector_norm(ref)).item() <= 1e-6
             op.close()
-        elif case == "view3d_peer":
+        elif case in ("view3d_peer", "view3d_peer_add"):
             N, D, V = (20, 24, 28), (30, 36), 10
             ang = np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, 0.5)], 1)
             M = sb.matrices_from_euler_angles(N, D, "XY", ang)
-            op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange="peer")
+            op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange="peer" if case == "view3d_peer" else "peer_add")
             (z0, z1), (v0, v1) = op.slab, op.views
             for it in range(3):
                 y = rng.standard_normal((V,) + D).astype(np.float32)
@@ -160,7 +160,8 @@ def _worker(rank, world, port, case):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["slab", "slab_halo", "view3d", "view2d", "view2d_peer", "view3d_peer", "pdhg_slab", "admm_slab", "ladmm_slab", "padmm_slab"])
+@pytest.mark.parametrize("case", ["slab", "slab_halo", "view3d", "view2d", "view2d_peer", "view3d_peer", "view2d_peer_add",
+                                  "view3d_peer_add", "pdhg_slab", "admm_slab", "ladmm_slab", "padmm_slab"])
 def test_sharded_operators_nccl(case):
     import torch
     import torch.multiprocessing as mp

@@ -26,12 +26,14 @@ def _tilt_mats(N, D, V):
     return sb.matrices_from_euler_angles(N, D, "XY", ang)
 
 
-def _scatter(torch, dev, op, y, bounds):
-    """Run back_project_scatter into len(bounds)-1 separate zeroed blocks; returns them concatenated."""
+def _scatter(torch, dev, op, y, bounds, store=False):
+    """Run back_project_scatter into len(bounds)-1 separate blocks (zeroed for the add mode, poisoned for the
+    store mode, which must overwrite every element); returns them concatenated."""
     inner = tuple(op.input_shape[1:])
-    blocks = [torch.zeros((b - a,) + inner, dtype=torch.float32, device=dev) for a, b in zip(bounds[:-1], bounds[1:])]
+    blocks = [torch.full((b - a,) + inner, 7.0 if store else 0.0, dtype=torch.float32, device=dev)
+              for a, b in zip(bounds[:-1], bounds[1:])]
     ptrs = [blk.data_ptr() if blk.numel() else 0 for blk in blocks]
-    op.back_project_scatter(y, ptrs, bounds)
+    op.back_project_scatter(y, ptrs, bounds, store)
     return torch.cat(blocks, dim=0)
 
 
@@ -71,6 +73,10 @@ def test_scatter_matches_back_projection(cuda_device, name):
     else:
         ref = C.back_project_3d(y_np, op.matrices, op.input_shape)
     assert O.rel_l2(got.cpu().numpy(), ref) <= 1e-5
+    # store mode: plain stores, every element written exactly once (the blocks start out poisoned)
+    got_s = _scatter(torch, cuda_device, op, y, bounds, store=True)
+    rel_s = (torch.linalg.vector_norm(got_s - want) / torch.linalg.vector_norm(want)).item()
+    assert rel_s <= 1e-6, rel_s
     # the blocks are ADDED to: a second application doubles them
     inner = tuple(op.input_shape[1:])
     blk = torch.zeros(tuple(op.input_shape), dtype=torch.float32, device=cuda_device)
@@ -104,26 +110,45 @@ def test_scatter_rejects_bad_routes(cuda_device):
     op.back_project_scatter(y, [p, 0, p], [0, 16, 16, 32])  # an empty block may be null
 
 
-def test_peer_blocks_protocol_single_rank(cuda_device):
-    """World size 1: allocation, double-buffered exchange, copy-out and re-zeroing of the blocks."""
+def test_sum_slots(cuda_device):
+    import torch
+
+    L = _lib.lib()
+    for n, pitch, nslots in [(1024, 1024, 3), (1001, 1003, 5), (8, 8, 1), (4100, 4200, 16)]:
+        g = torch.Generator(device=cuda_device).manual_seed(n)
+        slots = torch.randn((nslots, pitch), device=cuda_device, generator=g)
+        dst = torch.full((n,), 9.0, device=cuda_device)
+        _lib.check(L.xct_sum_slots(0, dst.data_ptr(), slots.data_ptr(), nslots, n, pitch,
+                                   torch.cuda.current_stream().cuda_stream))
+        want = slots[0, :n].clone()
+        for s_ in range(1, nslots):  # same association order: bit-exact
+            want = want + slots[s_, :n]
+        assert torch.equal(dst, want), (n, pitch, nslots)
+    with pytest.raises(_lib.XctError):
+        _lib.check(L.xct_sum_slots(0, dst.data_ptr(), slots.data_ptr(), 0, 8, 8, None))
+
+
+@pytest.mark.parametrize("mode", ["store", "add"])
+def test_peer_blocks_protocol_single_rank(cuda_device, mode):
+    """World size 1: allocation, double-buffered exchange, slot sum / copy-out and re-zeroing of the blocks."""
     import torch
 
     nx, V = (64, 48), 20
     angles = np.linspace(0, np.pi, V, endpoint=False)
     op = sb.XRayTransform2D(nx, angles)
-    pb = sharded.PeerBlocks([(0, nx[0])], nx[1:], rank=0, world_size=1)
+    pb = sharded.PeerBlocks([(0, nx[0])], nx[1:], rank=0, world_size=1, mode=mode)
     try:
         assert pb.local_shape == nx and len(pb.ptrs) == 2 and pb.ptrs[0] != pb.ptrs[1]
         rng = np.random.default_rng(5)
         for it in range(5):  # both copies are used more than once: each must come back zeroed
             y = torch.as_tensor(rng.standard_normal(op.output_shape).astype(np.float32), device=cuda_device)
             out = torch.empty(nx, dtype=torch.float32, device=cuda_device)
-            pb.exchange(lambda ptrs, rb: op.back_project_scatter(y, ptrs, rb), out)
+            pb.exchange(lambda ptrs, rb, st: op.back_project_scatter(y, ptrs, rb, st), out)
             want = op.adj(y)
             rel = (torch.linalg.vector_norm(out - want) / torch.linalg.vector_norm(want)).item()
             assert rel <= 1e-6, (it, rel)
         with pytest.raises(ValueError):
-            pb.exchange(lambda ptrs, rb: None, torch.empty((3, 3), device=cuda_device))
+            pb.exchange(lambda ptrs, rb, st: None, torch.empty((3, 3), device=cuda_device))
     finally:
         pb.close()
     pb.close()  # idempotent

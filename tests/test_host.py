@@ -143,6 +143,52 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.PlanInfo) == 64
 
 
+def test_route_structs_match_the_header_as_gcc_lays_them_out(tmp_path):
+    """xct_out_route / xct_ipc_handle: ctypes mirror against sizeof / offsetof of the C header."""
+    import subprocess
+
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "scico_b200_xray.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %d\\n", sizeof(xct_out_route), offsetof(xct_out_route, nparts),'
+        ' offsetof(xct_out_route, row_begin), offsetof(xct_out_route, ptr), offsetof(xct_out_route, store),'
+        ' sizeof(xct_ipc_handle), XCT_MAX_ROUTE_PARTS); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(t) for t in subprocess.check_output([str(exe)]).split()]
+    R = _lib.OutRoute
+    assert got == [ctypes.sizeof(R), R.nparts.offset, R.row_begin.offset, R.ptr.offset, R.store.offset,
+                   ctypes.sizeof(_lib.IpcHandle), _lib.MAX_ROUTE_PARTS]
+
+
+def test_scatter_and_peer_entry_points_report_errors_without_a_device():
+    import torch
+
+    L = _lib.lib()
+    assert L.xct_adjoint_scatter(None, None, None, None) == _lib.XCT_ERR_INVALID
+    assert L.xct_sum_slots(0, None, None, 1, 4, 4, None) == _lib.XCT_ERR_INVALID
+    assert L.xct_peer_zero(0, None, 16, None) == _lib.XCT_ERR_INVALID
+    assert L.xct_peer_copy_out(0, None, None, 16, None) == _lib.XCT_ERR_INVALID
+    assert L.xct_peer_close(0, None) == 0 and L.xct_peer_free(0, None) == 0  # no-ops
+    ptr, h = ctypes.c_void_p(), _lib.IpcHandle()
+    assert L.xct_peer_alloc(0, 0, ctypes.byref(ptr), ctypes.byref(h)) == _lib.XCT_ERR_INVALID
+    A = sb.XRayTransform2D((12, 13), np.linspace(0, np.pi, 10, endpoint=False))
+    with pytest.raises(ValueError):  # no routed path for host arrays
+        A.back_project_scatter(np.zeros(A.output_shape, np.float32), [1], [0, 12])
+    if not torch.cuda.is_available():
+        assert L.xct_peer_alloc(0, 1024, ctypes.byref(ptr), ctypes.byref(h)) == _lib.XCT_ERR_NO_DEVICE
+        assert L.xct_peer_open(0, ctypes.byref(h), ctypes.byref(ptr)) == _lib.XCT_ERR_NO_DEVICE
+        from scico_b200 import sharded
+
+        with pytest.raises(RuntimeError):
+            sharded.PeerBlocks([(0, 12)], (13,), rank=0, world_size=1)
+    with pytest.raises(ValueError):
+        from scico_b200 import sharded
+
+        sharded.ViewShardedXRayTransform2D((12, 13), np.linspace(0, np.pi, 10, endpoint=False), rank=0, world_size=1,
+                                           exchange="carrier pigeon")
+
+
 def test_invalid_arguments_are_reported_not_fatal():
     L = _lib.lib()
     pl = ctypes.c_void_p()

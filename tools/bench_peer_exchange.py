@@ -6,7 +6,8 @@
 * C3 (BASELINE.json configs[2]): 2D 4096^2, 2048 views, view blocks.  "nccl": plane adjoint kernel writes a
   partial image (64 MB), one NCCL reduce_scatter sums the row blocks into their owners.  "peer": ONE kernel
   (xct_adjoint_scatter) whose epilogue adds every image row into its owner's block through NVLink peer
-  memory, one one-element all-reduce as the rendezvous, copy-out of the block.
+  memory (plain stores into per-rank slots that the owner sums, or atomics), one one-element all-reduce as
+  the rendezvous.
 * tilted 3D (general matrices, 256^3 x 64 views at 74 degrees): "nccl": one kernel + one NCCL reduce per
   destination slab; "peer": one routed kernel.
 
@@ -75,16 +76,21 @@ n, V = (1024, 512) if small else (4096, 2048)
 angles = np.linspace(0, np.pi, V, endpoint=False)
 A_nccl = sharded.ViewShardedXRayTransform2D((n, n), angles)
 A_peer = sharded.ViewShardedXRayTransform2D((n, n), angles, exchange="peer")
+A_add = sharded.ViewShardedXRayTransform2D((n, n), angles, exchange="peer_add")
 y = torch.rand(A_nccl.local_output_shape, device=dev, generator=g)
 r = rel(A_peer.back_project(y), A_nccl.back_project(y))
+r_add = rel(A_add.back_project(y), A_nccl.back_project(y))
 t_nccl = timeit(lambda: A_nccl.back_project(y))
 t_peer = timeit(lambda: A_peer.back_project(y))
+t_add = timeit(lambda: A_add.back_project(y))
 t_kern = timeit(lambda: A_nccl.local.back_project(y))
 out[f"C3 2D {n}^2 x {V} views, view blocks, adjoint"] = {
     "views_per_rank": A_nccl.views[1] - A_nccl.views[0], "adj_ms_nccl_reduce_scatter": t_nccl,
-    "adj_ms_peer_fused": t_peer, "adj_ms_kernel_only_no_exchange": t_kern, "peer_vs_nccl_rel_l2": r}
+    "adj_ms_peer_fused_store_slots": t_peer, "adj_ms_peer_fused_atomics": t_add,
+    "adj_ms_kernel_only_no_exchange": t_kern, "peer_vs_nccl_rel_l2": r, "peer_add_vs_nccl_rel_l2": r_add}
 A_peer.close()
-del A_nccl, A_peer, y
+A_add.close()
+del A_nccl, A_peer, A_add, y
 torch.cuda.empty_cache()
 
 # ---- tilted 3D: general kernels
@@ -94,13 +100,18 @@ D = (n + 64, n + 64)
 M = sb.matrices_from_euler_angles((n,) * 3, D, "XY", angs)
 A_nccl = sharded.ViewShardedXRayTransform3D((n,) * 3, M, D)
 A_peer = sharded.ViewShardedXRayTransform3D((n,) * 3, M, D, exchange="peer")
+A_add = sharded.ViewShardedXRayTransform3D((n,) * 3, M, D, exchange="peer_add")
 ys = torch.rand(A_nccl.local_output_shape, device=dev, generator=g)
 r = rel(A_peer.back_project(ys), A_nccl.back_project(ys))
+r_add = rel(A_add.back_project(ys), A_nccl.back_project(ys))
 t_nccl = timeit(lambda: A_nccl.back_project(ys))
 t_peer = timeit(lambda: A_peer.back_project(ys))
+t_add = timeit(lambda: A_add.back_project(ys))
 out[f"3D {n}^3 x {V} views, XY tilt 74 deg, view blocks, adjoint"] = {
-    "adj_ms_nccl_per_slab_reduce": t_nccl, "adj_ms_peer_fused": t_peer, "peer_vs_nccl_rel_l2": r}
+    "adj_ms_nccl_per_slab_reduce": t_nccl, "adj_ms_peer_fused_store_slots": t_peer, "adj_ms_peer_fused_atomics": t_add,
+    "peer_vs_nccl_rel_l2": r, "peer_add_vs_nccl_rel_l2": r_add}
 A_peer.close()
+A_add.close()
 
 if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)
