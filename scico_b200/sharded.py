@@ -175,24 +175,21 @@ class PeerBlocks:
 
     def __init__(self, slabs: Sequence[tuple[int, int]], inner_shape: Sequence[int], group=None,
                  rank: Optional[int] = None, world_size: Optional[int] = None, device: Optional[int] = None,
-                 mode: str = "store"):
-        import ctypes
-
-        from . import _lib
-
-        if torch is None or not torch.cuda.is_available():
-            raise RuntimeError("PeerBlocks needs CUDA devices (there is no CPU path)")
+                 mode: str = "store", mem=None):
         if mode not in ("store", "add"):
             raise ValueError("mode must be 'store' or 'add'")
         self.mode = mode
-        self._lib, self._L = _lib, _lib.lib()
         self.group = group
         r, w = _world(group)
         self.rank = r if rank is None else rank
         self.world_size = w if world_size is None else world_size
-        if len(slabs) != self.world_size or self.world_size > _lib.MAX_ROUTE_PARTS:
-            raise ValueError(f"need one row block per rank and at most {_lib.MAX_ROUTE_PARTS} ranks")
-        self.device = torch.cuda.current_device() if device is None else int(device)
+        # `mem`: where the buffers live.  The product always uses the native CUDA-IPC memory; the CPU tests
+        # inject a shared-memory stand-in to run this protocol (slot addressing, alternation) under gloo.
+        self.mem = mem if mem is not None else _NativePeerMemory(device)
+        from ._lib import MAX_ROUTE_PARTS
+
+        if len(slabs) != self.world_size or self.world_size > MAX_ROUTE_PARTS:
+            raise ValueError(f"need one row block per rank and at most {MAX_ROUTE_PARTS} ranks")
         self.slabs = [tuple(sl) for sl in slabs]
         self.row_begin = [self.slabs[0][0]] + [b for _, b in self.slabs]
         self.inner_shape = tuple(int(n) for n in inner_shape)
@@ -202,42 +199,37 @@ class PeerBlocks:
         self.nelems = self._block_elems[self.rank]
         slots = self.world_size if mode == "store" else 1
         alloc = max(4 * self.nelems * slots, 256)  # an empty block still needs a valid pointer
-        self._own: list[int] = []
-        self._mapped: list[int] = []
+        self._own: list = []
+        self._mapped: list = []
         handles = []
-        stream = torch.cuda.current_stream(self.device).cuda_stream
         for _ in range(self.COPIES):
-            ptr, h = ctypes.c_void_p(), _lib.IpcHandle()
-            _lib.check(self._L.xct_peer_alloc(self.device, alloc, ctypes.byref(ptr), ctypes.byref(h)))
+            ptr, handle = self.mem.alloc(alloc)
             # add: blocks start at zero; store: the slot of a rank without views is never written and stays zero
-            _lib.check(self._L.xct_peer_zero(self.device, ptr, alloc, stream))
-            self._own.append(ptr.value)
-            handles.append(bytes(h.bytes))
-        torch.cuda.synchronize(self.device)
+            self.mem.zero(ptr, alloc)
+            self._own.append(ptr)
+            handles.append(handle)
+        self.mem.sync()
         gathered = [None] * self.world_size
         if self.world_size > 1:
             dist.all_gather_object(gathered, handles, group=group)
         else:
             gathered[0] = handles
-        self.ptrs: list[list[int]] = []  # [copy][owner] -> where this rank writes the owner's rows
+        self.ptrs: list[list] = []  # [copy][owner] -> where this rank writes the owner's rows
         for c in range(self.COPIES):
             row = []
             for k in range(self.world_size):
                 if k == self.rank:
                     base = self._own[c]
                 else:
-                    h = _lib.IpcHandle()
-                    ctypes.memmove(h.bytes, gathered[k][c], 64)
-                    q = ctypes.c_void_p()
-                    _lib.check(self._L.xct_peer_open(self.device, ctypes.byref(h), ctypes.byref(q)))
-                    self._mapped.append(q.value)
-                    base = q.value
+                    base = self.mem.open(gathered[k][c])
+                    self._mapped.append(base)
                 if mode == "store":  # this rank's slot in owner k's staging area
-                    base += 4 * self.rank * self._block_elems[k]
+                    base = self.mem.offset(base, 4 * self.rank * self._block_elems[k])
                 row.append(base)
             self.ptrs.append(row)
-        self._token = torch.zeros(1, dtype=torch.float32, device=f"cuda:{self.device}")
+        self._token = self.mem.token()
         self._turn = 0
+        self._closed = False
         if self.world_size > 1:
             dist.barrier(group=group)  # every buffer is zeroed and mapped before anybody writes into it
 
@@ -249,32 +241,32 @@ class PeerBlocks:
         launch(self.ptrs[c], self.row_begin, self.mode == "store")
         if self.world_size > 1:
             dist.all_reduce(self._token, group=self.group)  # stream-ordered: no host synchronisation
-        stream = torch.cuda.current_stream(self.device).cuda_stream
         if self.nelems == 0:
             return out
         if self.mode == "store":
-            self._lib.check(self._L.xct_sum_slots(self.device, out.data_ptr(), self._own[c], self.world_size,
-                                                  self.nelems, self.nelems, stream))
+            self.mem.sum_slots(out, self._own[c], self.world_size, self.nelems)
         else:
-            self._lib.check(self._L.xct_peer_copy_out(self.device, out.data_ptr(), self._own[c], 4 * self.nelems, stream))
-            self._lib.check(self._L.xct_peer_zero(self.device, self._own[c], 4 * self.nelems, stream))
+            self.mem.copy_out(out, self._own[c], 4 * self.nelems)
+            self.mem.zero(self._own[c], 4 * self.nelems)
         return out
 
     def close(self, collective: bool = True):
         """Unmap the peers' buffers and free this rank's (``collective``: rendezvous first, so that no peer is
         still writing into them)."""
-        if self._L is None:
+        if getattr(self, "_closed", True):
             return
-        if collective and self.world_size > 1 and dist.is_initialized():
-            torch.cuda.synchronize(self.device)
+        self._closed = True
+        both = collective and self.world_size > 1 and dist.is_initialized()
+        if both:
+            self.mem.sync()
             dist.barrier(group=self.group)
         for q in self._mapped:
-            self._L.xct_peer_close(self.device, q)
-        if collective and self.world_size > 1 and dist.is_initialized():
+            self.mem.close(q)
+        if both:
             dist.barrier(group=self.group)
         for q in self._own:
-            self._L.xct_peer_free(self.device, q)
-        self._mapped, self._own, self._L = [], [], None
+            self.mem.free(q)
+        self._mapped, self._own = [], []
 
     def __del__(self):
         try:
@@ -283,17 +275,73 @@ class PeerBlocks:
             pass
 
 
+class _NativePeerMemory:
+    """Device buffers of :class:`PeerBlocks` through the C ABI (``xct_peer_*``, ``xct_sum_slots``): pointers
+    are integers (device addresses), handles are the 64 bytes of a ``cudaIpcMemHandle_t``."""
+
+    def __init__(self, device: Optional[int] = None):
+        from . import _lib
+
+        if torch is None or not torch.cuda.is_available():
+            raise RuntimeError("PeerBlocks needs CUDA devices (there is no CPU path)")
+        self._lib, self._L = _lib, _lib.lib()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def alloc(self, nbytes: int):
+        import ctypes
+
+        ptr, h = ctypes.c_void_p(), self._lib.IpcHandle()
+        self._lib.check(self._L.xct_peer_alloc(self.device, nbytes, ctypes.byref(ptr), ctypes.byref(h)))
+        return ptr.value, bytes(h.bytes)
+
+    def open(self, handle: bytes):
+        import ctypes
+
+        h, q = self._lib.IpcHandle(), ctypes.c_void_p()
+        ctypes.memmove(h.bytes, handle, 64)
+        self._lib.check(self._L.xct_peer_open(self.device, ctypes.byref(h), ctypes.byref(q)))
+        return q.value
+
+    @staticmethod
+    def offset(ptr: int, nbytes: int) -> int:
+        return ptr + nbytes
+
+    def zero(self, ptr: int, nbytes: int):
+        self._lib.check(self._L.xct_peer_zero(self.device, ptr, nbytes, self._stream()))
+
+    def sum_slots(self, out, ptr: int, nslots: int, n: int):
+        self._lib.check(self._L.xct_sum_slots(self.device, out.data_ptr(), ptr, nslots, n, n, self._stream()))
+
+    def copy_out(self, out, ptr: int, nbytes: int):
+        self._lib.check(self._L.xct_peer_copy_out(self.device, out.data_ptr(), ptr, nbytes, self._stream()))
+
+    def token(self):
+        return torch.zeros(1, dtype=torch.float32, device=f"cuda:{self.device}")
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)
+
+    def close(self, ptr: int):
+        self._L.xct_peer_close(self.device, ptr)
+
+    def free(self, ptr: int):
+        self._L.xct_peer_free(self.device, ptr)
+
+
 class _ViewSharded:
     """Shared machinery of the view-block partitions (volume / image rows sharded on axis 0)."""
 
-    def _setup_exchange(self, exchange, inner_shape):
+    def _setup_exchange(self, exchange, inner_shape, peer_mem=None):
         if exchange not in ("nccl", "peer", "peer_add"):
             raise ValueError("exchange must be 'nccl', 'peer' (stores into per-rank slots) or 'peer_add' (atomics)")
         self.exchange = exchange
         self.peer = None
         if exchange != "nccl" and self.world_size > 1:
             self.peer = PeerBlocks(self.slabs, inner_shape, group=self.group, rank=self.rank, world_size=self.world_size,
-                                   mode="store" if exchange == "peer" else "add")
+                                   mode="store" if exchange == "peer" else "add", mem=peer_mem)
 
     def close(self):
         if getattr(self, "peer", None) is not None:
@@ -355,12 +403,12 @@ class ViewShardedXRayTransform3D(_ViewSharded):
     of the per-slab NCCL reductions."""
 
     def __init__(self, input_shape, matrices, det_shape, group=None, op_factory: Optional[Callable] = None,
-                 rank: Optional[int] = None, world_size: Optional[int] = None, exchange: str = "nccl"):
+                 rank: Optional[int] = None, world_size: Optional[int] = None, exchange: str = "nccl", peer_mem=None):
         self.input_shape = tuple(int(s) for s in input_shape)
         self.det_shape = tuple(int(s) for s in det_shape)
         self.matrices = np.asarray(matrices, dtype=np.float32)
         self._setup(len(self.matrices), self.input_shape[0], group, rank, world_size)
-        self._setup_exchange(exchange, self.input_shape[1:])
+        self._setup_exchange(exchange, self.input_shape[1:], peer_mem)  # peer_mem: CPU tests only
         v0, v1 = self.views
         self.local_output_shape = (v1 - v0,) + self.det_shape
         z0, z1 = self.slab
@@ -415,11 +463,12 @@ class ViewShardedXRayTransform2D(_ViewSharded):
     back projection + NCCL reduce-scatter."""
 
     def __init__(self, input_shape, angles, group=None, op_factory: Optional[Callable] = None,
-                 rank: Optional[int] = None, world_size: Optional[int] = None, exchange: str = "nccl", **kw):
+                 rank: Optional[int] = None, world_size: Optional[int] = None, exchange: str = "nccl", peer_mem=None,
+                 **kw):
         self.input_shape = tuple(int(s) for s in input_shape)
         self.angles = np.asarray(angles, dtype=np.float64)
         self._setup(len(self.angles), self.input_shape[0], group, rank, world_size)
-        self._setup_exchange(exchange, self.input_shape[1:])
+        self._setup_exchange(exchange, self.input_shape[1:], peer_mem)  # peer_mem: CPU tests only
         v0, v1 = self.views
         if kw.get("det_count") is None:  # the default depends on the image only, not on the views
             kw["det_count"] = int(np.ceil(np.linalg.norm(self.input_shape)))

@@ -165,6 +165,163 @@ def test_view_sharded_2d():
 
 
 # ---------------------------------------------------------------------------------------------
+# Fused view-block exchange (sharded.PeerBlocks): the protocol -- handle exchange, slot addressing with
+# uneven row blocks, a rank without views, the two alternating copies, the slot sum in rank order -- run
+# under gloo with shared memory standing in for the CUDA-IPC buffers and the oracle for the routed kernel.
+class ShmPeerMemory:
+    """multiprocessing.shared_memory stand-in for sharded._NativePeerMemory: pointer = (segment name, byte
+    offset), handle = the segment name."""
+
+    def __init__(self):
+        self._segs, self._mine = {}, {}
+
+    def _seg(self, name):
+        from multiprocessing import shared_memory
+
+        if name not in self._segs:
+            self._segs[name] = shared_memory.SharedMemory(name=name)
+        return self._segs[name]
+
+    def view(self, ptr, n):
+        return np.ndarray((n,), np.float32, buffer=self._seg(ptr[0]).buf, offset=ptr[1])
+
+    def alloc(self, nbytes):
+        from multiprocessing import shared_memory
+
+        shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        self._segs[shm.name] = self._mine[shm.name] = shm
+        return (shm.name, 0), shm.name.encode()
+
+    def open(self, handle):
+        self._seg(handle.decode())
+        return (handle.decode(), 0)
+
+    @staticmethod
+    def offset(ptr, nbytes):
+        return (ptr[0], ptr[1] + nbytes)
+
+    def zero(self, ptr, nbytes):
+        self.view(ptr, nbytes // 4)[:] = 0
+
+    def sum_slots(self, out, ptr, nslots, n):
+        slots = self.view(ptr, nslots * n).reshape(nslots, n)
+        acc = slots[0].copy()
+        for s in range(1, nslots):
+            acc = acc + slots[s]
+        out.numpy().reshape(-1)[:] = acc
+
+    def copy_out(self, out, ptr, nbytes):
+        out.numpy().reshape(-1)[:] = self.view(ptr, nbytes // 4)
+
+    @staticmethod
+    def token():
+        return torch.zeros(1)
+
+    def sync(self):
+        pass
+
+    def close(self, ptr):
+        if ptr[0] not in self._mine:
+            self._segs.pop(ptr[0]).close()
+
+    def free(self, ptr):
+        shm = self._mine.pop(ptr[0])
+        self._segs.pop(ptr[0], None)
+        shm.close()
+        shm.unlink()
+
+
+_MEM = None  # the worker's ShmPeerMemory (the stand-in operators below write through it)
+
+
+class _ScatterMixin:
+    """back_project_scatter of the native operators, on the shared-memory stand-in."""
+
+    def back_project_scatter(self, y, ptrs, row_begin, store=False):
+        full = self.back_project(y).numpy()
+        inner = int(np.prod(full.shape[1:]))
+
+        def write():
+            for k, (a, b) in enumerate(zip(row_begin[:-1], row_begin[1:])):
+                if b > a:
+                    dst = _MEM.view(ptrs[k], (b - a) * inner)
+                    if store:
+                        dst[:] = full[a:b].reshape(-1)
+                    else:
+                        dst += full[a:b].reshape(-1)
+
+        if store:
+            write()
+        else:  # the GPUs add atomically; the stand-in takes turns
+            for turn in range(dist.get_world_size()):
+                if turn == dist.get_rank():
+                    write()
+                dist.barrier()
+
+
+class ScatterOp2D(_ScatterMixin, OracleOp2D):
+    pass
+
+
+class ScatterOp3D(_ScatterMixin, OracleOp3D):
+    pass
+
+
+def _peer_case(rank, world, ndim, shape, V, exchange, calls):
+    global _MEM
+    _MEM = ShmPeerMemory()
+    rng = np.random.default_rng(21)
+    if ndim == 2:
+        angles = np.linspace(0, np.pi, V, endpoint=False)
+        op = sharded.ViewShardedXRayTransform2D(shape, angles, op_factory=ScatterOp2D, exchange=exchange, peer_mem=_MEM)
+        ref = OracleOp2D(shape, angles, det_count=op.ny)
+        out_shape = (V, op.ny)
+        part = lambda r, y: OracleOp2D(shape, angles[slice(*op.view_blocks[r])], det_count=op.ny).back_project(  # noqa: E731
+            torch.from_numpy(np.ascontiguousarray(y[slice(*op.view_blocks[r])]))).numpy()
+    else:
+        D = (shape[0] + 3, shape[2] + 4)
+        ang = np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, 0.4)], 1)
+        M = O.matrices_from_euler_angles(shape, D, "XY", ang).astype(np.float32)
+        op = sharded.ViewShardedXRayTransform3D(shape, M, D, op_factory=ScatterOp3D, exchange=exchange, peer_mem=_MEM)
+        ref = OracleOp3D(shape, M, D)
+        out_shape = (V,) + D
+        part = lambda r, y: OracleOp3D(shape, M[slice(*op.view_blocks[r])], D).back_project(  # noqa: E731
+            torch.from_numpy(np.ascontiguousarray(y[slice(*op.view_blocks[r])]))).numpy()
+    assert op.peer is not None and op.peer.mode == ("store" if exchange == "peer" else "add")
+    z0, z1 = op.slab
+    v0, v1 = op.views
+    for it in range(calls):  # more calls than copies: every copy is reused
+        y = rng.standard_normal(out_shape).astype(np.float32)
+        got = op.back_project(torch.from_numpy(np.ascontiguousarray(y[v0:v1]))).numpy()
+        assert got.shape == (z1 - z0,) + tuple(shape[1:])
+        parts = [part(r, y)[z0:z1] if op.view_blocks[r][1] > op.view_blocks[r][0] else np.zeros_like(got)
+                 for r in range(world)]
+        want = parts[0].copy()
+        for r in range(1, world):
+            want = want + parts[r]
+        if exchange == "peer":
+            assert np.array_equal(got, want), it  # slots are summed in rank order: bit-exact
+        else:
+            assert np.allclose(got, want, rtol=1e-6, atol=1e-6), it
+        assert O.rel_l2(got, ref.back_project(torch.from_numpy(y)).numpy()[z0:z1]) <= 1e-5
+    op.close()
+    op.close()  # idempotent
+
+
+@pytest.mark.parametrize("exchange", ["peer", "peer_add"])
+def test_fused_exchange_protocol_2d_three_ranks_uneven_blocks(exchange):
+    _spawn(_peer_case, 2, (25, 20), 10, exchange, 5, world=3)
+
+
+def test_fused_exchange_protocol_rank_without_views():
+    _spawn(_peer_case, 2, (13, 12), 2, "peer", 3, world=3)  # view blocks (0,0), (0,1), (1,2)
+
+
+def test_fused_exchange_protocol_3d_tilted():
+    _spawn(_peer_case, 3, (9, 8, 7), 5, "peer", 4, world=2)
+
+
+# ---------------------------------------------------------------------------------------------
 def test_block_bounds_cover_exactly():
     for n, p in ((1024, 8), (10, 3), (5, 8), (7, 7)):
         b = [sharded.block_bounds(n, p, i) for i in range(p)]
