@@ -189,6 +189,62 @@ def test_scatter_and_peer_entry_points_report_errors_without_a_device():
                                            exchange="carrier pigeon")
 
 
+def test_native_peer_memory_calls_the_c_abi_with_well_typed_arguments(monkeypatch):
+    """sharded._NativePeerMemory (the product's backend of PeerBlocks) against a recording double of the
+    library: every call must convert under the real ctypes argtypes, and PeerBlocks must drive it in the
+    documented order (alloc + zero per copy, sum_slots / copy_out + zero per exchange, free on close)."""
+    import torch
+
+    from scico_b200 import sharded
+
+    real = _lib.lib()
+    calls = []
+
+    class Fake:
+        def __getattr__(self, name):
+            fn = getattr(real, name)
+
+            def call(*args):
+                assert len(args) == len(fn.argtypes), (name, args)
+                for a, t in zip(args, fn.argtypes):
+                    t.from_param(a)  # raises ctypes.ArgumentError on a badly typed argument
+                calls.append(name)
+                if name == "xct_peer_alloc":
+                    args[2]._obj.value = 0x7000_0000_0000 + 0x1000_0000 * calls.count("xct_peer_alloc")
+                return 0
+
+            return call
+
+    class Stream:
+        cuda_stream = 0
+
+    monkeypatch.setattr(_lib, "lib", lambda: Fake())
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: Stream())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(sharded._NativePeerMemory, "token", lambda self: torch.zeros(1))
+    for mode, per_call in (("store", ["xct_sum_slots"]), ("add", ["xct_peer_copy_out", "xct_peer_zero"])):
+        calls.clear()
+        pb = sharded.PeerBlocks([(0, 6)], (5,), rank=0, world_size=1, mode=mode)
+        assert calls == ["xct_peer_alloc", "xct_peer_zero"] * 2
+        assert pb.ptrs[0][0] != pb.ptrs[1][0] and pb.local_shape == (6, 5) and pb.row_begin == [0, 6]
+        seen = []
+        out = torch.empty((6, 5))
+        for _ in range(3):
+            pb.exchange(lambda ptrs, rb, store: seen.append((ptrs[0], store)), out)
+        assert [p for p, _ in seen] == [pb.ptrs[0][0], pb.ptrs[1][0], pb.ptrs[0][0]]  # the copies alternate
+        assert all(st == (mode == "store") for _, st in seen)
+        assert calls[4:] == per_call * 3
+        pb.close()
+        assert calls[-2:] == ["xct_peer_free", "xct_peer_free"]
+        pb.close()
+    # opening a peer's handle: 64 bytes in, device address out
+    mem = sharded._NativePeerMemory(0)
+    assert isinstance(mem.open(bytes(range(64))), (int, type(None)))
+    assert mem.offset(4096, 128) == 4224
+
+
 def test_invalid_arguments_are_reported_not_fatal():
     L = _lib.lib()
     pl = ctypes.c_void_p()

@@ -76,10 +76,16 @@ f_ms = timeit(lambda: A.project(x))
 a_scatter = timeit(lambda: A.back_project(y, scatter=True))
 a_allred = timeit(lambda: A.back_project(y, scatter=False))
 a_local = timeit(lambda: A.local.back_project(y))
+a_peer = None
+if world > 1:  # back projection fused with the exchange over NVLink peer memory (xct_adjoint_scatter)
+    P = sharded.ViewShardedXRayTransform2D((n, n), np.linspace(0, np.pi, V, endpoint=False), exchange="peer")
+    a_peer = timeit(lambda: P.back_project(y))
+    P.close()
+    del P
 upd = float(n) * n * V
 out["C3 2D 4096^2 x 2048 views, view blocks"] = {
     "views_per_rank": A.views[1] - A.views[0], "fwd_ms": f_ms, "adj_ms_reduce_scatter": a_scatter,
-    "adj_ms_all_reduce": a_allred, "adj_ms_kernels_only": a_local,
+    "adj_ms_all_reduce": a_allred, "adj_ms_kernels_only": a_local, "adj_ms_fused_peer_exchange": a_peer,
     "pair_updates_per_s": 2 * upd / (f_ms + a_scatter) * 1e3,
     "exchange": "partial images (64 MB per rank): one NCCL reduce_scatter over equal row blocks (per-block reduce when the rows do not divide evenly)"}
 del A, x, y
@@ -95,9 +101,15 @@ xs = torch.rand(A.local_input_shape, device=dev, generator=g)
 ys = A.project(xs)
 f_ms = timeit(lambda: A.project(xs))
 a_ms = timeit(lambda: A.back_project(ys))
+a_peer = None
+if world > 1:
+    P = sharded.ViewShardedXRayTransform3D((n,) * 3, M, D, exchange="peer")
+    a_peer = timeit(lambda: P.back_project(ys))
+    P.close()
+    del P
 upd = float(n) ** 3 * V
 out["3D 256^3 x 64 views, XY tilt 74 deg, view blocks (general kernels)"] = {
-    "fwd_ms": f_ms, "adj_ms": a_ms, "pair_updates_per_s": 2 * upd / (f_ms + a_ms) * 1e3,
+    "fwd_ms": f_ms, "adj_ms": a_ms, "adj_ms_fused_peer_exchange": a_peer, "pair_updates_per_s": 2 * upd / (f_ms + a_ms) * 1e3,
     "exchange": "forward: all-gather of the slab-sharded volume; adjoint: per-slab NCCL reduce overlapped with the next slab's kernels"}
 del A, xs, ys
 torch.cuda.empty_cache()
