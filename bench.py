@@ -53,6 +53,9 @@ def time_cpu_port(sample, reps=1):
     from oracle import xray_c as C
     from oracle import xray_np as O
 
+    # all the host threads this process may use, whatever OMP_NUM_THREADS says (torchrun exports
+    # OMP_NUM_THREADS=1 to every rank, which would time a single core)
+    C.set_num_threads(len(os.sched_getaffinity(0)))
     N, D, V = sample["N"], sample["D"], sample["V"]
     ang = np.linspace(0, np.pi, sample.get("V_total", V), endpoint=False)[:V, None]
     M = O.matrices_from_euler_angles(N, D, "X", ang).astype(np.float32)
