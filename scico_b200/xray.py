@@ -121,6 +121,37 @@ def _apply(plans: _Plans, x, out_shape, forward: bool, batch: int, default_devic
     return torch.from_numpy(out) if was_torch else out
 
 
+if torch is not None:
+
+    class _ProjectorFn(torch.autograd.Function):
+        """The pair as one differentiable linear map for ``torch.autograd``: the VJP of ``project`` is
+        ``back_project`` and vice versa, which is how the reference wires an external projector
+        (``jax.custom_vjp(self._proj)`` with ``bwd -> self._bproj``, ``scico/linop/xray/astra/_astra_3d.py:498-502``)
+        and what ``test/linop/xray/astra/test_astra_2d.py:145-187`` checks (``grad ||A x||^2 == 2 A^T A x``, gradient
+        through ``A.T``).  The backward pass is differentiable again (it is the other kernel)."""
+
+        @staticmethod
+        def forward(ctx, x, plans, out_shape, forward, batch, default_device):
+            ctx.args = (plans, tuple(x.shape), forward, batch, x.device)
+            return _apply(plans, x, out_shape, forward, batch, default_device)
+
+        @staticmethod
+        def backward(ctx, g):
+            plans, in_shape, forward, batch, x_device = ctx.args
+            gx = _apply_ad(plans, g.contiguous(), in_shape, not forward, batch, None)
+            if gx.device != x_device:
+                gx = gx.to(x_device)
+            return gx, None, None, None, None, None
+
+
+def _apply_ad(plans: _Plans, x, out_shape, forward: bool, batch: int, default_device: Optional[int], out=None):
+    """:func:`_apply`, recorded on the autograd tape when ``x`` is a tensor that requires grad."""
+    if (out is None and torch is not None and isinstance(x, torch.Tensor) and x.requires_grad
+            and torch.is_grad_enabled()):
+        return _ProjectorFn.apply(x, plans, tuple(out_shape), forward, batch, default_device)
+    return _apply(plans, x, out_shape, forward, batch, default_device, out)
+
+
 def _analyse(fn, geom) -> dict:
     info, cls = _lib.PlanInfo(), _lib.PlanClasses()
     _lib.check(fn(ctypes.byref(geom), ctypes.byref(info), ctypes.byref(cls)))
@@ -235,13 +266,13 @@ class XRayTransform2D(LinearOperator):
         """X-ray projection, ``H @ im``; a leading batch axis is accepted (the reference's
         ``jax.vmap(A)`` use, ``scico/flax/examples/data_generation.py:153-186``)."""
         batch, lead = self._batch(im, self.nx)
-        return _apply(self._plans, im, lead + self.output_shape, True, batch,
+        return _apply_ad(self._plans, im, lead + self.output_shape, True, batch,
                       _device_index(self.output_device), out)
 
     def back_project(self, y, out=None):
         """X-ray back projection, ``H.T @ y`` (exact adjoint of :meth:`project`)."""
         batch, lead = self._batch(y, self.output_shape)
-        return _apply(self._plans, y, lead + self.nx, False, batch, _device_index(self.input_device), out)
+        return _apply_ad(self._plans, y, lead + self.nx, False, batch, _device_index(self.input_device), out)
 
     def back_project_scatter(self, y, ptrs, row_begin, store: bool = False) -> None:
         """Back projection fused with the view-block exchange: image row ``i`` is added into (or, with
@@ -353,13 +384,13 @@ class XRayTransform3D(LinearOperator):
         """Compute X-ray projection (``out``: optional preallocated result, see :func:`_apply`)."""
         if tuple(im.shape) != self.input_shape:
             raise ValueError(f"array of shape {tuple(im.shape)} does not match {self.input_shape}")
-        return _apply(self._plans, im, self.output_shape, True, 1, _device_index(self.output_device), out)
+        return _apply_ad(self._plans, im, self.output_shape, True, 1, _device_index(self.output_device), out)
 
     def back_project(self, proj, out=None):
         """Compute X-ray back projection (exact adjoint of :meth:`project`)."""
         if tuple(proj.shape) != self.output_shape:
             raise ValueError(f"array of shape {tuple(proj.shape)} does not match {self.output_shape}")
-        return _apply(self._plans, proj, self.input_shape, False, 1, _device_index(self.input_device), out)
+        return _apply_ad(self._plans, proj, self.input_shape, False, 1, _device_index(self.input_device), out)
 
     def back_project_scatter(self, proj, ptrs, row_begin, store: bool = False) -> None:
         """Back projection fused with the view-block exchange: slice ``i`` of the result is added into (or,
