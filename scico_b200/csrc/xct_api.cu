@@ -46,8 +46,8 @@ constexpr int kFwd3S = 2, kFwd3TN = 16;
 constexpr int kFwd2S = 1, kFwd2TN = 16;
 // walk kernels (xct_plane2.cuh)
 constexpr int kWAdjS = 8, kWAdjTA = 8, kWAdjWin = 64, kWAdjStages = 4;
-constexpr int kWFwdS = 4, kWFwdTN = 8;
-constexpr int kW2dTN = 8, kW2dWin = 160;  // 2D joint forward tile: 128 (major) x 8 (minor), one image  // walk forward tile: 64 (major) x 8 (minor) x 4 slices
+constexpr int kWFwdS = 4, kWFwdTN = 8;     // walk forward tile: 64 (major) x 8 (minor) x 4 slices
+constexpr int kW2dTN = 8, kW2dWin = 160;  // 2D joint forward tile: 128 (major) x 8 (minor), one image
 
 }  // namespace
 
