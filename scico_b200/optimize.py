@@ -15,7 +15,9 @@ fused elementwise/stencil kernels (``scico_b200/csrc/xct_tv.cuh``); all state li
 host synchronisation happens inside :meth:`step` (the reference syncs once per iteration statistic,
 ``scico/optimize/_common.py:305-312``; here statistics are optional and off by default).
 
-With a :class:`~scico_b200.sharded.SlabShardedXRayTransform3D` the state is z-slab sharded: the
+With a :class:`~scico_b200.sharded.ViewShardedXRayTransform3D` (general matrices) the volume-shaped state is
+z-slab sharded in the same way and the sinogram-shaped state is view-block sharded (first device run: next
+round).  With a :class:`~scico_b200.sharded.SlabShardedXRayTransform3D` the state is z-slab sharded: the
 projector needs no collective, the finite difference along axis 0 needs a one-plane halo per
 iteration in each direction (``N1*N2*4`` bytes, point-to-point between neighbouring ranks).
 
@@ -222,8 +224,8 @@ class _TVSolver:
     def _owned(self, t):
         """Sinogram-shaped array restricted to the detector rows this rank owns (shared rows are
         counted once in global sums)."""
-        if self.sharded and tuple(t.shape) == self.out_shape:
-            lo, hi = self.A.owned_rows
+        if self.sharded and hasattr(self.A, "owned_rows") and tuple(t.shape) == self.out_shape:
+            lo, hi = self.A.owned_rows  # z-slabs; a view block is owned entirely (views are disjoint)
             return t[:, lo - self.A.rows[0]: hi - self.A.rows[0]]
         return t
 

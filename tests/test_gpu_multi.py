@@ -127,6 +127,31 @@ def _worker(rank, world, port, case):
             rel = (torch.linalg.vector_norm(S.x - ref.x[z0:z1]) / torch.linalg.vector_norm(ref.x[z0:z1])).item()
             assert rel <= 1e-5, rel
             assert abs(S.objective() - ref.objective()) <= 1e-5 * ref.objective()
+        elif case == "pdhg_view3d":
+            # TV-PDHG over the view-block partition of a tilted geometry: volume state in z-slabs, sinogram
+            # state in view blocks, fused peer exchange in the back projection
+            from scico_b200.optimize import TVPDHG
+
+            N, D, V = (16, 24, 20), (26, 32), 10
+            ang = np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, 0.5)], 1)
+            M = sb.matrices_from_euler_angles(N, D, "XY", ang)
+            x_gt = np.zeros(N, np.float32)
+            x_gt[3:13, 6:16, 5:14] = 1.0
+            full = sb.XRayTransform3D(N, M, D)
+            y = full(torch.as_tensor(x_gt, device=dev)) + 0.05 * torch.randn((V,) + D, device=dev,
+                                                                              generator=torch.Generator(device=dev).manual_seed(1))
+            dist.broadcast(y, src=0)
+            ref = TVPDHG(full, y, 0.1, 0.05, 0.05, maxiter=20)
+            ref.solve()
+            for exchange in ("nccl", "peer"):
+                op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange=exchange)
+                (z0, z1), (v0, v1) = op.slab, op.views
+                S = TVPDHG(op, y[v0:v1].contiguous(), 0.1, 0.05, 0.05, maxiter=20)
+                S.solve()
+                rel = (torch.linalg.vector_norm(S.x - ref.x[z0:z1]) / torch.linalg.vector_norm(ref.x[z0:z1])).item()
+                assert rel <= 1e-5, (exchange, rel)
+                assert abs(S.objective() - ref.objective()) <= 1e-5 * ref.objective(), exchange
+                op.close()
         elif case in ("admm_slab", "ladmm_slab", "padmm_slab"):
             from scico_b200.optimize import TVADMM, TVLinearizedADMM, TVProximalADMM
 
@@ -161,7 +186,7 @@ def _worker(rank, world, port, case):
 
 
 @pytest.mark.parametrize("case", ["slab", "slab_halo", "view3d", "view2d", "view2d_peer", "view3d_peer", "view2d_peer_add",
-                                  "view3d_peer_add", "pdhg_slab", "admm_slab", "ladmm_slab", "padmm_slab"])
+                                  "view3d_peer_add", "pdhg_slab", "pdhg_view3d", "admm_slab", "ladmm_slab", "padmm_slab"])
 def test_sharded_operators_nccl(case):
     import torch
     import torch.multiprocessing as mp
