@@ -1,6 +1,6 @@
 """Developer GPU check: parity vs the oracle on a few shapes + first timings (run under gpurun)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))  # repo root
 import numpy as np, torch
 import scico_b200 as sb
 from scico_b200 import _lib
