@@ -334,6 +334,15 @@ def test_product_never_imports_oracle():
                 assert "oracle" not in src.replace("the oracle's", "").replace("as the oracle", "") or f.endswith((".cuh", ".cu")), f
                 if f.endswith(".py"):
                     assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+    # tools/ runs the product alone; bench.py touches the oracle only inside its CPU arm (time_cpu_port)
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            assert not re.search(r"^\s*(from|import)\s+oracle", open(os.path.join(ROOT, "tools", f)).read(), re.M), f
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    assert not re.search(r"^(from|import)\s+oracle", bench, re.M)  # no module-level import
+    uses = [m.start() for m in re.finditer(r"from oracle import", bench)]
+    lo, hi = bench.index("def time_cpu_port"), bench.index("class ClockSampler")
+    assert uses and all(lo < u < hi for u in uses)
 
 
 # ---- ASTRA-free geometry conversion (scico/linop/xray/astra/_astra_3d.py:185-307,595-631) ------------
