@@ -317,8 +317,24 @@ def test_fused_exchange_protocol_rank_without_views():
     _spawn(_peer_case, 2, (13, 12), 2, "peer", 3, world=3)  # view blocks (0,0), (0,1), (1,2)
 
 
-def test_fused_exchange_protocol_3d_tilted():
-    _spawn(_peer_case, 3, (9, 8, 7), 5, "peer", 4, world=2)
+@pytest.mark.parametrize("exchange", ["peer", "peer_add"])
+def test_fused_exchange_protocol_3d_tilted(exchange):
+    _spawn(_peer_case, 3, (9, 8, 7), 5, exchange, 4, world=2)
+
+
+def test_fused_exchange_is_a_no_op_choice_for_a_single_rank():
+    """World size 1: nothing to exchange, the operator keeps the plain back projection (no peer buffers)."""
+    op = sharded.ViewShardedXRayTransform2D((12, 10), np.linspace(0, np.pi, 4, endpoint=False), op_factory=OracleOp2D,
+                                            exchange="peer", rank=0, world_size=1)
+    assert op.peer is None and op.exchange == "peer"
+    y = np.random.default_rng(0).standard_normal((4, op.ny)).astype(np.float32)
+    want = OracleOp2D((12, 10), np.linspace(0, np.pi, 4, endpoint=False), det_count=op.ny).back_project(torch.from_numpy(y))
+    assert torch.equal(op.back_project(torch.from_numpy(y)), want)
+    op.close()
+    with pytest.raises(ValueError):
+        sharded.PeerBlocks([(0, 4), (4, 8)], (3,), rank=0, world_size=3, mem=ShmPeerMemory())  # one block per rank
+    with pytest.raises(ValueError):
+        sharded.PeerBlocks([(0, 4)], (3,), rank=0, world_size=1, mode="carrier", mem=ShmPeerMemory())
 
 
 # ---------------------------------------------------------------------------------------------
