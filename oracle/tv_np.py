@@ -118,6 +118,7 @@ def cg(A, b, x0, tol=1e-5, atol=0.0, maxiter=1000):
     num = np.sum(r * r, dtype=f32)
     ii = 0
     termination_tol_sq = np.maximum(f32(tol) * bn, f32(atol)) ** 2
+    trace = [float(num)]  # <r, r> before every iteration (diagnostic, not part of the reference's info)
     while ii < maxiter and num > termination_tol_sq:
         Ap = A(p)
         alpha = f32(num / np.sum(p * Ap, dtype=f32))
@@ -128,7 +129,9 @@ def cg(A, b, x0, tol=1e-5, atol=0.0, maxiter=1000):
         beta = f32(num / num_old)
         p = (r + beta * p).astype(f32)
         ii += 1
-    return x, {"num_iter": ii, "rel_res": float(np.sqrt(num) / bn) if bn > 0 else 0.0}
+        trace.append(float(num))
+    return x, {"num_iter": ii, "rel_res": float(np.sqrt(num) / bn) if bn > 0 else 0.0, "trace": trace,
+               "tol_sq": float(termination_tol_sq)}
 
 
 def admm_tv_init(x0):

@@ -565,6 +565,7 @@ size_t out_elems(const xct_plan* pl) { return (size_t)pl->V * pl->d0 * pl->d1; }
 
 int check_call(const xct_plan* pl, const void* a, const void* b, int batch) {
   if (!pl) return fail(XCT_ERR_INVALID, "null plan");
+  if (pl->dry) return fail(XCT_ERR_INVALID, "analysis-only plan (xct*_plan_analyse) cannot compute");
   if (!a || !b) return fail(XCT_ERR_INVALID, "null buffer");
   if (batch < 1) return fail(XCT_ERR_INVALID, "batch must be >= 1");
   if (pl->ndim == 3 && batch != 1) return fail(XCT_ERR_INVALID, "3D plans take batch == 1");
@@ -920,6 +921,7 @@ int xct_forward(const xct_plan* pl, const float* in, float* out, int32_t batch, 
   int rc = check_call(pl, in, out, batch);
   if (rc) return rc;
   DeviceGuard guard(pl->device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
   // every forward kernel accumulates with RED: the (possibly uninitialised) output is zeroed first
   XCT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * out_elems(pl) * batch, st));
@@ -939,6 +941,7 @@ int xct_adjoint(const xct_plan* pl, const float* in, float* out, int32_t batch, 
   int rc = check_call(pl, in, out, batch);
   if (rc) return rc;
   DeviceGuard guard(pl->device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
   if (pl->ndim == 3) {
     if (pl->adj_walk && (reinterpret_cast<uintptr_t>(in) & 15) == 0) return launch_walk_adjoint(pl, in, out, st);
@@ -975,6 +978,7 @@ int xct_adjoint_scatter(const xct_plan* pl, const float* in, const xct_out_route
   }
   for (int k = r->nparts; k <= xct::kMaxRouteParts; ++k) route.row_begin[k] = rows;
   DeviceGuard guard(pl->device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
   if (pl->ndim == 3) {
     if (pl->adj_plane) return launch_plane_adjoint<xct::Geom3, true, kAdj3S, kAdj3TA>(pl, 1, in, nullptr, st, &route);
@@ -1020,12 +1024,14 @@ int xct_peer_open(int32_t device, const xct_ipc_handle* handle, void** ptr) {
 int xct_peer_zero(int32_t device, void* ptr, size_t bytes, void* stream) {
   if (!ptr) return fail(XCT_ERR_INVALID, "null argument");
   DeviceGuard guard(device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
   XCT_CUDA(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream));
   return XCT_OK;
 }
 int xct_peer_copy_out(int32_t device, void* dst, const void* src, size_t bytes, void* stream) {
   if (!dst || !src) return fail(XCT_ERR_INVALID, "null argument");
   DeviceGuard guard(device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
   XCT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return XCT_OK;
 }
@@ -1033,6 +1039,7 @@ int xct_sum_slots(int32_t device, float* dst, const float* slots, int32_t nslots
   if (!dst || !slots || nslots < 1 || pitch < n) return fail(XCT_ERR_INVALID, "xct_sum_slots: bad argument");
   if (n == 0) return XCT_OK;
   DeviceGuard guard(device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
   xct::sum_slots_kernel<<<general_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(dst, slots, nslots, n, pitch);
   return launch_ok("sum_slots_kernel");
 }
@@ -1128,6 +1135,7 @@ static int run_host(xct_plan* pl, const float* in_host, float* out_host, int32_t
   int rc = check_call(pl, in_host, out_host, batch);
   if (rc) return rc;
   DeviceGuard guard(pl->device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
   if (pl->pipe_ok && pl->n0 >= 64) return run_host_pipelined(pl, in_host, out_host, forward);
   const size_t n_in = (forward ? in_elems(pl) : out_elems(pl)) * batch;
   const size_t n_out = (forward ? out_elems(pl) : in_elems(pl)) * batch;
@@ -1301,6 +1309,7 @@ int xct3d_debug_weights(const xct_plan* pl, int32_t view, int32_t* ul, float* w,
   if (pl->ndim != 3) return fail(XCT_ERR_INVALID, "not a 3D plan");
   if (view < 0 || view >= pl->V) return fail(XCT_ERR_INVALID, "view out of range");
   DeviceGuard guard(pl->device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
   if (pl->adj_plane || pl->fwd_plane) {
     xct::sep3d_weights_kernel<<<general_grid(in_elems(pl)), 256, 0, st>>>(
@@ -1316,6 +1325,7 @@ int xct2d_debug_weights(const xct_plan* pl, int32_t view, int32_t* inds, float* 
   if (pl->ndim != 2) return fail(XCT_ERR_INVALID, "not a 2D plan");
   if (view < 0 || view >= pl->V) return fail(XCT_ERR_INVALID, "view out of range");
   DeviceGuard guard(pl->device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
   xct::gen2d_weights_kernel<<<general_grid(in_elems(pl)), 256, 0, (cudaStream_t)stream>>>(
       gen2_params(pl, 1), view, inds, w);
   return launch_ok("gen2d_weights_kernel");

@@ -247,9 +247,11 @@ class _TVSolver:
         return 0.5 * self._sum(r.double() ** 2) + self.lam * self._l21(d)
 
     @staticmethod
-    def operator_norm_sq(A, dscale: float = 1.0, maxiter: int = 20, seed: int = 0) -> float:
+    def operator_norm_sq(A, dscale: float = 1.0, maxiter: int = 100, seed: int = 0) -> float:
         """``|| (A; dscale*D) ||_2^2`` by power iteration of ``A^T A + dscale^2 D^T D`` on the device
-        (``scico/linop/_util.py:27-110``; the reference runs 100 iterations by default)."""
+        (``scico/linop/_util.py:27-110``; 100 iterations by default like the reference).  Power iteration
+        approaches the norm from BELOW: fewer iterations under-estimate it, which makes every step size
+        derived from it too large -- pass a smaller ``maxiter`` only together with a safety margin."""
         h = _TVSolver()
         sharded = hasattr(A, "slab")
         shape = tuple(A.local_input_shape if sharded else A.input_shape)
@@ -326,10 +328,11 @@ class TVPDHG(_TVSolver):
             self.history.append({"iter": self.itnum, "objective": self.objective(), "prml_rsdl": pr, "dual_rsdl": du})
 
     @staticmethod
-    def estimate_parameters(A, ratio: float = 1.0, factor: Optional[float] = 1.01, maxiter: int = 20, seed: int = 0):
+    def estimate_parameters(A, ratio: float = 1.0, factor: Optional[float] = 1.01, maxiter: int = 100, seed: int = 0):
         """(tau, sigma) from ``||C||_2`` by power iteration of ``C^T C = A^T A + D^T D`` on the device
-        (``_primaldual.py:234-288``, ``scico/linop/_util.py:27-110``; the reference runs 100
-        iterations, 20 are enough for the 1 % safety factor)."""
+        (``_primaldual.py:234-288``, ``scico/linop/_util.py:27-110``; 100 iterations like the reference:
+        the estimate converges from below, so a truncated iteration makes ``tau * sigma * ||C||^2`` larger,
+        not smaller)."""
         cnorm = math.sqrt(_TVSolver.operator_norm_sq(A, 1.0, maxiter, seed))
         factor = 1.0 if factor is None else factor
         # reference formula (_primaldual.py:286-288); note that factor > 1 loosens tau*sigma*||C||^2 < 1,
@@ -370,6 +373,7 @@ class TVADMM(_TVSolver):
         self.scal = torch.zeros(8, dtype=torch.float64, device=self.dev)  # CG inner products (device)
         self.cg_info = {"num_iter": 0, "rel_res": 0.0}
         self.cg_iters_total = 0
+        self.cg_trace, self.cg_tol_sq = [], 0.0
 
     def _allreduce(self, i):
         if self.world > 1:
@@ -399,7 +403,14 @@ class TVADMM(_TVSolver):
         self._allreduce(5)
         host = sc.cpu()
         num, bn2 = float(host[0]), float(host[5])
-        tol_sq = (self.cg_tol ** 2) * bn2
+        # the reference's stop test in its own fp32 arithmetic (scico/solver.py:384-391): bn = ||b|| and
+        # num = <r, r> are float32 scalars there, termination_tol_sq = maximum(tol * bn, atol) ** 2; the
+        # device accumulates both sums in fp64 and they are rounded to fp32 here, before the comparison
+        f32 = np.float32
+        tol_sq = float((f32(self.cg_tol) * f32(math.sqrt(bn2))) ** 2)
+        num = float(f32(num))
+        self.cg_trace = [num]  # <r, r> before every CG iteration of this x-step (fp32-rounded)
+        self.cg_tol_sq = tol_sq
         k = 0
         while k < self.cg_maxiter and num > tol_sq:
             cur, nxt, pq, pq_nxt = k % 3, (k + 1) % 3, 3 + k % 2, 3 + (k + 1) % 2
@@ -413,7 +424,8 @@ class TVADMM(_TVSolver):
                                           sp(cur), sp(pq), sp(nxt), sp(pq_nxt), st))
             self._allreduce(nxt)
             _lib.check(L.xct_cg_update_p(n, self.p.data_ptr(), self.r.data_ptr(), sp(cur), sp(nxt), st))
-            num = float(sc[nxt].item())
+            num = float(f32(sc[nxt].item()))
+            self.cg_trace.append(num)
             k += 1
         self.cg_info = {"num_iter": k, "rel_res": math.sqrt(num / bn2) if bn2 > 0 else 0.0}
         self.cg_iters_total += k
@@ -525,8 +537,8 @@ class TVLinearizedADMM(_TVSplitSolver):
         self._iterate(_lib.SPLIT_LADMM, self.mu / self.nu, 1.0, self.lam * self.nu, self.nu, 1.0)
 
     @staticmethod
-    def estimate_parameters(A, nu: float = 1.0, factor: float = 1.01, maxiter: int = 20, seed: int = 0):
-        """(mu, nu) with ``mu = nu / (factor ||C||^2)``."""
+    def estimate_parameters(A, nu: float = 1.0, factor: float = 1.01, maxiter: int = 100, seed: int = 0):
+        """(mu, nu) with ``mu = nu / (factor ||C||^2)`` (``maxiter``: see :meth:`_TVSolver.operator_norm_sq`)."""
         return nu / (factor * _TVSolver.operator_norm_sq(A, 1.0, maxiter, seed)), nu
 
 
@@ -549,7 +561,7 @@ class TVProximalADMM(_TVSplitSolver):
         self._iterate(_lib.SPLIT_PADMM, 1.0 / self.mu, self.alpha, (self.lam / self.alpha) * plam, plam, 1.0 / self.nu)
 
     @staticmethod
-    def estimate_parameters(A, alpha: float = 1.0, factor: Optional[float] = 1.01, maxiter: int = 20, seed: int = 0):
+    def estimate_parameters(A, alpha: float = 1.0, factor: Optional[float] = 1.01, maxiter: int = 100, seed: int = 0):
         """(mu, nu) = factor * (``||(A; alpha D)||^2``, ``||-I||^2 = 1``) (``_padmm.py:365-412``)."""
         mu = _TVSolver.operator_norm_sq(A, alpha, maxiter, seed)
         f = 1.0 if factor is None else factor

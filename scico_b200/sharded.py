@@ -87,11 +87,10 @@ class SlabShardedXRayTransform3D:
                            for z0, z1 in self.slabs]
         self.slab = self.slabs[self.rank]
         self.rows = self.row_ranges[self.rank]
-        # ownership: a row shared with the previous rank belongs to the previous rank
-        own_lo = self.rows[0]
-        if self.rank > 0:
-            own_lo = max(own_lo, self.row_ranges[self.rank - 1][1])
-        self.owned_rows = (min(own_lo, self.rows[1]), self.rows[1])
+        # ownership: a row held by several ranks (any number of them: with |M00| < 1/2 a detector row collects
+        # slices of more than two slabs, and with M00 < 0 the row ranges run backwards) belongs to the
+        # LOWEST rank that holds it; every global row a slab touches is then owned exactly once.
+        self.owned_rows = self._ownership(self.rank)
         z0, z1 = self.slab
         self.local_input_shape = (z1 - z0,) + self.input_shape[1:]
         self.local_output_shape = (len(self.matrices), self.rows[1] - self.rows[0], self.det_shape[1])
@@ -101,19 +100,40 @@ class SlabShardedXRayTransform3D:
             self.local = factory(self.local_input_shape, self.matrices, self.local_output_shape[1:],
                                  slice_offset=z0, det_row_offset=self.rows[0], det_rows_total=self.det_shape[0])
 
-    # -- halo: rows shared with the neighbours --------------------------------------------------
+    def _ownership(self, rank: int) -> tuple[int, int]:
+        """Rows of ``row_ranges[rank]`` that no lower rank holds, as one interval ``(lo, hi)``."""
+        lo, hi = self.row_ranges[rank]
+        mine = np.ones(max(hi - lo, 0), dtype=bool)
+        for q in range(rank):
+            a, b = self.row_ranges[q]
+            a, b = max(a, lo), min(b, hi)
+            if b > a:
+                mine[a - lo: b - lo] = False
+        idx = np.flatnonzero(mine)
+        if idx.size == 0:
+            return (hi, hi)
+        if idx[-1] - idx[0] + 1 != idx.size:
+            # cannot happen for slabs of a monotone row map; refuse rather than drop rows from the sums
+            raise ValueError(f"z-slab sharding: rank {rank}'s own detector rows are not one interval "
+                             f"(row ranges {self.row_ranges}); use ViewShardedXRayTransform3D")
+        return (lo + int(idx[0]), lo + int(idx[-1]) + 1)
+
+    # -- halo: rows shared with other ranks -------------------------------------------------------
     def _overlap(self, other: int) -> tuple[int, int]:
         a, b = self.rows, self.row_ranges[other]
         return max(a[0], b[0]), min(a[1], b[1])
 
     def halo_rows(self) -> list[tuple[int, int, int]]:
-        """[(neighbour rank, global row lo, global row hi)] for every non-empty overlap."""
+        """[(other rank, global row lo, global row hi)] for every rank whose detector rows overlap this
+        rank's -- the two neighbours for the usual |M00| >= 1/2, more ranks when a detector row collects
+        the slices of several slabs."""
         out = []
-        for other in (self.rank - 1, self.rank + 1):
-            if 0 <= other < self.world_size:
-                lo, hi = self._overlap(other)
-                if hi > lo:
-                    out.append((other, lo, hi))
+        for other in range(self.world_size):
+            if other == self.rank or self.slabs[other][1] <= self.slabs[other][0]:
+                continue
+            lo, hi = self._overlap(other)
+            if hi > lo:
+                out.append((other, lo, hi))
         return out
 
     def _exchange_halo_sum(self, y):
@@ -251,14 +271,19 @@ class PeerBlocks:
         return out
 
     def close(self, collective: bool = True):
-        """Unmap the peers' buffers and free this rank's (``collective``: rendezvous first, so that no peer is
-        still writing into them)."""
+        """Unmap the peers' buffers and free this rank's.  MUST be called by every rank (``collective=True``,
+        the default: two rendezvous make sure no peer is still writing into the buffers that are freed).
+        The non-collective form exists for ``__del__`` / interpreter shutdown only: it waits for this rank's
+        own device work and frees, and is safe only once the peers have stopped using the exchange."""
         if getattr(self, "_closed", True):
             return
         self._closed = True
         both = collective and self.world_size > 1 and dist.is_initialized()
+        try:
+            self.mem.sync()  # this rank's kernels (stores / REDs into mapped peer memory, slot sums) are done
+        except Exception:  # interpreter shutdown
+            pass
         if both:
-            self.mem.sync()
             dist.barrier(group=self.group)
         for q in self._mapped:
             self.mem.close(q)

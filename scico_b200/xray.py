@@ -51,6 +51,9 @@ class _Plans:
         self._make = make
         self._plans: dict[int, ctypes.c_void_p] = {}
         self._lock = threading.Lock()
+        # xct_*_host keeps its staging buffers, streams and events inside the plan (not re-entrant on one
+        # plan): one lock per device serialises concurrent host-array applications of the same operator
+        self._host_locks: dict[int, threading.Lock] = {}
 
     def get(self, device: int) -> ctypes.c_void_p:
         with self._lock:
@@ -59,6 +62,10 @@ class _Plans:
                 pl = self._make(device)
                 self._plans[device] = pl
             return pl
+
+    def host_lock(self, device: int) -> threading.Lock:
+        with self._lock:
+            return self._host_locks.setdefault(device, threading.Lock())
 
     def info(self, device: int) -> dict:
         inf = _lib.PlanInfo()
@@ -117,7 +124,8 @@ def _apply(plans: _Plans, x, out_shape, forward: bool, batch: int, default_devic
         dev = default_device
     else:  # host arrays run on the process's current CUDA device (one process per GPU under torchrun)
         dev = torch.cuda.current_device() if (torch is not None and torch.cuda.is_available()) else 0
-    _lib.check(fn_host(plans.get(dev), xin.ctypes.data, out.ctypes.data, batch))
+    with plans.host_lock(dev):
+        _lib.check(fn_host(plans.get(dev), xin.ctypes.data, out.ctypes.data, batch))
     return torch.from_numpy(out) if was_torch else out
 
 
@@ -146,8 +154,9 @@ if torch is not None:
 
 def _apply_ad(plans: _Plans, x, out_shape, forward: bool, batch: int, default_device: Optional[int], out=None):
     """:func:`_apply`, recorded on the autograd tape when ``x`` is a tensor that requires grad."""
-    if (out is None and torch is not None and isinstance(x, torch.Tensor) and x.requires_grad
-            and torch.is_grad_enabled()):
+    if torch is not None and isinstance(x, torch.Tensor) and x.requires_grad and torch.is_grad_enabled():
+        if out is not None:  # writing into a caller's buffer cannot be recorded: refuse rather than detach silently
+            raise ValueError("'out=' cannot be combined with an input that requires grad (use torch.no_grad() or drop out=)")
         return _ProjectorFn.apply(x, plans, tuple(out_shape), forward, batch, default_device)
     return _apply(plans, x, out_shape, forward, batch, default_device, out)
 

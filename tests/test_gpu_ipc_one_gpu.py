@@ -1,0 +1,122 @@
+"""The fused view-block exchange (``xct_adjoint_scatter`` + ``sharded.PeerBlocks``) with the REAL peer
+memory on ONE GPU: several processes share ``cuda:0``, rendezvous over gloo, and map each other's
+exchange buffers through CUDA IPC (which works between processes on the same device exactly as it does
+across NVLink).  This is what the driver's one-GPU box can run of tests/test_gpu_multi.py: the protocol
+(slot addressing, double-buffered copies, rendezvous placement, re-zeroing), the routed kernels writing
+through IPC-mapped pointers, uneven row blocks, three ranks, a rank without views, store and add mode --
+all against the oracle.  NCCL itself needs one GPU per rank and stays in tests/test_gpu_multi.py.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, case, exchange):
+    import torch
+    import torch.distributed as dist
+
+    import scico_b200 as sb
+    from scico_b200 import sharded
+    from oracle import xray_c as C
+    from oracle import xray_np as O
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(0)
+    dev = "cuda:0"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(17)  # same stream on every rank: same global arrays
+        if case.startswith("view2d"):
+            nx, V = {"view2d": ((200, 168), 48), "view2d_uneven": ((203, 168), 50), "view2d_idle_rank": ((96, 80), 2)}[case]
+            angles = np.linspace(0, np.pi, V, endpoint=False)
+            op = sharded.ViewShardedXRayTransform2D(nx, angles, exchange=exchange)
+            assert op.peer is not None and isinstance(op.peer.mem, sharded._NativePeerMemory)
+            T = sb.XRayTransform2D(nx, angles).view_table
+            (z0, z1), (v0, v1) = op.slab, op.views
+            if case == "view2d_idle_rank":
+                assert world == 3 and (rank != 0 or v1 == v0)  # rank 0 holds no view and only receives
+            for it in range(5):  # both buffer copies are recycled at least twice
+                y = rng.standard_normal((V, op.ny)).astype(np.float32)
+                back = op.back_project(torch.as_tensor(np.ascontiguousarray(y[v0:v1]), device=dev))
+                assert tuple(back.shape) == (z1 - z0, nx[1])
+                assert O.rel_l2(back.cpu().numpy(), C.back_project_2d(y, T, nx)[z0:z1]) <= 1e-5, (it, rank)
+            x = rng.standard_normal(nx).astype(np.float32)
+            got = op.project(torch.as_tensor(x, device=dev)).cpu().numpy()
+            if v1 > v0:
+                assert O.rel_l2(got, C.project_2d(x, T, op.ny)[v0:v1]) <= 1e-5
+            op.close()
+        elif case in ("view3d_tilt", "view3d_sep"):
+            if case == "view3d_tilt":  # general kernels (routed gen3d adjoint)
+                N, D, V = (20, 24, 28), (30, 36), 10
+                ang = np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, 0.5)], 1)
+                M = sb.matrices_from_euler_angles(N, D, "XY", ang)
+            else:  # separable plan in view-block mode (routed walk / plane adjoint)
+                N, D, V = (24, 96, 80), (24, 128), 12
+                M = sb.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, V, endpoint=False)[:, None])
+            op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange=exchange)
+            assert op.peer is not None
+            (z0, z1), (v0, v1) = op.slab, op.views
+            for it in range(4):
+                y = rng.standard_normal((V,) + D).astype(np.float32)
+                back = op.back_project(torch.as_tensor(np.ascontiguousarray(y[v0:v1]), device=dev)).cpu().numpy()
+                assert back.shape == (z1 - z0,) + N[1:]
+                assert O.rel_l2(back, C.back_project_3d(y, op.matrices, N)[z0:z1]) <= 1e-5, (it, rank)
+            x = rng.standard_normal(N).astype(np.float32)
+            got = op.project(torch.as_tensor(x[z0:z1], device=dev)).cpu().numpy()  # all-gather of the slabs
+            assert O.rel_l2(got, C.project_3d(x, op.matrices, D)[v0:v1]) <= 1e-5
+            op.close()
+        elif case == "pdhg_view3d":
+            # TV-PDHG over the view-block partition of a tilted geometry: volume state in z-slabs, sinogram
+            # state in view blocks, the fused peer exchange inside every back projection
+            from scico_b200.optimize import TVPDHG
+
+            N, D, V = (16, 24, 20), (26, 32), 10
+            ang = np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, 0.5)], 1)
+            M = sb.matrices_from_euler_angles(N, D, "XY", ang)
+            x_gt = np.zeros(N, np.float32)
+            x_gt[3:13, 6:16, 5:14] = 1.0
+            full = sb.XRayTransform3D(N, M, D)
+            noise = rng.standard_normal((V,) + D).astype(np.float32)
+            y = full(torch.as_tensor(x_gt, device=dev)) + 0.05 * torch.as_tensor(noise, device=dev)
+            ref = TVPDHG(full, y, 0.1, 0.05, 0.05, maxiter=20)
+            ref.solve()
+            op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange=exchange)
+            (z0, z1), (v0, v1) = op.slab, op.views
+            S = TVPDHG(op, y[v0:v1].contiguous(), 0.1, 0.05, 0.05, maxiter=20)
+            S.solve()
+            rel = (torch.linalg.vector_norm(S.x - ref.x[z0:z1]) / torch.linalg.vector_norm(ref.x[z0:z1])).item()
+            assert rel <= 1e-5, (exchange, rel)
+            assert abs(S.objective() - ref.objective()) <= 1e-5 * ref.objective(), exchange
+            op.close()
+        else:
+            raise AssertionError(case)
+        torch.cuda.synchronize()
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+CASES = [
+    ("view2d", 2, "peer"), ("view2d", 2, "peer_add"), ("view2d_uneven", 3, "peer"), ("view2d_uneven", 3, "peer_add"),
+    ("view2d_idle_rank", 3, "peer"), ("view2d_idle_rank", 3, "peer_add"),
+    ("view3d_tilt", 2, "peer"), ("view3d_tilt", 3, "peer"), ("view3d_tilt", 3, "peer_add"),
+    ("view3d_sep", 2, "peer"), ("view3d_sep", 3, "peer_add"),
+    ("pdhg_view3d", 2, "peer"),
+]
+
+
+@pytest.mark.parametrize("case,world,exchange", CASES, ids=[f"{c}-w{w}-{e}" for c, w, e in CASES])
+def test_fused_exchange_over_cuda_ipc_on_one_gpu(cuda_device, case, world, exchange):
+    import torch.multiprocessing as mp
+
+    mp.spawn(_worker, args=(world, _free_port(), case, exchange), nprocs=world, join=True)

@@ -77,8 +77,11 @@ def _gather_rows(op, y_local, V, D):
 
 
 # ---------------------------------------------------------------------------------------------
-def _slab_case(rank, world, N, D, V, spacing):
+def _slab_case(rank, world, N, D, V, spacing, flip=False):
     M = O.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, V, endpoint=False)[:, None], voxel_spacing=spacing)
+    if flip:  # detector rows run against the slice index: M00 < 0
+        M = np.array(M, copy=True)
+        M[:, 0, 0], M[:, 0, 3] = -M[:, 0, 0], D[0] - M[:, 0, 3]
     rng = np.random.default_rng(5)
     x = rng.standard_normal(N).astype(np.float32)
     y = rng.standard_normal((V,) + D).astype(np.float32)
@@ -114,6 +117,17 @@ def test_slab_sharded_with_row_halo():
 
 def test_slab_sharded_three_ranks_uneven():
     _spawn(_slab_case, (10, 8, 9), (10, 12), 3, None, world=3)
+
+
+def test_slab_sharded_rows_shared_by_more_than_two_ranks():
+    """|M00| = 0.4 with one-slice slabs: a detector row collects the slices of three or four ranks, so the
+    halo exchange and the row ownership must look beyond the two neighbours."""
+    _spawn(_slab_case, (4, 6, 5), (6, 8), 3, [0.4, 1.0, 1.0], world=4)
+
+
+def test_slab_sharded_reversed_row_order():
+    """M00 < 0: row ranges decrease with the rank; every touched row must still be owned exactly once."""
+    _spawn(_slab_case, (11, 10, 9), (12, 14), 4, [0.8, 1.0, 1.0], True)
 
 
 def _view_case_3d(rank, world, N, D, V, seq):
