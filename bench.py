@@ -3,9 +3,13 @@
 
 Workload (BASELINE.json configs[4] operator / north_star target): 3D parallel-beam
 XRayTransform3D, 1024^3 volume, 1024 views about axis 0, 1024x1024 detector.  One step = one
-forward projection + one back projection.  With N GPUs the operator is partitioned into N z-slabs
-(volume slices <-> detector rows), one process per GPU, no data-path collective: total work is
-fixed, so scaling is "strong".
+forward projection + one back projection on DENSE input (standard-normal volume, its sinogram); the
+tanglecube phantom (56 % zeros, for which the forward skips all-zero flushes) is timed beside it as
+`phantom`.  With N GPUs the operator is partitioned into N z-slabs (volume slices <-> detector rows),
+one process per GPU, no data-path collective: total work is fixed, so scaling is "strong".  The
+partition that DOES communicate (view blocks: C3 = BASELINE.json configs[2] and a tilted 3D geometry,
+back projection + NCCL reduce-scatter or the exchange fused into the kernel over NVLink peer memory)
+is timed at every N as `view_block`.
 
     python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
@@ -133,8 +137,12 @@ def hbm_peak():
 
 
 def ncu_profile():
-    """Per-launch DRAM bytes of the two kernels from the committed ncu summary (profiles/), if any."""
-    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    """Warp instructions and DRAM bytes per voxel-view update of the two hot kernels, from the committed ncu
+    capture AT BENCH SIZE (profiles/ncu_r02_bench_size.json, written by tools/ncu_inst_counts.py from
+    `ncu --metrics smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum` over this very script).
+    Instruction counts are a property of the code and the shape, not of the data or the clocks; the launch
+    durations they are divided by are measured live, below."""
+    p = os.path.join(ROOT, "profiles", "ncu_r02_bench_size.json")
     if os.path.exists(p):
         try:
             return json.load(open(p))
@@ -189,6 +197,86 @@ def other_configs(torch, sb, dev):
     return out
 
 
+def view_block_configs(torch, dist, sb, sharded, dev, world, barrier, reduce_max):
+    """The partition of the path that has a real exchange step, timed at this N (BASELINE.json
+    configs[2]): contiguous view blocks per rank.  C3 (2D 4096^2 x 2048 views): image replicated, partial
+    back projections summed row block by row block into their owners -- by ONE NCCL reduce_scatter
+    ("nccl") or inside the back-projection kernel's epilogue over NVLink peer memory ("peer",
+    xct_adjoint_scatter + sharded.PeerBlocks).  Tilted 3D (256^3 x 64 views, 74 degree XY tilt, general
+    matrices): all-gather of the slab-sharded volume before the forward, per-slab reduce / fused exchange after
+    the adjoint.  CUDA events between barriers, 3 warm-ups, max over ranks."""
+
+    def timeit(fn, reps=3):
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        return reduce_max(e0.elapsed_time(e1) / reps)
+
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(1234)  # same seed on every rank: replicated inputs agree
+    n, V = 4096, 2048
+    angles = np.linspace(0, np.pi, V, endpoint=False)
+    A = sharded.ViewShardedXRayTransform2D((n, n), angles)
+    x = torch.randn((n, n), device=dev, generator=g)
+    y = A.project(x)
+    f_ms = timeit(lambda: A.project(x))
+    a_nccl = timeit(lambda: A.back_project(y, scatter=True))
+    a_local = timeit(lambda: A.local.back_project(y))
+    a_peer = None
+    if world > 1:
+        P = sharded.ViewShardedXRayTransform2D((n, n), angles, exchange="peer")
+        a_peer = timeit(lambda: P.back_project(y))
+        ref, got = A.back_project(y), P.back_project(y)
+        peer_err = reduce_max((torch.linalg.vector_norm(got - ref) / torch.linalg.vector_norm(ref)).item())
+        P.close()
+        del P, ref, got
+    upd = float(n) * n * V
+    best = a_nccl if a_peer is None else min(a_nccl, a_peer)
+    out["C3 2D 4096^2 x 2048 views"] = {
+        "views_per_rank": A.views[1] - A.views[0], "fwd_ms": f_ms, "adj_ms_nccl_reduce_scatter": a_nccl,
+        "adj_ms_fused_peer_exchange": a_peer, "adj_ms_kernel_only": a_local,
+        "pair_updates_per_s_nccl": 2 * upd / (f_ms + a_nccl) * 1e3, "pair_updates_per_s_best": 2 * upd / (f_ms + best) * 1e3,
+        "peer_vs_nccl_rel_l2": None if a_peer is None else peer_err,
+        "collective": "none (one rank)" if world == 1 else
+                      "ncclReduceScatter(sum) of the 64 MB partial images over equal row blocks | fused: stores into the "
+                      "owners' slots over NVLink + slot sum"}
+    del A, x, y
+    torch.cuda.empty_cache()
+
+    n, V = 256, 64
+    angs = np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, np.deg2rad(74.0))], 1)
+    D = (n + 64, n + 64)
+    M = sb.matrices_from_euler_angles((n,) * 3, D, "XY", angs)
+    A = sharded.ViewShardedXRayTransform3D((n,) * 3, M, D)
+    xs = torch.randn(A.local_input_shape, device=dev, generator=g)
+    ys = A.project(xs)
+    f_ms = timeit(lambda: A.project(xs))
+    a_nccl = timeit(lambda: A.back_project(ys))
+    a_peer = None
+    if world > 1:
+        P = sharded.ViewShardedXRayTransform3D((n,) * 3, M, D, exchange="peer")
+        a_peer = timeit(lambda: P.back_project(ys))
+        P.close()
+        del P
+    upd = float(n) ** 3 * V
+    best = a_nccl if a_peer is None else min(a_nccl, a_peer)
+    info = A.full.plan_info(torch.cuda.current_device()) if A.full is not None else {}
+    out["3D 256^3 x 64 views, XY tilt 74 deg (general matrices)"] = {
+        "fwd_ms": f_ms, "adj_ms_nccl_reduce": a_nccl, "adj_ms_fused_peer_exchange": a_peer,
+        "pair_updates_per_s_nccl": 2 * upd / (f_ms + a_nccl) * 1e3, "pair_updates_per_s_best": 2 * upd / (f_ms + best) * 1e3,
+        "kernel_path": info.get("path_name"),
+        "collective": "none (one rank)" if world == 1 else
+                      "forward: ncclAllGather of the slab-sharded volume; adjoint: per-slab ncclReduce overlapped with the "
+                      "next slab's kernel | fused peer exchange"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -230,6 +318,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the C2 / C3 / C4 timings")
+    ap.add_argument("--no-view-block", action="store_true", help="skip the view-block (communicating) partition timings")
     ap.add_argument("--solver-iters", type=int, default=3, help="TV-PDHG iterations timed after the operator bench (0 = skip)")
     args = ap.parse_args()
 
@@ -252,7 +341,8 @@ def main():
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)  # NCCL's version banner goes to stdout: keep it to ONE JSON line
+        # NCCL_DEBUG is left as the caller set it (the driver counts ranks from NCCL's own log); whatever NCCL
+        # prints are separate lines, the JSON line below is printed once, by rank 0, at the very end
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     wl = workload(args)
@@ -274,10 +364,6 @@ def main():
         val = (xx**4 - 5 * xx**2 + yy**4 - 5 * yy**2 + zz**4 - 5 * zz**2 + 11.8) * 0.2 + 0.5
         return torch.where(val <= 2.0, 2.0 - val, torch.zeros_like(val)).clamp_(min=0.0).contiguous()
 
-    x = tangle(z0, z1)
-    y = A(x)  # sinogram of the phantom: the adjoint's input
-    torch.cuda.synchronize()
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -292,6 +378,32 @@ def main():
         return float(t.item())
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def time_pairs(x, y, warmup, steps):
+        """`steps` forward + adjoint pairs on resident inputs: (total ms, fwd ms, adj ms), max over ranks."""
+        for _ in range(warmup):
+            A(x)
+            A.adj(y)
+        barrier()
+        e0, e1 = ev(), ev()
+        fe = [(ev(), ev(), ev()) for _ in range(steps)]
+        e0.record()
+        for k in range(steps):
+            fe[k][0].record()
+            A(x)
+            fe[k][1].record()
+            A.adj(y)
+            fe[k][2].record()
+        e1.record()
+        barrier()
+        return (reduce_max(e0.elapsed_time(e1)), reduce_max(float(np.mean([a.elapsed_time(b) for a, b, _ in fe]))),
+                reduce_max(float(np.mean([b.elapsed_time(c) for _, b, c in fe]))))
+
+    # headline input: DENSE (standard-normal volume, no zeros: nothing for the forward's zero-block flush
+    # predication to skip) and its own sinogram
+    x = torch.randn((z1 - z0,) + N[1:], device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank))
+    y = A(x)
+    torch.cuda.synchronize()
     for _ in range(args.warmup):
         A(x)
         A.adj(y)
@@ -303,65 +415,68 @@ def main():
         time.sleep(0.3)
     _lib.launch_count_reset()
     t_wall0 = time.perf_counter()
-    e0, e1 = ev(), ev()
-    fe = [(ev(), ev(), ev()) for _ in range(args.steps)]
-    e0.record()
-    for k in range(args.steps):
-        fe[k][0].record()
-        A(x)
-        fe[k][1].record()
-        A.adj(y)
-        fe[k][2].record()
-    e1.record()
-    barrier()
+    total_ms, fwd_ms, adj_ms = time_pairs(x, y, 0, args.steps)
     t_wall1 = time.perf_counter()
     launches = _lib.launch_count()
-    total_ms = reduce_max(e0.elapsed_time(e1))
-    fwd_ms = reduce_max(float(np.mean([a.elapsed_time(b) for a, b, _ in fe])))
-    adj_ms = reduce_max(float(np.mean([b.elapsed_time(c) for _, b, c in fe])))
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # the same step on the tanglecube phantom (the reference examples' test object; 56 % zeros)
+    xp = tangle(z0, z1)
+    yp = A(xp)
+    p_total, p_fwd, p_adj = time_pairs(xp, yp, 1, args.steps)
+    nz = reduce_max(float((xp != 0).float().mean().item()))
+    del xp, yp
 
     ms_per_step = total_ms / args.steps
     updates_step = 2.0 * float(np.prod(N)) * V  # whole job: fwd + adj over the full volume
     value = updates_step / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel (forward plane kernel; one launch per view class).
-    # algorithmic bytes per application = 4 B per voxel-view update + the sinogram once
+    # ---- roofline of the dominant kernel (the forward: 60 % of a step) --------------------------------
+    # The binding resource is INSTRUCTION ISSUE, not HBM: voxels (forward) / accumulators (adjoint) stay in
+    # registers across all views, so real DRAM traffic is ~0.3 % of what the per-view streaming model of
+    # SURVEY 8(d) assumes (that model is kept below as `hbm_model`, labelled; its "fraction" exceeds 1).
+    #   achieved = warp instructions per launch (ncu smsp__inst_executed.sum at THIS shape, committed under
+    #              profiles/; a property of code + shape) / the launch duration measured live with CUDA events
+    #   peak     = SMs x 4 schedulers x SM clock sampled during the timed region (1 warp instruction per
+    #              scheduler per cycle)
     peak, peak_src = hbm_peak()
     loc_updates = float((z1 - z0) * N[1] * N[2]) * V
     loc_bytes = 4.0 * (loc_updates + float(V) * (r1 - r0) * D[1])
     n_fwd_launch = max(1, int(launches) // max(1, args.steps) - 1)  # per step: forward class launches + 1 adjoint
-    ach_fwd = loc_bytes / (fwd_ms * 1e-3) / 1e9
-    ach_adj = loc_bytes / (adj_ms * 1e-3) / 1e9
     kname = {0: "gen3d", 1: "plane", 2: "walk"}
     prof = ncu_profile()
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    if world > 1:
+        t = torch.tensor([sm_mhz], device=dev, dtype=torch.float64)
+        dist.broadcast(t, src=0)
+        sm_mhz = float(t.item())
+    issue_peak = n_sm * 4 * sm_mhz * 1e6 / 1e9  # G warp instructions / s
 
-    def ncu_metric(pattern, label):  # mean of a metric over the captured launches of one kernel family
-        vals = [k[label] for k in prof.get("kernels", []) if pattern in k.get("name", "") and isinstance(k.get(label), float)]
-        return float(np.mean(vals)) if vals else None
+    def issue_roofline(key, ms, launches_per_app):
+        k = prof.get(key) or {}
+        ipu = k.get("warp_inst_per_update")
+        inst = ipu * loc_updates if ipu else None
+        ach = inst / (ms * 1e-3) / 1e9 if inst else None
+        return {"achieved": ach, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": ach / issue_peak if ach else None,
+                "warp_inst_per_launch": inst / launches_per_app if inst else None, "warp_inst_per_update": ipu,
+                "launch_ms": ms / launches_per_app, "launches_per_application": launches_per_app,
+                "traffic": (k.get("dram_bytes_per_update") * loc_updates / launches_per_app) if k.get("dram_bytes_per_update") else None,
+                "traffic_source": k.get("source"), "issue_active_pct_ncu": k.get("issue_active_pct"),
+                "hbm_model": {"achieved": loc_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": loc_bytes / (ms * 1e-3) / 1e9 / peak,
+                              "note": "SURVEY 8(d) per-view streaming model (4 B per update + the sinogram once): NOT a lower "
+                                      "bound for kernels that keep voxels in registers across views; kept for reference"}}
 
-    fwd_name = (f"walk_forward_joint_kernel<Geom3> (+ walk_forward_kernel for the views within rounding distance of a unit "
-                f"coefficient; {n_fwd_launch} class launches per application)" if info.get("fwd_joint")
+    fwd_name = (f"walk_forward_joint_kernel<Geom3> ({n_fwd_launch} class launches per application)" if info.get("fwd_joint")
                 else f"{kname[info['fwd_kernel']]}_forward_kernel<Geom3> ({n_fwd_launch} launches per application, one per view class)")
-    roofline = {
-        "bound": "hbm", "kernel": fwd_name,
-        "achieved": ach_fwd, "peak": peak, "unit": "GB/s", "frac": ach_fwd / peak,
-        "algorithmic_bytes_per_launch": loc_bytes / n_fwd_launch, "launch_ms": fwd_ms / n_fwd_launch,
-        "traffic": prof.get("forward_traffic_bytes_per_launch_at_bench_size"), "peak_source": peak_src + ", of measured",
-        "model": "4 B per voxel-view update + 4 B per sinogram element (per-view streaming model the reference executes); "
-                 "real DRAM traffic (ncu) is ~1000x lower: the kernels are shared-memory / instruction-issue bound, "
-                 "so a fraction above 1 is possible and only says the per-view streaming model is beaten",
-        # the binding resource under the real traffic (committed ncu --set full capture, profiles/ncu_summary.json)
-        "binding_resource": "instruction issue",
-        "issue_active_pct_ncu": ncu_metric("walk_forward_joint", "issue active %"),
-        "dram_throughput_pct_ncu": ncu_metric("walk_forward_joint", "dram throughput %"),
-        "adjoint": {"issue_active_pct_ncu": ncu_metric("walk_adjoint", "issue active %"),
-                    "dram_throughput_pct_ncu": ncu_metric("walk_adjoint", "dram throughput %"),
-                    "kernel": f"{kname[info['adj_kernel']]}_adjoint_kernel<Geom3> (1 launch per application"
-                              + (", TMA-staged sinogram window)" if info.get("adj_tma") else ")"), "achieved": ach_adj,
-                    "frac": ach_adj / peak, "launch_ms": adj_ms,
-                    "traffic": prof.get("adjoint_traffic_bytes_per_launch_at_bench_size")},
-    }
+    roofline = {"bound": "issue", "kernel": fwd_name, "sm_clock_mhz_in_timed_region": sm_mhz, "sms": n_sm,
+                "peak_source": "SMs x 4 warp schedulers x the SM clock nvidia-smi reported during the timed region",
+                "hbm_peak_source": peak_src + ", of measured"}
+    roofline.update(issue_roofline("walk_forward_joint", fwd_ms, n_fwd_launch))
+    roofline["adjoint"] = {"kernel": f"{kname[info['adj_kernel']]}_adjoint_kernel<Geom3> (1 launch per application"
+                                     + (", TMA-staged sinogram window)" if info.get("adj_tma") else ")")}
+    roofline["adjoint"].update(issue_roofline("walk_adjoint", adj_ms, 1))
 
     # end-to-end through the public API with HOST buffers (pinned): H2D + kernels + D2H per call
     e2e = None
@@ -386,6 +501,7 @@ def main():
         per_dir = 4 * (x.numel() + y.numel())
         e2e = {"value": updates_step / dt, "unit": UNIT, "h2d_bytes_per_step": int(per_dir * world),
                "d2h_bytes_per_step": int(per_dir * world), "ms_per_step": dt * 1e3,
+               "pcie_gb_per_s_per_gpu_per_direction": per_dir / dt / 1e9,
                "api": "XRayTransform3D.project/.back_project(host array, out=pinned host array) -> xct_forward_host/xct_adjoint_host"}
 
     # second half of BASELINE.json's metric: TV-regularised PDHG iterations/s on the same operator
@@ -447,6 +563,13 @@ def main():
         torch.cuda.empty_cache()
         others = other_configs(torch, sb, dev)
 
+    # the communicating partition (view blocks), at this N
+    view_block = None
+    if not args.no_view_block:
+        x = y = None
+        torch.cuda.empty_cache()
+        view_block = view_block_configs(torch, dist, sb, sharded, dev, world, barrier, reduce_max)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = cpu_sample(wl)
@@ -460,11 +583,15 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"XRayTransform3D {N[0]}x{N[1]}x{N[2]} volume, {V} views about axis 0, detector {D[0]}x{D[1]}, "
-                                   "one forward + one adjoint per step (tanglecube phantom)",
+                                   "one forward + one adjoint per step, dense standard-normal input",
                        "partition": f"{world} z-slab(s), no collective", "kernel_path": info["path_name"],
                        "l2": "no flush: per-rank volume and sinogram (>= 0.5 GB each at 8 GPUs) exceed the 126 MB L2",
                        "fwd_ms": fwd_ms, "adj_ms": adj_ms},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "solver": solver, "other_configs": others,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "phantom": {"input": f"tanglecube phantom, {100 * nz:.1f} % non-zero voxels (the forward skips all-zero flushes)",
+                        "ms_per_step": p_total / args.steps, "fwd_ms": p_fwd, "adj_ms": p_adj,
+                        "value": updates_step / (p_total / args.steps * 1e-3), "unit": UNIT},
+            "view_block": view_block, "solver": solver, "other_configs": others,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -126,32 +126,35 @@ class _TVSolver:
     def _neighbour(self, r):
         return r if self.group is None else dist.get_global_rank(self.group, r)
 
+    def _exchange_planes(self, plane, send_to, recv_from):
+        """Point-to-point exchange of one boundary plane: send ``plane`` to rank ``send_to`` (None: nobody),
+        receive the matching plane of rank ``recv_from`` (None: nobody -> returns None).  NCCL moves device
+        memory directly; under gloo (the CPU / one-GPU test rendezvous, which cannot send device pointers) the
+        plane is staged through host memory."""
+        staged = plane.is_cuda and dist.get_backend(self.group) == "gloo"
+        src = plane.cpu() if staged else plane
+        ops, recv = [], None
+        if send_to is not None:
+            ops.append(dist.P2POp(dist.isend, src, self._neighbour(send_to), self.group))
+        if recv_from is not None:
+            recv = torch.empty_like(src)
+            ops.append(dist.P2POp(dist.irecv, recv, self._neighbour(recv_from), self.group))
+        for req in dist.batch_isend_irecv(ops) if ops else []:
+            req.wait()
+        return recv.to(plane.device) if (staged and recv is not None) else recv
+
     def _halo_from_prev(self, plane_to_next):
         """Send ``plane_to_next`` to rank+1, receive the previous rank's plane (None on rank 0)."""
         if self.world == 1:
             return None
-        ops, recv = [], None
-        if self.rank + 1 < self.world:
-            ops.append(dist.P2POp(dist.isend, plane_to_next, self._neighbour(self.rank + 1), self.group))
-        if self.rank > 0:
-            recv = torch.empty_like(plane_to_next)
-            ops.append(dist.P2POp(dist.irecv, recv, self._neighbour(self.rank - 1), self.group))
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-        return recv
+        return self._exchange_planes(plane_to_next, self.rank + 1 if self.rank + 1 < self.world else None,
+                                     self.rank - 1 if self.rank > 0 else None)
 
     def _halo_from_next(self, plane_to_prev):
         if self.world == 1:
             return None
-        ops, recv = [], None
-        if self.rank > 0:
-            ops.append(dist.P2POp(dist.isend, plane_to_prev, self._neighbour(self.rank - 1), self.group))
-        if self.rank + 1 < self.world:
-            recv = torch.empty_like(plane_to_prev)
-            ops.append(dist.P2POp(dist.irecv, recv, self._neighbour(self.rank + 1), self.group))
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-        return recv
+        return self._exchange_planes(plane_to_prev, self.rank - 1 if self.rank > 0 else None,
+                                     self.rank + 1 if self.rank + 1 < self.world else None)
 
     def _lo_plane(self, g):
         """Halo for ``D^T g``: plane ``g[0][-1]`` of the previous slab."""

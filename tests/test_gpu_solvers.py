@@ -279,6 +279,23 @@ def _disc_phantom(n, seed=1234, discs=40):
     return img
 
 
+def _cg_fp64_sums(Aop, b, x0, k):
+    """k iterations of scico.solver.cg's recurrences (oracle/tv_np.py::cg) with the inner products accumulated
+    in fp64 -- the device's accumulation -- and everything else in fp32: a second, equally valid arithmetic."""
+    x = np.asarray(x0, f32)
+    r = (b - Aop(x)).astype(f32)
+    p = r
+    num = np.sum(r.astype(np.float64) ** 2)
+    for _ in range(k):
+        Ap = Aop(p)
+        alpha = f32(num / np.sum(p.astype(np.float64) * Ap))
+        x = (x + alpha * p).astype(f32)
+        r = (r - alpha * Ap).astype(f32)
+        num_old, num = num, np.sum(r.astype(np.float64) ** 2)
+        p = (r + f32(num / num_old) * p).astype(f32)
+    return x
+
+
 def test_c1_tv_admm_reference_defaults_every_iteration_matches_oracle(cuda_device):
     """BASELINE.json configs[0] (C1: 256^2, 180 views) with the reference example's parameters
     (ct_tv_admm.py:61-84: lam 2, rho 5, 25 iterations, CG tol 1e-4 / maxiter 25, x0 = clip(fbp)).
@@ -292,8 +309,8 @@ def test_c1_tv_admm_reference_defaults_every_iteration_matches_oracle(cuda_devic
     from identical state: 6e-9 after 1, 6e-8 after 5, 5e-6 after 15, 4e-4 after 25 iterations).
 
     What CAN be pinned, and is: every one of the 25 ADMM iterations, started from the GPU solver's own state,
-    equals the oracle's iteration from that state with the same CG depth (tolerance by depth, from the
-    amplification above); the <r, r> sequence the stop test reads agrees with the oracle's; the stop test is
+    equals the oracle's iteration from that state with the same CG depth (tolerance: 4x the oracle's own
+    sensitivity to fp32-vs-fp64 inner products at that state and depth, at least 1e-4); the <r, r> sequence the stop test reads agrees with the oracle's; the stop test is
     the reference's fp32 expression; and the reconstruction quality equals a free-running oracle's."""
     import torch
 
@@ -328,10 +345,16 @@ def test_c1_tv_admm_reference_defaults_every_iteration_matches_oracle(cuda_devic
         # <r, r> before each CG iteration: same sequence while the depth keeps fp32 amplification small
         for j in range(min(k, 12) + 1):
             worst["trace"] = max(worst["trace"], abs(info["trace"][j] / tr_g[j] - 1.0))
-        tol_x = 1e-4 if k <= 15 else 2e-3
+        # tolerance: the oracle's own sensitivity to the accumulation precision of CG's inner products (fp32
+        # as in the reference vs fp64 as on the device) from the same state at the same depth, times 4, and
+        # never below the 1e-4 of the fixed-depth tests: fp32 CG amplifies rounding by ~2.5x per iteration
+        x64 = _cg_fp64_sums(lambda v: (f32(rho) * T.finite_difference_adj(T.finite_difference(v)) + ATo(Ao(v))).astype(f32),
+                            rhs, xs, k)
+        tol_x = max(1e-4, 4.0 * O.rel_l2(x64, xo))
         ex = O.rel_l2(S.x.cpu().numpy(), xo)
         worst["x"] = max(worst["x"], ex / tol_x)
-        assert ex <= tol_x, (it, k, ex)
+        assert ex <= tol_x, (it, k, ex, tol_x)
+        assert tol_x <= 2e-2, (it, k, tol_x)  # the calibration itself stays small (seen: <= 2e-3)
         assert O.rel_l2(S.z.cpu().numpy(), zo) <= 10 * tol_x, (it, k)
         assert np.abs(S.u.cpu().numpy() - uo).max() <= 10 * tol_x * max(1.0, np.abs(uo).max()), (it, k)
     assert worst["trace"] <= 0.05, worst

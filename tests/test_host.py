@@ -178,7 +178,10 @@ def test_autograd_resolves_to_the_adjoint_kernel(monkeypatch):
         assert not A(x).requires_grad
     assert not A(x.detach()).requires_grad and calls == ["f", "f"]
     out = torch.empty(A.output_shape, dtype=torch.float32)
-    assert not A.project(x, out=out).requires_grad  # an explicit result buffer bypasses the tape, as in-place results must
+    with pytest.raises(ValueError):  # an explicit result buffer cannot be recorded on the tape: refused, not detached
+        A.project(x, out=out)
+    with torch.no_grad():
+        assert not A.project(x, out=out).requires_grad
 
 
 # ---- C ABI ----------------------------------------------------------------------------------
