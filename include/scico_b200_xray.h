@@ -62,6 +62,7 @@ typedef enum xct_status {
 #define XCT_FLAG_NO_HOST_PIPELINE 0x4u /* xct_*_host: one H2D, kernels, one D2H (testing / comparison) */
 #define XCT_FLAG_NO_TMA 0x10u       /* walk adjoint: stage the sinogram window with cp.async, not TMA (testing / comparison) */
 #define XCT_FLAG_NO_JOINT 0x8u      /* walk forward: one column per walk for every view (testing / comparison) */
+#define XCT_FLAG_NO_BRICK 0x20u     /* general 3D matrices: thread-per-voxel kernels instead of the brick kernels (testing / comparison) */
 
 /* kernel families a plan can resolve to (xct_plan_info.path) */
 #define XCT_PATH_2D_PLANE 1   /* 2D, warp-autonomous plane kernels */
@@ -73,6 +74,7 @@ typedef enum xct_status {
 #define XCT_KERNEL_GENERAL 0 /* thread-per-voxel, any geometry */
 #define XCT_KERNEL_PLANE 1   /* warp-autonomous plane kernels (xct_plane.cuh) */
 #define XCT_KERNEL_WALK 2    /* register-walk kernels with cp.async staging (xct_plane2.cuh) */
+#define XCT_KERNEL_BRICK 3   /* general 3D matrices: brick kernels, TMA-staged detector windows (xct_brick.cuh) */
 
 typedef struct xct_plan xct_plan; /* opaque */
 
@@ -109,7 +111,7 @@ typedef struct xct_plan_info {
   int32_t adj_kernel;     /* XCT_KERNEL_*: what xct_adjoint launches (16-byte aligned input assumed) */
   int32_t fwd_kernel;     /* XCT_KERNEL_*: what xct_forward launches */
   int32_t fwd_joint;      /* walk forward: views that move by at most one bin per step use the joint-column kernel */
-  int32_t adj_tma;        /* walk adjoint: sinogram window staged by TMA (one box per view) */
+  int32_t adj_tma;        /* walk / brick adjoint: sinogram window staged by TMA (one box per view and tile) */
   int64_t in_elems;       /* elements of one forward input (per batch item) */
   int64_t out_elems;      /* elements of one forward output (per batch item) */
   int64_t updates;        /* voxel-view updates per application = in_elems * num_views */
@@ -123,6 +125,7 @@ typedef struct xct_plan_classes {
   int32_t rows_unit;        /* 3D sep: every (view, slice) lands in one detector row with weight 2 */
   int32_t rows_consecutive; /* 3D sep: local row = local slice + const per view (TMA box / krow flush) */
   int32_t fwd_cold;         /* some minor coefficient can move the bin by two per step */
+  int32_t brick_views[6];   /* general 3D (brick forward): views per class [2*depth_axis + needs_shared_atomics] */
 } xct_plan_classes;
 
 XCT_API int xct_version(void);

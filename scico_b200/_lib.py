@@ -26,8 +26,9 @@ FLAG_FORCE_GENERAL = 0x1
 FLAG_NO_WALK = 0x2
 FLAG_NO_HOST_PIPELINE = 0x4
 FLAG_NO_JOINT = 0x8
+FLAG_NO_BRICK = 0x20
 FLAG_NO_TMA = 0x10
-KERNEL_NAMES = {0: "general", 1: "plane", 2: "walk"}
+KERNEL_NAMES = {0: "general", 1: "plane", 2: "walk", 3: "brick"}
 
 PATH_NAMES = {1: "2d_plane", 2: "2d_general", 3: "3d_sep", 4: "3d_general"}
 
@@ -130,6 +131,7 @@ class PlanClasses(ctypes.Structure):
         ("rows_unit", c_int32),
         ("rows_consecutive", c_int32),
         ("fwd_cold", c_int32),
+        ("brick_views", c_int32 * 6),
     ]
 
 

@@ -14,6 +14,7 @@
 #include "xct_general.cuh"
 #include "xct_plane.cuh"
 #include "xct_plane2.cuh"
+#include "xct_brick.cuh"
 #include "xct_tv.cuh"
 #include "xct_solver.cuh"
 
@@ -48,6 +49,9 @@ constexpr int kFwd2S = 1, kFwd2TN = 16;
 constexpr int kWAdjS = 8, kWAdjTA = 8, kWAdjWin = 64, kWAdjStages = 4;
 constexpr int kWFwdS = 4, kWFwdTN = 8;     // walk forward tile: 64 (major) x 8 (minor) x 4 slices
 constexpr int kW2dTN = 8, kW2dWin = 160;  // 2D joint forward tile: 128 (major) x 8 (minor), one image
+// brick kernels (xct_brick.cuh): general 3D matrices
+constexpr int kBrAdjWR = 20, kBrAdjWC = 24, kBrAdjStages = 4;  // adjoint window of an 8^3 brick (columns start at a multiple of 4), ring depth
+constexpr int kBrFwdWR = 24, kBrFwdWC = 24;                    // forward window of an 8 x 16 x 4 brick
 
 }  // namespace
 
@@ -89,6 +93,11 @@ struct xct_plan {
   int* d_listR[4] = {nullptr, nullptr, nullptr, nullptr};
   int n_listR[4] = {0, 0, 0, 0};
   long long* d_rowoff = nullptr;  // [V][n0] element offset of the (local) sinogram row, or -1
+  // brick kernels (general 3D matrices): adjoint over all views; forward view lists by
+  // [2 * depth_axis + needs_atomics]
+  bool brick_adj = false, brick_adj_tma = false, brick_fwd = false;
+  int* d_listB[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_listB[6] = {0, 0, 0, 0, 0, 0};
   int n_list[2] = {0, 0};
   // host-buffer staging (xct_*_host)
   float* stage_in = nullptr;
@@ -546,6 +555,150 @@ int launch_walk_forward3(const xct_plan* pl, const float* in, float* out, cudaSt
   return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, false, false>(pl, 1, in, out, st, s_begin, s_count);
 }
 
+size_t in_elems(const xct_plan* pl) { return (size_t)pl->n0 * pl->n1 * pl->n2; }
+size_t out_elems(const xct_plan* pl) { return (size_t)pl->V * pl->d0 * pl->d1; }
+
+// ------------------------------------------------------------------ brick kernels (general 3D)
+// Host analysis of one plan: window extents of every view, and per view the depth axis of the forward
+// lattice and whether the 2-voxel lane lattice keeps the lanes of one instruction on distinct bins.
+struct BrickAnalysis {
+  bool adj_ok = true, fwd_ok = true;
+  std::vector<int> list[6];  // [2 * depth + needs_atomics]
+};
+BrickAnalysis analyse_bricks(const float* mats, int V, int n0, int n1, int n2, int slice_offset) {
+  BrickAnalysis out;
+  using BG = xct::BrickFwdGeom;
+  const float idx_max = (float)std::max(std::max(n0 + std::abs(slice_offset), n1), n2) + 1.f;
+  for (int v = 0; v < V; ++v) {
+    const float* M = mats + 8 * (size_t)v;
+    // coordinate magnitude -> rounding slack (each coordinate is one product + four sums: <= 4 ulp)
+    float umax = 0.f;
+    for (int r = 0; r < 2; ++r)
+      umax = std::max(umax, (std::fabs(M[4 * r]) + std::fabs(M[4 * r + 1]) + std::fabs(M[4 * r + 2])) * idx_max + std::fabs(M[4 * r + 3]) + 2.f);
+    if (!(umax < 4.0e6f)) { out.adj_ok = out.fwd_ok = false; continue; }  // int / fp32 index headroom
+    const float slack = 16.f * std::ldexp(1.f, std::ilogb(umax) - 23) + 0.01f;
+    // adjoint: 8^3 brick
+    for (int r = 0; r < 2; ++r) {
+      const float e = (std::fabs(M[4 * r]) + std::fabs(M[4 * r + 1]) + std::fabs(M[4 * r + 2])) * (float)(xct::kBrick - 1);
+      if (!(e + slack < (float)(r == 0 ? kBrAdjWR - 2 : kBrAdjWC - 5))) out.adj_ok = false;  // columns: 4-aligned start
+    }
+    // forward: depth axis = smallest projected length first; the lane lattice must separate all lane pairs
+    float len[3];
+    for (int q = 0; q < 3; ++q) len[q] = std::hypot(M[q], M[4 + q]);
+    int order[3] = {0, 1, 2};
+    std::sort(order, order + 3, [&](int a, int b) { return len[a] < len[b]; });
+    int pick = -1, pick_atomic = -1;
+    for (int t = 0; t < 3 && pick < 0; ++t) {
+      const int depth = order[t];
+      const int ax_a = depth == 0 ? 1 : 0, ax_b = depth == 2 ? 1 : 2;
+      const float er = std::fabs(M[ax_a]) * (BG::EA - 1) + std::fabs(M[ax_b]) * (BG::EB - 1) + std::fabs(M[depth]) * (BG::EC - 1);
+      const float ec = std::fabs(M[4 + ax_a]) * (BG::EA - 1) + std::fabs(M[4 + ax_b]) * (BG::EB - 1) + std::fabs(M[4 + depth]) * (BG::EC - 1);
+      if (!(er + slack < (float)(kBrFwdWR - 2)) || !(ec + slack + 3.f < (float)(kBrFwdWC - 2))) continue;  // +3: 4-bin aligned start
+      if (pick_atomic < 0) pick_atomic = depth;
+      bool distinct = true;
+      for (int na = -(BG::LA - 1); na < BG::LA && distinct; ++na)
+        for (int nb = -(BG::LB - 1); nb < BG::LB; ++nb) {
+          if (na == 0 && nb == 0) continue;
+          const float d0 = 2.f * (na * M[ax_a] + nb * M[ax_b]), d1 = 2.f * (na * M[4 + ax_a] + nb * M[4 + ax_b]);
+          if (!(std::max(std::fabs(d0), std::fabs(d1)) >= 1.f + slack)) { distinct = false; break; }
+        }
+      if (distinct) pick = depth;
+    }
+    if (pick >= 0) out.list[2 * pick].push_back(v);
+    else if (pick_atomic >= 0) out.list[2 * pick_atomic + 1].push_back(v);
+    else out.fwd_ok = false;
+  }
+  return out;
+}
+
+xct::BrickParams brick_params(const xct_plan* pl) {
+  xct::BrickParams b{};
+  b.mats = pl->d_mats;
+  b.view_list = nullptr;
+  b.n_list = pl->V;
+  b.V = pl->V;
+  b.N0 = pl->n0; b.N1 = pl->n1; b.N2 = pl->n2; b.D0 = pl->d0; b.D1 = pl->d1;
+  b.slice_offset = pl->slice_offset; b.row_off = pl->row_off;
+  b.views_per_chunk = pl->V;
+  return b;
+}
+
+int view_chunks(long long tasks, int n_views, int min_views, int& views_per_chunk) {
+  const long long target_warps = 148LL * 32;
+  int chunks = 1;
+  if (tasks < target_warps) chunks = (int)std::min<long long>((target_warps + tasks - 1) / tasks, std::max(1, n_views / min_views));
+  views_per_chunk = ceil_div(n_views, chunks);
+  return ceil_div(n_views, views_per_chunk);
+}
+
+int launch_brick_adjoint(const xct_plan* pl, const float* in, float* out, cudaStream_t st, const xct::OutRoute* route = nullptr) {
+  xct::BrickParams b = brick_params(pl);
+  b.nb0 = ceil_div(pl->n0, xct::kBrick); b.nb1 = ceil_div(pl->n1, xct::kBrick); b.nb2 = ceil_div(pl->n2, xct::kBrick);
+  const long long tasks = (long long)b.nb0 * b.nb1 * b.nb2;
+  int chunks = view_chunks(tasks, b.n_list, 8, b.views_per_chunk);
+  if (route && route->store) { chunks = 1; b.views_per_chunk = b.n_list; }  // plain stores: each element exactly once
+  const int blocks = ceil_div(tasks, kWarps);
+  constexpr int stage_floats = ((kBrAdjWR * kBrAdjWC + 31) / 32) * 32;
+  const size_t smem = (size_t)kWarps * kBrAdjStages * stage_floats * sizeof(float) + (size_t)kWarps * kBrAdjStages * sizeof(unsigned long long);
+  if (!route && chunks > 1) XCT_CUDA(cudaMemsetAsync(out, 0, in_elems(pl) * sizeof(float), st));
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  bool tma = pl->brick_adj_tma && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  if (tma) {
+    const cuuint64_t dims[3] = {(cuuint64_t)pl->d1, (cuuint64_t)pl->d0, (cuuint64_t)pl->V};
+    const cuuint64_t strides[2] = {(cuuint64_t)pl->d1 * sizeof(float), (cuuint64_t)pl->d0 * pl->d1 * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)kBrAdjWC, (cuuint32_t)kBrAdjWR, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), dims, strides, box,
+                                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) tma = false;  // e.g. a stride the tensor map cannot express: cp.async staging
+  }
+  const dim3 grid(blocks, chunks);
+  const xct::OutRoute none{};
+#define XCT_BRICK_ADJ(TMA_, ROUTE_)                                                                                            \
+  do {                                                                                                                         \
+    auto kern = xct::brick_adjoint_kernel<kBrAdjWR, kBrAdjWC, kBrAdjStages, kWarps, TMA_, ROUTE_>;                              \
+    XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                              \
+    kern<<<grid, kWarps * 32, smem, st>>>(b, in, out, tmap, route ? *route : none);                                            \
+  } while (0)
+  if (tma) { if (route) XCT_BRICK_ADJ(true, true); else XCT_BRICK_ADJ(true, false); }
+  else { if (route) XCT_BRICK_ADJ(false, true); else XCT_BRICK_ADJ(false, false); }
+#undef XCT_BRICK_ADJ
+  return launch_ok("brick_adjoint_kernel");
+}
+
+template <int DEPTH, bool ATOMIC>
+int launch_brick_forward_class(const xct_plan* pl, const float* in, float* out, cudaStream_t st) {
+  const int cls = 2 * DEPTH + (ATOMIC ? 1 : 0);
+  if (pl->n_listB[cls] == 0) return XCT_OK;
+  using BG = xct::BrickFwdGeom;
+  xct::BrickParams b = brick_params(pl);
+  b.view_list = pl->d_listB[cls];
+  b.n_list = pl->n_listB[cls];
+  const int dims[3] = {pl->n0, pl->n1, pl->n2};
+  const int ax_a = DEPTH == 0 ? 1 : 0, ax_b = DEPTH == 2 ? 1 : 2;
+  b.nb0 = ceil_div(dims[ax_a], BG::EA); b.nb1 = ceil_div(dims[ax_b], BG::EB); b.nb2 = ceil_div(dims[DEPTH], BG::EC);
+  const long long tasks = (long long)b.nb0 * b.nb1 * b.nb2;
+  const int chunks = view_chunks(tasks, b.n_list, 4, b.views_per_chunk);
+  const dim3 grid(ceil_div(tasks, kWarps), chunks);
+  const size_t smem = (size_t)kWarps * kBrFwdWR * kBrFwdWC * sizeof(float);
+  const bool vec4 = (pl->d1 % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec4) xct::brick_forward_kernel<DEPTH, kBrFwdWR, kBrFwdWC, kWarps, ATOMIC, true><<<grid, kWarps * 32, smem, st>>>(b, in, out);
+  else xct::brick_forward_kernel<DEPTH, kBrFwdWR, kBrFwdWC, kWarps, ATOMIC, false><<<grid, kWarps * 32, smem, st>>>(b, in, out);
+  return launch_ok("brick_forward_kernel");
+}
+
+int launch_brick_forward(const xct_plan* pl, const float* in, float* out, cudaStream_t st) {
+  int rc;
+  if ((rc = launch_brick_forward_class<2, false>(pl, in, out, st))) return rc;
+  if ((rc = launch_brick_forward_class<1, false>(pl, in, out, st))) return rc;
+  if ((rc = launch_brick_forward_class<0, false>(pl, in, out, st))) return rc;
+  if ((rc = launch_brick_forward_class<2, true>(pl, in, out, st))) return rc;
+  if ((rc = launch_brick_forward_class<1, true>(pl, in, out, st))) return rc;
+  return launch_brick_forward_class<0, true>(pl, in, out, st);
+}
+
 xct::Gen3Params gen3_params(const xct_plan* pl) {
   xct::Gen3Params g{};
   g.mats = pl->d_mats;
@@ -560,8 +713,6 @@ xct::Gen2Params gen2_params(const xct_plan* pl, int batch) {
   return g;
 }
 
-size_t in_elems(const xct_plan* pl) { return (size_t)pl->n0 * pl->n1 * pl->n2; }
-size_t out_elems(const xct_plan* pl) { return (size_t)pl->V * pl->d0 * pl->d1; }
 
 int check_call(const xct_plan* pl, const void* a, const void* b, int batch) {
   if (!pl) return fail(XCT_ERR_INVALID, "null plan");
@@ -833,6 +984,20 @@ static int plan3d_create_impl(xct_plan** out, const xct3d_geom* g, bool dry) {
       if (pl->adj_plane && pl->fwd_plane) pl->path = XCT_PATH_3D_SEP;
     }
   }
+  if (pl->path == XCT_PATH_3D_GENERAL && !(g->flags & (XCT_FLAG_FORCE_GENERAL | XCT_FLAG_NO_BRICK)) &&
+      g->det_row_offset >= 0 && g->det_row_offset + g->d0 <= pl->rows_total) {
+    // general matrices: brick kernels wherever every view's brick windows fit (else thread-per-voxel)
+    BrickAnalysis ba = analyse_bricks(g->matrices, V, g->n0, g->n1, g->n2, g->slice_offset);
+    pl->brick_adj = ba.adj_ok;
+    pl->brick_adj_tma = ba.adj_ok && (g->d1 % 4 == 0) && (dry || tensor_map_encoder() != nullptr) && !(g->flags & XCT_FLAG_NO_TMA);
+    pl->brick_fwd = ba.fwd_ok;
+    if (ba.fwd_ok)
+      for (int c = 0; c < 6; ++c) {
+        pl->n_listB[c] = (int)ba.list[c].size();
+        e = dev_upload(pl, pl->d_listB[c], ba.list[c].data(), ba.list[c].size());
+        if (e != cudaSuccess) return cleanup(fail(XCT_ERR_CUDA, std::string("view list upload: ") + cudaGetErrorString(e)));
+      }
+  }
   *out = pl;
   return XCT_OK;
 }
@@ -849,6 +1014,7 @@ static void fill_classes(const xct_plan* pl, xct_plan_classes* c) {
   c->rows_unit = pl->rows_unit ? 1 : 0;
   c->rows_consecutive = pl->rows_krow ? 1 : 0;
   c->fwd_cold = pl->fwd_cold ? 1 : 0;
+  for (int k = 0; k < 6; ++k) c->brick_views[k] = pl->n_listB[k];
 }
 int xct_plan_get_classes(const xct_plan* pl, xct_plan_classes* classes) {
   if (!pl || !classes) return fail(XCT_ERR_INVALID, "null argument");
@@ -890,6 +1056,7 @@ void xct_plan_destroy(xct_plan* pl) {
   for (int c = 0; c < 4; ++c) cudaFree(pl->d_list4[c]);
   for (int c = 0; c < 8; ++c) cudaFree(pl->d_listJ[c]);
   for (int c = 0; c < 4; ++c) cudaFree(pl->d_listR[c]);
+  for (int c = 0; c < 6; ++c) cudaFree(pl->d_listB[c]);
   cudaFree(pl->stage_in);
   cudaFree(pl->stage_out);
   if (pl->hstream) cudaStreamDestroy(pl->hstream);
@@ -907,10 +1074,11 @@ int xct_plan_get_info(const xct_plan* pl, xct_plan_info* info) {
   info->fwd_lane_stride = pl->gs;
   info->row_aligned = pl->row_aligned ? 1 : 0;
   info->device = pl->device;
-  info->adj_kernel = pl->adj_walk ? XCT_KERNEL_WALK : (pl->adj_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL);
-  info->fwd_kernel = (pl->fwd_walk || pl->fwd_joint2d) ? XCT_KERNEL_WALK : (pl->fwd_plane ? XCT_KERNEL_PLANE : XCT_KERNEL_GENERAL);
+  info->adj_kernel = pl->adj_walk ? XCT_KERNEL_WALK : (pl->adj_plane ? XCT_KERNEL_PLANE : (pl->brick_adj ? XCT_KERNEL_BRICK : XCT_KERNEL_GENERAL));
+  info->fwd_kernel = (pl->fwd_walk || pl->fwd_joint2d) ? XCT_KERNEL_WALK
+                     : (pl->fwd_plane ? XCT_KERNEL_PLANE : (pl->brick_fwd ? XCT_KERNEL_BRICK : XCT_KERNEL_GENERAL));
   info->fwd_joint = (pl->fwd_joint || pl->fwd_joint2d) ? 1 : 0;
-  info->adj_tma = pl->adj_tma ? 1 : 0;
+  info->adj_tma = (pl->adj_tma || pl->brick_adj_tma) ? 1 : 0;
   info->in_elems = (int64_t)in_elems(pl);
   info->out_elems = (int64_t)out_elems(pl);
   info->updates = info->in_elems * pl->V;
@@ -928,6 +1096,7 @@ int xct_forward(const xct_plan* pl, const float* in, float* out, int32_t batch, 
   if (pl->ndim == 3) {
     if (pl->fwd_walk) return launch_walk_forward3(pl, in, out, st);
     if (pl->fwd_plane) return launch_plane_forward<xct::Geom3, true, kFwd3S, kFwd3TN>(pl, 1, in, out, st);
+    if (pl->brick_fwd) return launch_brick_forward(pl, in, out, st);
     xct::gen3d_forward_kernel<<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, out);
     return launch_ok("gen3d_forward_kernel");
   }
@@ -946,6 +1115,7 @@ int xct_adjoint(const xct_plan* pl, const float* in, float* out, int32_t batch, 
   if (pl->ndim == 3) {
     if (pl->adj_walk && (reinterpret_cast<uintptr_t>(in) & 15) == 0) return launch_walk_adjoint(pl, in, out, st);
     if (pl->adj_plane) return launch_plane_adjoint<xct::Geom3, true, kAdj3S, kAdj3TA>(pl, 1, in, out, st);
+    if (pl->brick_adj) return launch_brick_adjoint(pl, in, out, st);
     xct::gen3d_adjoint_kernel<false><<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, out, xct::OutRoute{});
     return launch_ok("gen3d_adjoint_kernel");
   }
@@ -982,6 +1152,7 @@ int xct_adjoint_scatter(const xct_plan* pl, const float* in, const xct_out_route
   cudaStream_t st = (cudaStream_t)stream;
   if (pl->ndim == 3) {
     if (pl->adj_plane) return launch_plane_adjoint<xct::Geom3, true, kAdj3S, kAdj3TA>(pl, 1, in, nullptr, st, &route);
+    if (pl->brick_adj) return launch_brick_adjoint(pl, in, nullptr, st, &route);
     xct::gen3d_adjoint_kernel<true><<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, nullptr, route);
     return launch_ok("gen3d_adjoint_kernel<route>");
   }

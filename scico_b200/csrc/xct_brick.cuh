@@ -9,7 +9,8 @@
 //   adjoint : the warp's 8 x 8 x 8 voxels are register accumulators (16 per lane) for ALL views, in order.
 //             Per view ONE TMA box (cp.async.bulk.tensor.3d, WR x WC bins of the (V, D0, D1) sinogram, issued
 //             by one elected lane, completing on a per-(warp, stage) mbarrier, hardware zero fill outside the
-//             detector = the reference's zero weights for out-of-range taps) lands in a STAGES-deep ring; the
+//             detector = the reference's zero weights for out-of-range taps; first column a multiple of 4: the
+//             innermost TMA coordinate must be 16-byte aligned) lands in a STAGES-deep ring; the
 //             four taps of a voxel are four LDS off one address register.  No global gather, no bounds test.
 //   forward : the warp's 512 voxels are register-stationary for every view of the launch; lanes sit on a
 //             2-voxel lattice across the two volume axes that are most perpendicular to the rays, so that the
@@ -148,7 +149,9 @@ brick_adjoint_kernel(BrickParams p, const float* __restrict__ sino, float* __res
   auto fetch = [&](int v, int stage, int& rb, int& cb) {
     const Mat24 m = load_mat(p.mats, v);
     rb = brick_origin(m.r0, xi_lo, xi_hi, xj_lo, xj_hi, xk_lo, xk_hi);
-    cb = brick_origin(m.r1, xi_lo, xi_hi, xj_lo, xj_hi, xk_lo, xk_hi);
+    // the innermost TMA coordinate must address a 16-byte aligned element (measured: tools/tma_probe.cu, a box
+    // starting at column 5 raises "illegal instruction"): the window starts at a multiple of 4 columns
+    cb = brick_origin(m.r1, xi_lo, xi_hi, xj_lo, xj_hi, xk_lo, xk_hi) & ~3;
     if (TMA) {
       if (elect_one()) {
         const unsigned bar = bars_sa + 8u * stage;

@@ -76,6 +76,39 @@ CASES_3D.update({
 })
 
 
+# general matrices (both detector coordinates depend on all three voxel indices): the brick kernels
+def _tilt_mats(N, D, V, tilt_deg=74.0, seq="XY", **kw):
+    ang = np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, np.deg2rad(tilt_deg))], 1)
+    return sb.matrices_from_euler_angles(N, D, seq, ang, **kw)
+
+
+def _xyz_mats(N, D, V):
+    rng = np.random.default_rng(5)
+    return sb.matrices_from_euler_angles(N, D, "XYZ", rng.uniform(0, 2 * np.pi, size=(V, 3)))
+
+
+CASES_3D.update({
+    # several bricks per axis, ragged edges, detector rows 16-byte aligned (TMA-staged window, vector flush)
+    "brick_tilt_aligned": ((21, 30, 37), (44, 48), lambda: _tilt_mats((21, 30, 37), (44, 48), 7)),
+    # D1 % 4 != 0: cp.async-staged window, scalar flush
+    "brick_tilt_odd_det": ((19, 22, 26), (33, 35), lambda: _tilt_mats((19, 22, 26), (33, 35), 6)),
+    # random orientations: all three depth classes of the forward, rays along the volume diagonal included
+    "brick_random_orientations": ((24, 20, 28), (40, 44), lambda: _xyz_mats((24, 20, 28), (40, 44), 24)),
+    # detector smaller than the projected volume: zero fill outside the detector
+    "brick_small_det": ((26, 26, 26), (16, 20), lambda: _tilt_mats((26, 26, 26), (16, 20), 5, tilt_deg=30.0)),
+    # fine voxels (spacing 0.45): neighbouring lattice lanes share bins -> the forward's atomic variant
+    "brick_fine_voxels": ((20, 20, 20), (16, 16), lambda: _tilt_mats((20, 20, 20), (16, 16), 6, voxel_spacing=[0.45, 0.45, 0.45])),
+    # coarse voxels (spacing 2.6): the brick window does not fit -> thread-per-voxel kernels
+    "brick_coarse_voxels_fallback": ((9, 10, 11), (40, 44), lambda: _tilt_mats((9, 10, 11), (40, 44), 4, voxel_spacing=[2.6, 2.6, 2.6])),
+    # one brick, many views (views split over blockIdx.y)
+    "brick_one_brick_many_views": ((8, 8, 8), (16, 16), lambda: _tilt_mats((8, 8, 8), (16, 16), 40)),
+    # exact-integer left edges with a general matrix (the ceil quirk inside bins3)
+    "brick_integer_edges": ((8, 8, 8), (12, 12), lambda: np.array(
+        [[[1, 0, 0.5, 0.0], [0, 1, 0.5, 0.25]], [[0.5, 0.5, 0.5, 0.5], [0.25, -0.25, 1.0, 3.0]],
+         [[0, 1, 1, -0.75], [1, 0, -1, 7.75]]], dtype=np.float64)),
+})
+
+
 def _quirk_mats():
     M = _x_mats((8, 12, 10), (9, 16), 3)
     M[:, :, 3] += 0.25
@@ -262,6 +295,46 @@ def test_2d_joint_forward_matches_plane_kernel_and_oracle(torch_dev):
     assert W.plan_info()["fwd_joint"] == 0
     x = rng.standard_normal((48, 48)).astype(np.float32)
     assert O.rel_l2(_gpu(torch, dev, W, x), C.project_2d(x, W.view_table, W.ny)) <= TOL
+
+
+def test_brick_kernels_selected_and_match_thread_per_voxel_kernels(torch_dev):
+    """General matrices run the brick kernels (TMA-staged adjoint window when detector rows are 16-byte aligned);
+    they reproduce the thread-per-voxel family (XCT_FLAG_NO_BRICK) and the oracle, also through a z-slab with
+    slice / detector-row offsets, and the expected forward classes are exercised."""
+    torch, dev = torch_dev
+    rng = np.random.default_rng(12)
+    expect = {"brick_tilt_aligned": (3, 3, 1), "brick_tilt_odd_det": (3, 3, 0), "brick_random_orientations": (3, 3, 1),
+              "brick_fine_voxels": (3, 3, 1), "brick_coarse_voxels_fallback": (0, 0, 0), "xy_tilt": (3, 3, 0)}
+    for name, (fk, ak, tma) in expect.items():
+        N, D, mk = CASES_3D[name]
+        A = sb.XRayTransform3D(N, mk(), D)
+        B = sb.XRayTransform3D(N, mk(), D, _flags=_lib.FLAG_NO_BRICK)
+        ia, ib = A.plan_info(), B.plan_info()
+        assert (ia["fwd_kernel"], ia["adj_kernel"], ia["adj_tma"]) == (fk, ak, tma), (name, ia)
+        assert ib["fwd_kernel"] == 0 and ib["adj_kernel"] == 0 and ia["path_name"] == "3d_general"
+        x = rng.standard_normal(N).astype(np.float32)
+        y = rng.standard_normal(A.output_shape).astype(np.float32)
+        assert O.rel_l2(_gpu(torch, dev, A, x), _gpu(torch, dev, B, x)) <= 1e-6, name
+        assert O.rel_l2(_gpu(torch, dev, A, y, adj=True), _gpu(torch, dev, B, y, adj=True)) <= 1e-6, name
+    # cp.async staging (XCT_FLAG_NO_TMA) equals the TMA staging bit for bit
+    N, D, mk = CASES_3D["brick_tilt_aligned"]
+    A, Cp = sb.XRayTransform3D(N, mk(), D), sb.XRayTransform3D(N, mk(), D, _flags=_lib.FLAG_NO_TMA)
+    assert A.plan_info()["adj_tma"] == 1 and Cp.plan_info()["adj_tma"] == 0 and Cp.plan_info()["adj_kernel"] == 3
+    y = rng.standard_normal(A.output_shape).astype(np.float32)
+    np.testing.assert_array_equal(_gpu(torch, dev, A, y, adj=True), _gpu(torch, dev, Cp, y, adj=True))
+    # z-slab of a tilted volume: slice offset + local detector rows (what the view-block sharding's per-slab plans use)
+    M = mk()
+    full_x = rng.standard_normal(N).astype(np.float32)
+    full_y = rng.standard_normal((len(M),) + D).astype(np.float32)
+    z0, z1, r0, r1 = 5, 16, 8, 40
+    S = sb.XRayTransform3D((z1 - z0,) + N[1:], M, (r1 - r0, D[1]), slice_offset=z0, det_row_offset=r0, det_rows_total=D[0])
+    assert S.plan_info()["adj_kernel"] == 3 and S.plan_info()["fwd_kernel"] == 3
+    want_f = C.project_3d(full_x[z0:z1], S.matrices, D, slice_offset=z0)[:, r0:r1]
+    assert O.rel_l2(_gpu(torch, dev, S, full_x[z0:z1]), want_f) <= TOL
+    ypad = np.zeros_like(full_y)
+    ypad[:, r0:r1] = full_y[:, r0:r1]
+    want_a = C.back_project_3d(ypad, S.matrices, N)[z0:z1]
+    assert O.rel_l2(_gpu(torch, dev, S, np.ascontiguousarray(full_y[:, r0:r1]), adj=True), want_a) <= TOL
 
 
 def test_3d_paths_selected(torch_dev):

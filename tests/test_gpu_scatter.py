@@ -2,7 +2,7 @@
 its owner (view-block sharding fused with its exchange step).
 
 On ONE GPU the row blocks are separate local buffers: this checks the routing of every routed kernel
-(2D plane / 2D general / 3D plane / 3D general) against the plain back projection and the oracle, the
+(2D plane / 2D general / 3D plane / 3D brick / 3D thread-per-voxel) against the plain back projection and the oracle, the
 error behaviour of the entry point, and the PeerBlocks protocol (double-buffered blocks, copy-out,
 re-zeroing) with world size 1.  The cross-GPU part (CUDA IPC over NVLink) is tests/test_gpu_multi.py.
 """
@@ -47,8 +47,12 @@ CASES = {
     "3d_plane": (lambda: sb.XRayTransform3D((17, 18, 19), _x_mats((17, 18, 19), (20, 21), 5), (20, 21)), 1, [0, 8, 17]),
     "3d_sep_walk_plan": (lambda: sb.XRayTransform3D((24, 96, 80), _x_mats((24, 96, 80), (24, 128), 12), (24, 128)), 2,
                          [0, 6, 12, 18, 24]),
-    "3d_general": (lambda: sb.XRayTransform3D((17, 18, 19), _tilt_mats((17, 18, 19), (20, 21), 5), (20, 21)), 0,
-                   [0, 5, 11, 17]),
+    "3d_general": (lambda: sb.XRayTransform3D((17, 18, 19), _tilt_mats((17, 18, 19), (20, 21), 5), (20, 21)), 3,
+                   [0, 5, 11, 17]),  # brick adjoint, cp.async-staged window (odd detector width)
+    "3d_general_tma": (lambda: sb.XRayTransform3D((21, 30, 37), _tilt_mats((21, 30, 37), (44, 48), 7), (44, 48)), 3,
+                       [0, 3, 9, 9, 16, 21]),  # brick adjoint, TMA-staged window; blocks cut bricks, one block empty
+    "3d_general_thread_per_voxel": (lambda: sb.XRayTransform3D((17, 18, 19), _tilt_mats((17, 18, 19), (20, 21), 5), (20, 21),
+                                                                _flags=_lib.FLAG_NO_BRICK), 0, [0, 5, 11, 17]),
 }
 
 

@@ -309,8 +309,8 @@ def test_c1_tv_admm_reference_defaults_every_iteration_matches_oracle(cuda_devic
     from identical state: 6e-9 after 1, 6e-8 after 5, 5e-6 after 15, 4e-4 after 25 iterations).
 
     What CAN be pinned, and is: every one of the 25 ADMM iterations, started from the GPU solver's own state,
-    equals the oracle's iteration from that state with the same CG depth (tolerance: 4x the oracle's own
-    sensitivity to fp32-vs-fp64 inner products at that state and depth, at least 1e-4); the <r, r> sequence the stop test reads agrees with the oracle's; the stop test is
+    equals the oracle's iteration from that state with the same CG depth (tolerance: 8x the oracle's own
+    sensitivity to rounding-level changes of its arithmetic at that state and depth, at least 1e-4); the <r, r> sequence the stop test reads agrees with the oracle's; the stop test is
     the reference's fp32 expression; and the reconstruction quality equals a free-running oracle's."""
     import torch
 
@@ -345,12 +345,14 @@ def test_c1_tv_admm_reference_defaults_every_iteration_matches_oracle(cuda_devic
         # <r, r> before each CG iteration: same sequence while the depth keeps fp32 amplification small
         for j in range(min(k, 12) + 1):
             worst["trace"] = max(worst["trace"], abs(info["trace"][j] / tr_g[j] - 1.0))
-        # tolerance: the oracle's own sensitivity to the accumulation precision of CG's inner products (fp32
-        # as in the reference vs fp64 as on the device) from the same state at the same depth, times 4, and
-        # never below the 1e-4 of the fixed-depth tests: fp32 CG amplifies rounding by ~2.5x per iteration
-        x64 = _cg_fp64_sums(lambda v: (f32(rho) * T.finite_difference_adj(T.finite_difference(v)) + ATo(Ao(v))).astype(f32),
+        # tolerance: the oracle's own sensitivity, from the same state at the same depth, to two rounding-level
+        # changes the device also makes -- CG's inner products accumulated in fp64 instead of fp32, and the
+        # forward projection's sums taken in another order (the C port's `fused` scatter) -- times 8, and never
+        # below the 1e-4 of the fixed-depth tests: fp32 CG amplifies rounding by ~1.5 - 2.5x per iteration
+        Af = lambda v: C.project_2d(v, Tb, A.ny, fused=True)  # noqa: E731
+        x64 = _cg_fp64_sums(lambda v: (f32(rho) * T.finite_difference_adj(T.finite_difference(v)) + ATo(Af(v))).astype(f32),
                             rhs, xs, k)
-        tol_x = max(1e-4, 4.0 * O.rel_l2(x64, xo))
+        tol_x = max(1e-4, 8.0 * O.rel_l2(x64, xo))
         ex = O.rel_l2(S.x.cpu().numpy(), xo)
         worst["x"] = max(worst["x"], ex / tol_x)
         assert ex <= tol_x, (it, k, ex, tol_x)

@@ -44,7 +44,7 @@ def test_slab_geometry_keeps_consecutive_rows():
 
 
 @pytest.mark.parametrize("case,expect", [
-    ("tilt", dict(path_name="3d_general", fwd_kernel=0, adj_kernel=0, fwd_joint=0, adj_tma=0)),
+    ("tilt", dict(path_name="3d_general", fwd_kernel=3, adj_kernel=3, fwd_joint=0, adj_tma=1)),  # brick kernels
     ("odd_columns", dict(path_name="3d_sep", fwd_kernel=2, adj_kernel=1, fwd_joint=0, adj_tma=0)),
     ("wide_voxels", dict(path_name="3d_sep", fwd_cold=1, fwd_joint=0)),
     ("row_mixing", dict(path_name="3d_sep", rows_unit=0, fwd_kernel=2, fwd_joint=1, adj_kernel=1, adj_tma=0)),
@@ -90,3 +90,44 @@ def test_2d_plans():
     assert w["fwd_joint"] == 0 and w["fwd_kernel"] == 1
     g = sb.XRayTransform2D((48, 48), np.linspace(0, PI, 8, endpoint=False), _flags=_lib.FLAG_FORCE_GENERAL).analyse()
     assert g["path_name"] == "2d_general"
+
+
+def _tilt(N, D, V, tilt_deg=74.0, **kw):
+    ang = np.stack([np.linspace(0, PI, V, endpoint=False), np.full(V, np.deg2rad(tilt_deg))], 1)
+    return sb.matrices_from_euler_angles(N, D, "XY", ang, **kw)
+
+
+def test_general_matrices_take_the_brick_kernels():
+    """The tilted geometry of examples/scripts/ct_projector_comparison_3d.py:44-51 (and of bench.py's view-block
+    section): brick kernels in both directions, TMA-staged window, every view in a race-free lattice class."""
+    n, V = 256, 64
+    D = (n + 64, n + 64)
+    a = sb.XRayTransform3D((n,) * 3, _tilt((n,) * 3, D, V), D).analyse()
+    assert a["path_name"] == "3d_general" and a["fwd_kernel"] == 3 and a["adj_kernel"] == 3 and a["adj_tma"] == 1
+    assert sum(a["brick_views"]) == V
+    assert sum(a["brick_views"][1::2]) == 0  # no view needs shared-memory atomics
+    # an odd detector width cannot be described by a tensor map (row pitch not a multiple of 16 bytes): cp.async staging
+    b = sb.XRayTransform3D((40,) * 3, _tilt((40,) * 3, (60, 61), 8), (60, 61)).analyse()
+    assert b["adj_kernel"] == 3 and b["adj_tma"] == 0
+    # XCT_FLAG_NO_BRICK / XCT_FLAG_FORCE_GENERAL keep the thread-per-voxel family
+    for flag in (_lib.FLAG_NO_BRICK, _lib.FLAG_FORCE_GENERAL):
+        c = sb.XRayTransform3D((40,) * 3, _tilt((40,) * 3, (60, 64), 8), (60, 64), _flags=flag).analyse()
+        assert c["fwd_kernel"] == 0 and c["adj_kernel"] == 0 and sum(c["brick_views"]) == 0
+
+
+def test_brick_forward_classes_and_fallbacks():
+    N, D = (32, 32, 32), (48, 48)
+    # fine voxels: lattice lanes 2 voxels apart land less than one bin apart -> atomic classes only
+    fine = sb.XRayTransform3D(N, _tilt(N, D, 6, voxel_spacing=[0.45] * 3), D).analyse()
+    assert fine["fwd_kernel"] == 3 and sum(fine["brick_views"][0::2]) == 0 and sum(fine["brick_views"]) == 6
+    # coarse voxels: the projected brick does not fit the shared-memory window -> thread-per-voxel kernels
+    coarse = sb.XRayTransform3D(N, _tilt(N, D, 6, voxel_spacing=[2.6] * 3), D).analyse()
+    assert coarse["fwd_kernel"] == 0 and coarse["adj_kernel"] == 0
+    # random orientations: more than one depth class
+    rng = np.random.default_rng(5)
+    M = sb.matrices_from_euler_angles(N, D, "XYZ", rng.uniform(0, 2 * PI, size=(48, 3)))
+    r = sb.XRayTransform3D(N, M, D).analyse()
+    assert sum(r["brick_views"]) == 48 and sum(1 for k in (0, 2, 4) if r["brick_views"][k] + r["brick_views"][k + 1]) >= 2
+    # a separable geometry never reaches the brick analysis
+    sep = sb.XRayTransform3D(N, _x(N, D, 8), D).analyse()
+    assert sep["path_name"] == "3d_sep" and sum(sep["brick_views"]) == 0
