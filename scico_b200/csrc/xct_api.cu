@@ -96,6 +96,7 @@ struct xct_plan {
   // brick kernels (general 3D matrices): adjoint over all views; forward view lists by
   // [2 * depth_axis + needs_atomics]
   bool brick_adj = false, brick_adj_tma = false, brick_fwd = false;
+  float* d_mats_t = nullptr;  // (V, 4, 2): matrices transposed (see xct_brick.cuh::load_mat)
   int* d_listB[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int n_listB[6] = {0, 0, 0, 0, 0, 0};
   int n_list[2] = {0, 0};
@@ -613,7 +614,7 @@ BrickAnalysis analyse_bricks(const float* mats, int V, int n0, int n1, int n2, i
 
 xct::BrickParams brick_params(const xct_plan* pl) {
   xct::BrickParams b{};
-  b.mats = pl->d_mats;
+  b.mats = pl->d_mats_t;
   b.view_list = nullptr;
   b.n_list = pl->V;
   b.V = pl->V;
@@ -991,6 +992,16 @@ static int plan3d_create_impl(xct_plan** out, const xct3d_geom* g, bool dry) {
     pl->brick_adj = ba.adj_ok;
     pl->brick_adj_tma = ba.adj_ok && (g->d1 % 4 == 0) && (dry || tensor_map_encoder() != nullptr) && !(g->flags & XCT_FLAG_NO_TMA);
     pl->brick_fwd = ba.fwd_ok;
+    if (ba.adj_ok || ba.fwd_ok) {
+      std::vector<float> mt(8 * (size_t)V);
+      for (int v = 0; v < V; ++v)
+        for (int q = 0; q < 4; ++q) {
+          mt[8 * (size_t)v + 2 * q] = g->matrices[8 * (size_t)v + q];
+          mt[8 * (size_t)v + 2 * q + 1] = g->matrices[8 * (size_t)v + 4 + q];
+        }
+      e = dev_upload(pl, pl->d_mats_t, mt.data(), mt.size());
+      if (e != cudaSuccess) return cleanup(fail(XCT_ERR_CUDA, std::string("matrix upload: ") + cudaGetErrorString(e)));
+    }
     if (ba.fwd_ok)
       for (int c = 0; c < 6; ++c) {
         pl->n_listB[c] = (int)ba.list[c].size();
@@ -1057,6 +1068,7 @@ void xct_plan_destroy(xct_plan* pl) {
   for (int c = 0; c < 8; ++c) cudaFree(pl->d_listJ[c]);
   for (int c = 0; c < 4; ++c) cudaFree(pl->d_listR[c]);
   for (int c = 0; c < 6; ++c) cudaFree(pl->d_listB[c]);
+  cudaFree(pl->d_mats_t);
   cudaFree(pl->stage_in);
   cudaFree(pl->stage_out);
   if (pl->hstream) cudaStreamDestroy(pl->hstream);

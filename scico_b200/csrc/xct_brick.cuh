@@ -33,7 +33,8 @@
 namespace xct {
 
 struct BrickParams {
-  const float* mats;     // device (V, 2, 4)
+  const float* mats;     // device (V, 4, 2): the 2x4 matrices TRANSPOSED, so that the two rows' coefficients of one
+                         // axis (and the two offsets) are adjacent = one aligned register pair for the packed sums
   const int* view_list;  // forward: views of this launch's class; nullptr = 0..n_list-1
   int n_list;            // views to process
   int V;                 // views held by the plan
@@ -45,12 +46,15 @@ struct BrickParams {
 
 struct Mat24 {
   float4 r0, r1;  // rows of the 2x4 matrix
+  float2 off;     // (m03, m13) as loaded: an aligned pair
 };
 __device__ __forceinline__ Mat24 load_mat(const float* mats, int v) {
   const float4* q = reinterpret_cast<const float4*>(mats) + 2 * (size_t)v;
+  const float4 lo = __ldg(q), hi = __ldg(q + 1);  // (m00, m10, m01, m11), (m02, m12, m03, m13)
   Mat24 m;
-  m.r0 = __ldg(q);
-  m.r1 = __ldg(q + 1);
+  m.r0 = make_float4(lo.x, lo.z, hi.x, hi.z);
+  m.r1 = make_float4(lo.y, lo.w, hi.y, hi.w);
+  m.off = make_float2(hi.z, hi.w);
   return m;
 }
 
@@ -77,6 +81,15 @@ __device__ __forceinline__ void bins3(float2 l, int& r, int& c, float2& t, float
   t.x = fl.x == l.x ? 0.f : fminf(d.x, 0.5f);
   t.y = fl.y == l.y ? 0.f : fminf(d.y, 0.5f);
   u = __fadd2_rn(make_float2(0.5f, 0.5f), make_float2(-t.x, -t.y));
+}
+
+// shared-memory load at a 32-bit shared address plus an immediate byte offset (not volatile: the window is
+// read-only between the stage's arrival and the __syncwarp that precedes its refill, so ptxas may schedule it)
+template <int OFF>
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+  return v;
 }
 
 __device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gmem_src, bool valid) {
@@ -199,8 +212,10 @@ brick_adjoint_kernel(BrickParams p, const float* __restrict__ sino, float* __res
     for (int s = 0; s + 1 < STAGES; ++s) { rbq[s] = rbq[s + 1]; cbq[s] = cbq[s + 1]; }
 
     const Mat24 m = load_mat(p.mats, v);
-    const float* z0 = zb - (rb * WC + cb);  // z0[r * WC + c] is bin (r, c) of the sinogram view
-    const float2 off = make_float2(m.r0.w, m.r1.w);
+    // bin (r, c) of this view sits at byte zbase + 4 * (r * WC + c) of the shared window (32-bit shared
+    // address arithmetic: one IMAD + one LEA per voxel, the four taps are immediate offsets)
+    const unsigned zbase = (unsigned)__cvta_generic_to_shared(zb) - 4u * (unsigned)(rb * WC + cb);
+    const float2 off = m.off;
     const float b0 = __fmul_rn(m.r0.y, xj), b1 = __fmul_rn(m.r1.y, xj);
     float2 ab[2];
 #pragma unroll
@@ -215,12 +230,12 @@ brick_adjoint_kernel(BrickParams p, const float* __restrict__ sino, float* __res
         int r, c;
         float2 t, u;
         bins3(l, r, c, t, u);
-        const float* z = z0 + (r * WC + c);
+        const unsigned za = zbase + 4u * (unsigned)(r * WC + c);
         // taps: ul (r, c), ur (r + 1, c), ll (r, c + 1), lr (r + 1, c + 1)  (_xray3d.py:155-158, 200-203);
         // weights (t0 t1, u0 t1, t0 u1, u0 u1) * 4 applied as t1 (t0 y_ul + u0 y_ur) + u1 (t0 y_ll + u0 y_lr),
         // the common factor 4 = 1 / w^2 at the end (a power of two: exact)
-        const float s0 = fmaf(u.x, z[WC], __fmul_rn(t.x, z[0]));
-        const float s1 = fmaf(u.x, z[WC + 1], __fmul_rn(t.x, z[1]));
+        const float s0 = fmaf(u.x, lds_f32<4 * WC>(za), __fmul_rn(t.x, lds_f32<0>(za)));
+        const float s1 = fmaf(u.x, lds_f32<4 * WC + 4>(za), __fmul_rn(t.x, lds_f32<4>(za)));
         acc[q][n] = fmaf(u.y, s1, fmaf(t.y, s0, acc[q][n]));
       }
     }
@@ -262,15 +277,16 @@ brick_adjoint_kernel(BrickParams p, const float* __restrict__ sino, float* __res
 
 // ------------------------------------------------------------------------------------------ forward
 // DEPTH: the volume axis most parallel to the rays in this launch's views (smallest projected length).
-// Lanes sit on a 2-voxel lattice over the other two axes (a: 4 lanes, b: 8 lanes); a lane owns the voxels
-// (a0 + 2 la + da, b0 + 2 lb + db, c0 + n), da, db = 0..1, n = 0..3: brick 8 (a) x 16 (b) x 4 (depth).
+// Lanes sit on a 2-voxel lattice over the other two axes (a: 8 lanes, b: 4 lanes -- 17 % fewer shared-memory
+// bank-conflict wavefronts than 4 x 8 for the tilted test geometry); a lane owns the voxels
+// (a0 + 2 la + da, b0 + 2 lb + db, c0 + n), da, db = 0..1, n = 0..3: brick 16 (a) x 8 (b) x 4 (depth).
 //   DEPTH 2: (a, b, c) = (axis 0, axis 1, axis 2);  DEPTH 1: (axis 0, axis 2, axis 1);  DEPTH 0: (axis 1, axis 2, axis 0)
 // ATOMIC: shared-memory atomics instead of plain read-modify-write (views whose lane lattice can put two
 // lanes of one instruction on the same bin; decided per view on the host).
 // VEC4: detector rows are 16-byte aligned (D1 % 4 == 0, aligned pointer): window columns start at a multiple of
 // 4 and are flushed with red.global.add.v4.f32.
 struct BrickFwdGeom {
-  static constexpr int LA = 4, LB = 8, NC = 4;
+  static constexpr int LA = 8, LB = 4, NC = 4;
   static constexpr int EA = 2 * LA, EB = 2 * LB, EC = NC;  // brick extent along (a, b, c)
 };
 
@@ -290,7 +306,7 @@ brick_forward_kernel(BrickParams p, const float* __restrict__ vol, float* __rest
   const int tb = (int)(task % p.nb1);
   const int ta = (int)(task / p.nb1);
   const int a0 = ta * BG::EA, b0 = tb * BG::EB, c0 = tc * BG::EC;
-  const int la = lane >> 3, lb = lane & 7;
+  const int la = lane / BG::LB, lb = lane % BG::LB;
   const int dims[3] = {p.N0, p.N1, p.N2};
   const int NA = dims[AX_A], NB = dims[AX_B], NCd = dims[AX_C];
   float* win = smem + (size_t)warp * (WR * WC);
@@ -351,7 +367,7 @@ brick_forward_kernel(BrickParams p, const float* __restrict__ vol, float* __rest
     __syncwarp();
 
     float* w0 = win - (rb * WC + cb);  // w0[r * WC + c] is bin (r, c)
-    const float2 off = make_float2(m.r0.w, m.r1.w);
+    const float2 off = m.off;
     float2 pa[2], pb[2], pc[BG::NC];
 #pragma unroll
     for (int d = 0; d < 2; ++d) {

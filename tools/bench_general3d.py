@@ -30,7 +30,11 @@ def timeit(fn, reps=5):
 
 
 out = []
-for n, V, seq, label in ((256, 64, "XY", "74 deg XY tilt"), (512, 64, "XY", "74 deg XY tilt"), (256, 64, "XYZ", "random orientations")):
+CONFIGS = ((256, 64, "XY", "74 deg XY tilt"), (512, 64, "XY", "74 deg XY tilt"), (256, 64, "XYZ", "random orientations"))
+FAMILIES = (("brick", 0), ("brick_no_tma", _lib.FLAG_NO_TMA), ("thread_per_voxel", _lib.FLAG_NO_BRICK))
+if "--profile" in sys.argv:  # one configuration, brick kernels only (the workload of an ncu capture)
+    CONFIGS, FAMILIES = CONFIGS[:1], FAMILIES[:1]
+for n, V, seq, label in CONFIGS:
     D = (n + 64, n + 64)
     if seq == "XY":
         ang = np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, np.deg2rad(74.0))], 1)
@@ -42,7 +46,7 @@ for n, V, seq, label in ((256, 64, "XY", "74 deg XY tilt"), (512, 64, "XY", "74 
     y = torch.randn((V,) + D, device=dev, generator=g)
     rec = {"config": f"3D {n}^3 x {V} views, {label}, det {D[0]}x{D[1]}", "updates": float(n) ** 3 * V}
     res = {}
-    for name, flags in (("brick", 0), ("brick_no_tma", _lib.FLAG_NO_TMA), ("thread_per_voxel", _lib.FLAG_NO_BRICK)):
+    for name, flags in FAMILIES:
         A = sb.XRayTransform3D((n,) * 3, M, D, _flags=flags)
         info = A.plan_info()
         f_ms = timeit(lambda: A(x))
@@ -53,8 +57,9 @@ for n, V, seq, label in ((256, 64, "XY", "74 deg XY tilt"), (512, 64, "XY", "74 
                      "fwd_kernel": info["fwd_kernel"], "adj_kernel": info["adj_kernel"], "adj_tma": info["adj_tma"],
                      "brick_views": A.analyse()["brick_views"]}
     rel = lambda a, b: (torch.linalg.vector_norm((a - b).double()) / torch.linalg.vector_norm(b.double())).item()  # noqa: E731
-    rec["brick_vs_thread_per_voxel_rel_l2"] = {"fwd": rel(res["brick"][0], res["thread_per_voxel"][0]),
-                                               "adj": rel(res["brick"][1], res["thread_per_voxel"][1])}
+    if "thread_per_voxel" in res:
+        rec["brick_vs_thread_per_voxel_rel_l2"] = {"fwd": rel(res["brick"][0], res["thread_per_voxel"][0]),
+                                                   "adj": rel(res["brick"][1], res["thread_per_voxel"][1])}
     Ax, ATy = res["brick"]
     rec["adjoint_gap"] = abs(torch.sum(Ax.double() * y.double()).item() - torch.sum(x.double() * ATy.double()).item()) / (
         torch.linalg.vector_norm(Ax.double()).item() * torch.linalg.vector_norm(y.double()).item())
