@@ -126,6 +126,41 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pin_to_gpu_numa_node(torch, local):
+    """Run this rank (and first-touch its page-locked buffers) on the NUMA node its GPU hangs off: with 8 ranks
+    all on node 0, half of the host<->device traffic crosses the socket interconnect.  sysfs only (no libnuma):
+    /sys/bus/pci/devices/<gpu>/numa_node -> /sys/devices/system/node/nodeK/cpulist, intersected with the CPUs
+    this process may use.  Returns a one-line note for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        if all(hasattr(pr, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:
+            q = subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                               capture_output=True, text=True, timeout=10).stdout.strip()
+            bus = q[-12:].lower() if q else None  # 00000000:1B:00.0 -> 0000:1b:00.0
+        if not bus:
+            return "GPU PCI bus id unavailable: not pinned"
+        path = f"/sys/bus/pci/devices/{bus}/numa_node"
+        if not os.path.exists(path):
+            return f"{path} missing: not pinned"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "GPU reports no NUMA node: not pinned"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return f"GPU on NUMA node {node}, none of its CPUs allowed for this process: not pinned"
+        os.sched_setaffinity(0, use)
+        return f"pinned to NUMA node {node} ({len(use)} of {len(allowed)} allowed CPUs)"
+    except Exception as e:  # sysfs layout / permissions: measurement goes on unpinned
+        return f"not pinned ({type(e).__name__}: {e})"
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -340,6 +375,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    numa_note = pin_to_gpu_numa_node(torch, local)
     if world > 1:
         # NCCL_DEBUG is left as the caller set it (the driver counts ranks from NCCL's own log); whatever NCCL
         # prints are separate lines, the JSON line below is printed once, by rank 0, at the very end
@@ -494,15 +530,34 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            A.project(xh_np, out=so)        # host in -> host out: H2D, kernels, D2H
-            A.back_project(so, out=xo)      # host in -> host out
+            A.project(xh_np, out=so)        # host in -> host out: H2D, kernels, D2H; returns when `so` is complete
+            A.back_project(so, out=xo)      # its input is the forward's host result: the two calls cannot overlap
         barrier()
         dt = reduce_max((time.perf_counter() - t0) / args.steps)
+        # the same two applications on INDEPENDENT host inputs, both in flight (wait=False + host_wait): the
+        # adjoint's H2D runs under the forward's kernels and D2H, all three streams stay busy across the boundary
+        A.project(xh_np, out=so, wait=False)
+        A.back_project(sh_np, out=xo, wait=False)
+        A.host_wait()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            A.project(xh_np, out=so, wait=False)
+            A.back_project(sh_np, out=xo, wait=False)
+            A.host_wait()
+        barrier()
+        dt_ov = reduce_max((time.perf_counter() - t0) / args.steps)
         per_dir = 4 * (x.numel() + y.numel())
         e2e = {"value": updates_step / dt, "unit": UNIT, "h2d_bytes_per_step": int(per_dir * world),
                "d2h_bytes_per_step": int(per_dir * world), "ms_per_step": dt * 1e3,
                "pcie_gb_per_s_per_gpu_per_direction": per_dir / dt / 1e9,
-               "api": "XRayTransform3D.project/.back_project(host array, out=pinned host array) -> xct_forward_host/xct_adjoint_host"}
+               "api": "XRayTransform3D.project/.back_project(host array, out=pinned host array) -> xct_forward_host/xct_adjoint_host; "
+                      "the adjoint's input is the forward's host result",
+               "overlapped": {"value": updates_step / dt_ov, "ms_per_step": dt_ov * 1e3,
+                              "pcie_gb_per_s_per_gpu_per_direction": per_dir / dt_ov / 1e9,
+                              "api": "project(x_host, out=, wait=False); back_project(y_host, out=, wait=False); host_wait() -> "
+                                     "xct_forward_host_async / xct_adjoint_host_async / xct_host_wait (independent inputs)"},
+               "numa": numa_note}
 
     # second half of BASELINE.json's metric: TV-regularised PDHG iterations/s on the same operator
     # (device-resident state, iteration statistics off: no host sync inside an iteration)

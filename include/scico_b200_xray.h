@@ -192,10 +192,19 @@ XCT_API int xct_peer_free(int32_t device, void *ptr);  /* release (xct_peer_allo
 /* Same two operators for HOST buffers: H2D copy, kernel(s), D2H copy, synchronous on return.
  * Device staging buffers are cached inside the plan (these two calls are therefore NOT
  * re-entrant on one plan).  3D separable plans on the walk kernels cut the volume into chunks of
- * slices and overlap the H2D copy of chunk k+1 and the D2H copy of chunk k-1 with the kernels of
- * chunk k (page-locked host buffers are needed for the overlap; pageable ones still work). */
+ * slices (at least 8 chunks, 16 for a slab of 128 slices or more) and overlap the H2D copy of chunk k+1 and
+ * the D2H copy of chunk k-1 with the kernels of chunk k (page-locked host buffers are needed for the overlap;
+ * pageable ones still work). */
 XCT_API int xct_forward_host(xct_plan *plan, const float *in_host, float *out_host, int32_t batch);
 XCT_API int xct_adjoint_host(xct_plan *plan, const float *in_host, float *out_host, int32_t batch);
+/* The same two calls WITHOUT the final wait: they enqueue the copies and kernels on the plan's own streams
+ * and return.  Calls on one plan execute in the order they were made; a forward and an adjoint enqueued back
+ * to back share the copy engines and the SMs across the call boundary (each direction has its own staging
+ * buffers).  The host buffers must be page-locked and stay untouched until xct_host_wait(plan) returns;
+ * out_host is complete after it.  Not re-entrant on one plan (call from one thread at a time). */
+XCT_API int xct_forward_host_async(xct_plan *plan, const float *in_host, float *out_host, int32_t batch);
+XCT_API int xct_adjoint_host_async(xct_plan *plan, const float *in_host, float *out_host, int32_t batch);
+XCT_API int xct_host_wait(xct_plan *plan);
 
 /* Test hooks: dump what the reference's _calc_weights materialises, as computed by the code path
  * the plan resolved to.  DEVICE outputs.

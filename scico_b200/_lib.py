@@ -48,6 +48,9 @@ EXPORTED_SYMBOLS = (
     "xct_adjoint",
     "xct_forward_host",
     "xct_adjoint_host",
+    "xct_forward_host_async",
+    "xct_adjoint_host_async",
+    "xct_host_wait",
     "xct3d_debug_weights",
     "xct2d_debug_weights",
     "xct_adjoint_scatter",
@@ -190,8 +193,9 @@ def lib() -> ctypes.CDLL:
     L.xct3d_plan_analyse.argtypes = [POINTER(Geom3D), POINTER(PlanInfo), POINTER(PlanClasses)]
     for name in ("xct_forward", "xct_adjoint"):
         getattr(L, name).argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
-    for name in ("xct_forward_host", "xct_adjoint_host"):
+    for name in ("xct_forward_host", "xct_adjoint_host", "xct_forward_host_async", "xct_adjoint_host_async"):
         getattr(L, name).argtypes = [c_void_p, c_void_p, c_void_p, c_int32]
+    L.xct_host_wait.argtypes = [c_void_p]
     L.xct_adjoint_scatter.argtypes = [c_void_p, c_void_p, POINTER(OutRoute), c_void_p]
     L.xct_peer_alloc.argtypes = [c_int32, ctypes.c_size_t, POINTER(c_void_p), POINTER(IpcHandle)]
     L.xct_peer_open.argtypes = [c_int32, POINTER(IpcHandle), POINTER(c_void_p)]

@@ -100,10 +100,11 @@ struct xct_plan {
   int* d_listB[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int n_listB[6] = {0, 0, 0, 0, 0, 0};
   int n_list[2] = {0, 0};
-  // host-buffer staging (xct_*_host)
-  float* stage_in = nullptr;
-  float* stage_out = nullptr;
-  size_t cap_in = 0, cap_out = 0;
+  // host-buffer staging (xct_*_host): one (input, output) pair of device buffers per direction, so that a
+  // forward and an adjoint can be in flight together (xct_*_host_async)
+  float* stage_in[2] = {nullptr, nullptr};   // [0]: forward's volume, [1]: adjoint's sinogram
+  float* stage_out[2] = {nullptr, nullptr};  // [0]: forward's sinogram, [1]: adjoint's volume
+  size_t cap_in[2] = {0, 0}, cap_out[2] = {0, 0};
   cudaStream_t hstream = nullptr;
   // pipelined host path (3D separable, unit rows monotone in the slice index): H2D of slice chunk
   // k+1 and D2H of chunk k-1 overlap the kernels of chunk k
@@ -111,6 +112,7 @@ struct xct_plan {
   std::vector<int> h_row_lo, h_row_hi;  // per slice: smallest / largest local detector row over views (-1: none)
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> events;
+  cudaEvent_t done_ev[2] = {nullptr, nullptr};  // last D2H of the previous host call of each direction
 };
 
 namespace {
@@ -724,20 +726,22 @@ int check_call(const xct_plan* pl, const void* a, const void* b, int batch) {
   return XCT_OK;
 }
 
-int ensure_stage(xct_plan* pl, size_t n_in, size_t n_out) {
+int ensure_stage(xct_plan* pl, int dir, size_t n_in, size_t n_out) {
   if (!pl->hstream) XCT_CUDA(cudaStreamCreateWithFlags(&pl->hstream, cudaStreamNonBlocking));
-  if (n_in > pl->cap_in) {
-    if (pl->stage_in) cudaFree(pl->stage_in);
-    pl->stage_in = nullptr; pl->cap_in = 0;
-    XCT_CUDA(cudaMalloc(&pl->stage_in, n_in * sizeof(float)));
-    pl->cap_in = n_in;
-  }
-  if (n_out > pl->cap_out) {
-    if (pl->stage_out) cudaFree(pl->stage_out);
-    pl->stage_out = nullptr; pl->cap_out = 0;
-    XCT_CUDA(cudaMalloc(&pl->stage_out, n_out * sizeof(float)));
-    pl->cap_out = n_out;
-  }
+  if (!pl->s_in) XCT_CUDA(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
+  if (!pl->s_out) XCT_CUDA(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
+  auto grow = [&](float*& buf, size_t& cap, size_t n) -> cudaError_t {
+    if (n <= cap) return cudaSuccess;
+    // a larger batch than before: everything queued on the plan's streams may still use the old buffer
+    cudaStreamSynchronize(pl->s_in); cudaStreamSynchronize(pl->hstream); cudaStreamSynchronize(pl->s_out);
+    if (buf) cudaFree(buf);
+    buf = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&buf, n * sizeof(float));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  };
+  XCT_CUDA(grow(pl->stage_in[dir], pl->cap_in[dir], n_in));
+  XCT_CUDA(grow(pl->stage_out[dir], pl->cap_out[dir], n_out));
   return XCT_OK;
 }
 
@@ -1069,12 +1073,13 @@ void xct_plan_destroy(xct_plan* pl) {
   for (int c = 0; c < 4; ++c) cudaFree(pl->d_listR[c]);
   for (int c = 0; c < 6; ++c) cudaFree(pl->d_listB[c]);
   cudaFree(pl->d_mats_t);
-  cudaFree(pl->stage_in);
-  cudaFree(pl->stage_out);
+  for (int d = 0; d < 2; ++d) { cudaFree(pl->stage_in[d]); cudaFree(pl->stage_out[d]); }
   if (pl->hstream) cudaStreamDestroy(pl->hstream);
   if (pl->s_in) cudaStreamDestroy(pl->s_in);
   if (pl->s_out) cudaStreamDestroy(pl->s_out);
   for (cudaEvent_t ev : pl->events) cudaEventDestroy(ev);
+  for (int d = 0; d < 2; ++d)
+    if (pl->done_ev[d]) cudaEventDestroy(pl->done_ev[d]);
   delete pl;
 }
 
@@ -1239,29 +1244,34 @@ int xct_peer_free(int32_t device, void* ptr) {
   return XCT_OK;
 }
 
-// Pipelined host path for 3D separable plans with unit, monotone rows: the volume is cut into
-// chunks of slices; chunk k's kernels (stream hstream) overlap the H2D copy of chunk k+1 (stream
-// s_in) and the D2H copy of what chunk k-1 completed (stream s_out).  Detector rows of a slice
-// chunk are a row block of every view: strided 2D copies with the view pitch.
-static int run_host_pipelined(xct_plan* pl, const float* in_host, float* out_host, bool forward) {
+// Pipelined host path for 3D separable plans with unit, monotone rows: the volume is cut into >= 8
+// chunks of slices (16 for the headline shapes); chunk k's kernels (stream hstream) overlap the H2D copy of
+// chunk k+1 (stream s_in) and the D2H copy of what chunk k-1 completed (stream s_out).  Detector rows of a
+// slice chunk are a row block of every view: strided 2D copies with the view pitch.  Nothing here waits for
+// the device: the three streams carry the calls of a plan in order, so a forward and an adjoint enqueued back
+// to back (xct_*_host_async) keep all three busy across the call boundary -- the adjoint's first sinogram
+// rows go up while the forward's last chunks compute and its last rows come down.
+static int enqueue_host_pipelined(xct_plan* pl, const float* in_host, float* out_host, bool forward) {
   int rc;
+  const int dir = forward ? 0 : 1;
   const size_t n_vol = in_elems(pl), n_sino = out_elems(pl);
-  if ((rc = ensure_stage(pl, forward ? n_vol : n_sino, forward ? n_sino : n_vol))) return rc;
-  if (!pl->s_in) XCT_CUDA(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
-  if (!pl->s_out) XCT_CUDA(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
+  if ((rc = ensure_stage(pl, dir, forward ? n_vol : n_sino, forward ? n_sino : n_vol))) return rc;
   const int NS = pl->n0, D0 = pl->d0, D1 = pl->d1, V = pl->V;
-  int chunk = std::max(32, (NS + 15) / 16);
+  int chunk = std::max(8, (NS + 15) / 16);
   chunk = (chunk + 7) & ~7;  // whole slice groups of both kernels (S = 4 / 8)
   const int nchunks = ceil_div(NS, chunk);
-  while ((int)pl->events.size() < 2 * nchunks) {
+  const size_t ev_base = dir ? 2 * 64 : 0;  // each direction owns its events
+  while (pl->events.size() < 4 * 64) {
     cudaEvent_t ev;
     XCT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     pl->events.push_back(ev);
   }
+  if (nchunks > 64) return fail(XCT_ERR_INVALID, "host pipeline: more than 64 chunks");
   const size_t slice = (size_t)pl->n1 * pl->n2;
   const size_t vpitch = (size_t)D0 * D1 * sizeof(float);  // bytes between the same row of two views
-  float* vol_dev = forward ? pl->stage_in : pl->stage_out;
-  float* sino_dev = forward ? pl->stage_out : pl->stage_in;
+  float* vol_dev = forward ? pl->stage_in[0] : pl->stage_out[1];
+  float* sino_dev = forward ? pl->stage_out[0] : pl->stage_in[1];
+  auto ev = [&](int k, int which) { return pl->events[ev_base + 2 * k + which]; };
   auto rows_copy = [&](int r0, int r1, bool to_device, cudaStream_t st) -> cudaError_t {
     if (r1 <= r0) return cudaSuccess;
     const size_t off = (size_t)r0 * D1;
@@ -1270,6 +1280,14 @@ static int run_host_pipelined(xct_plan* pl, const float* in_host, float* out_hos
       return cudaMemcpy2DAsync(sino_dev + off, vpitch, in_host + off, vpitch, width, V, cudaMemcpyHostToDevice, st);
     return cudaMemcpy2DAsync(out_host + off, vpitch, sino_dev + off, vpitch, width, V, cudaMemcpyDeviceToHost, st);
   };
+  // the previous call of THIS direction may still be reading / draining these staging buffers: order after its
+  // last D2H (the other direction has its own buffers and is not waited for)
+  if (pl->done_ev[dir]) {
+    XCT_CUDA(cudaStreamWaitEvent(pl->s_in, pl->done_ev[dir], 0));
+    XCT_CUDA(cudaStreamWaitEvent(pl->hstream, pl->done_ev[dir], 0));
+  } else {
+    XCT_CUDA(cudaEventCreateWithFlags(&pl->done_ev[dir], cudaEventDisableTiming));
+  }
   if (forward) {
     XCT_CUDA(cudaMemsetAsync(sino_dev, 0, n_sino * sizeof(float), pl->hstream));
     // first row any slice >= i touches (rows never decrease with the slice index)
@@ -1280,13 +1298,13 @@ static int run_host_pipelined(xct_plan* pl, const float* in_host, float* out_hos
       const int a = k * chunk, b = std::min(NS, a + chunk);
       XCT_CUDA(cudaMemcpyAsync(vol_dev + a * slice, in_host + a * slice, (size_t)(b - a) * slice * sizeof(float),
                                cudaMemcpyHostToDevice, pl->s_in));
-      XCT_CUDA(cudaEventRecord(pl->events[2 * k], pl->s_in));
-      XCT_CUDA(cudaStreamWaitEvent(pl->hstream, pl->events[2 * k], 0));
+      XCT_CUDA(cudaEventRecord(ev(k, 0), pl->s_in));
+      XCT_CUDA(cudaStreamWaitEvent(pl->hstream, ev(k, 0), 0));
       if ((rc = launch_walk_forward3(pl, vol_dev, sino_dev, pl->hstream, a, b - a))) return rc;
-      XCT_CUDA(cudaEventRecord(pl->events[2 * k + 1], pl->hstream));
+      XCT_CUDA(cudaEventRecord(ev(k, 1), pl->hstream));
       const int complete = b == NS ? D0 : std::max(rows_done, first_from[b]);  // rows no later chunk adds to
       if (complete > rows_done) {
-        XCT_CUDA(cudaStreamWaitEvent(pl->s_out, pl->events[2 * k + 1], 0));
+        XCT_CUDA(cudaStreamWaitEvent(pl->s_out, ev(k, 1), 0));
         XCT_CUDA(rows_copy(rows_done, complete, false, pl->s_out));
         rows_done = complete;
       }
@@ -1299,44 +1317,68 @@ static int run_host_pipelined(xct_plan* pl, const float* in_host, float* out_hos
       for (int i = a; i < b; ++i) need = std::max(need, pl->h_row_hi[i] + 1);
       XCT_CUDA(rows_copy(rows_up, need, true, pl->s_in));
       rows_up = need;
-      XCT_CUDA(cudaEventRecord(pl->events[2 * k], pl->s_in));
-      XCT_CUDA(cudaStreamWaitEvent(pl->hstream, pl->events[2 * k], 0));
+      XCT_CUDA(cudaEventRecord(ev(k, 0), pl->s_in));
+      XCT_CUDA(cudaStreamWaitEvent(pl->hstream, ev(k, 0), 0));
       if ((rc = launch_walk_adjoint(pl, sino_dev, vol_dev, pl->hstream, a, b - a))) return rc;
-      XCT_CUDA(cudaEventRecord(pl->events[2 * k + 1], pl->hstream));
-      XCT_CUDA(cudaStreamWaitEvent(pl->s_out, pl->events[2 * k + 1], 0));
+      XCT_CUDA(cudaEventRecord(ev(k, 1), pl->hstream));
+      XCT_CUDA(cudaStreamWaitEvent(pl->s_out, ev(k, 1), 0));
       XCT_CUDA(cudaMemcpyAsync(out_host + a * slice, vol_dev + a * slice, (size_t)(b - a) * slice * sizeof(float),
                                cudaMemcpyDeviceToHost, pl->s_out));
     }
   }
-  XCT_CUDA(cudaStreamSynchronize(pl->s_out));
-  XCT_CUDA(cudaStreamSynchronize(pl->hstream));
-  XCT_CUDA(cudaStreamSynchronize(pl->s_in));
+  XCT_CUDA(cudaEventRecord(pl->done_ev[dir], pl->s_out));
   return XCT_OK;
 }
 
-static int run_host(xct_plan* pl, const float* in_host, float* out_host, int32_t batch, bool forward) {
+// One H2D, the kernels, one D2H, all on hstream (every plan that is not pipelined).  The D2H stream is made to
+// follow, so that xct_host_wait only has to drain the three streams.
+static int enqueue_host_plain(xct_plan* pl, const float* in_host, float* out_host, int32_t batch, bool forward) {
+  int rc;
+  const int dir = forward ? 0 : 1;
+  const size_t n_in = (forward ? in_elems(pl) : out_elems(pl)) * batch;
+  const size_t n_out = (forward ? out_elems(pl) : in_elems(pl)) * batch;
+  if ((rc = ensure_stage(pl, dir, n_in, n_out))) return rc;
+  XCT_CUDA(cudaMemcpyAsync(pl->stage_in[dir], in_host, n_in * sizeof(float), cudaMemcpyHostToDevice, pl->hstream));
+  rc = forward ? xct_forward(pl, pl->stage_in[dir], pl->stage_out[dir], batch, pl->hstream)
+               : xct_adjoint(pl, pl->stage_in[dir], pl->stage_out[dir], batch, pl->hstream);
+  if (rc) return rc;
+  XCT_CUDA(cudaMemcpyAsync(out_host, pl->stage_out[dir], n_out * sizeof(float), cudaMemcpyDeviceToHost, pl->hstream));
+  return XCT_OK;
+}
+
+static int enqueue_host(xct_plan* pl, const float* in_host, float* out_host, int32_t batch, bool forward) {
   int rc = check_call(pl, in_host, out_host, batch);
   if (rc) return rc;
   DeviceGuard guard(pl->device);
   if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
-  if (pl->pipe_ok && pl->n0 >= 64) return run_host_pipelined(pl, in_host, out_host, forward);
-  const size_t n_in = (forward ? in_elems(pl) : out_elems(pl)) * batch;
-  const size_t n_out = (forward ? out_elems(pl) : in_elems(pl)) * batch;
-  if ((rc = ensure_stage(pl, n_in, n_out))) return rc;
-  XCT_CUDA(cudaMemcpyAsync(pl->stage_in, in_host, n_in * sizeof(float), cudaMemcpyHostToDevice, pl->hstream));
-  rc = forward ? xct_forward(pl, pl->stage_in, pl->stage_out, batch, pl->hstream)
-               : xct_adjoint(pl, pl->stage_in, pl->stage_out, batch, pl->hstream);
-  if (rc) return rc;
-  XCT_CUDA(cudaMemcpyAsync(out_host, pl->stage_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, pl->hstream));
-  XCT_CUDA(cudaStreamSynchronize(pl->hstream));
+  if (pl->pipe_ok && pl->n0 >= 64) return enqueue_host_pipelined(pl, in_host, out_host, forward);
+  return enqueue_host_plain(pl, in_host, out_host, batch, forward);
+}
+
+int xct_host_wait(xct_plan* pl) {
+  if (!pl) return fail(XCT_ERR_INVALID, "null plan");
+  if (pl->dry) return fail(XCT_ERR_INVALID, "analysis-only plan");
+  DeviceGuard guard(pl->device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
+  if (pl->s_out) XCT_CUDA(cudaStreamSynchronize(pl->s_out));
+  if (pl->hstream) XCT_CUDA(cudaStreamSynchronize(pl->hstream));
+  if (pl->s_in) XCT_CUDA(cudaStreamSynchronize(pl->s_in));
   return XCT_OK;
 }
 
+int xct_forward_host_async(xct_plan* pl, const float* in_host, float* out_host, int32_t batch) {
+  return enqueue_host(pl, in_host, out_host, batch, true);
+}
+int xct_adjoint_host_async(xct_plan* pl, const float* in_host, float* out_host, int32_t batch) {
+  return enqueue_host(pl, in_host, out_host, batch, false);
+}
 int xct_forward_host(xct_plan* pl, const float* in_host, float* out_host, int32_t batch) {
-  return run_host(pl, in_host, out_host, batch, true);
+  int rc = enqueue_host(pl, in_host, out_host, batch, true);
+  return rc ? rc : xct_host_wait(pl);
 }
 int xct_adjoint_host(xct_plan* pl, const float* in_host, float* out_host, int32_t batch) {
-  return run_host(pl, in_host, out_host, batch, false);
+  int rc = enqueue_host(pl, in_host, out_host, batch, false);
+  return rc ? rc : xct_host_wait(pl);
 }
 
 // ---------------------------------------------------------------- TV / PDHG kernels (xct_tv.cuh)

@@ -87,15 +87,22 @@ class _Plans:
         self.close()
 
 
-def _apply(plans: _Plans, x, out_shape, forward: bool, batch: int, default_device: Optional[int], out=None):
+def _apply(plans: _Plans, x, out_shape, forward: bool, batch: int, default_device: Optional[int], out=None,
+           wait: bool = True):
     """Run one operator application on ``x`` (see module docstring for the array rules).
 
     ``out`` (optional): preallocated float32 C-contiguous result of shape ``out_shape`` -- a CUDA
     tensor for CUDA input, a NumPy array (ideally page-locked, e.g. the ``.numpy()`` view of a
-    ``torch.empty(..., pin_memory=True)``) for host input.  It is overwritten and returned."""
+    ``torch.empty(..., pin_memory=True)``) for host input.  It is overwritten and returned.
+
+    ``wait=False`` (host arrays with ``out=`` only): enqueue and return; ``x`` and ``out`` must be page-locked and
+    stay untouched until the operator's ``host_wait()`` returns (``xct_*_host_async`` / ``xct_host_wait``)."""
     L = _lib.lib()
     fn_dev = L.xct_forward if forward else L.xct_adjoint
-    fn_host = L.xct_forward_host if forward else L.xct_adjoint_host
+    if wait:
+        fn_host = L.xct_forward_host if forward else L.xct_adjoint_host
+    else:
+        fn_host = L.xct_forward_host_async if forward else L.xct_adjoint_host_async
     if torch is not None and isinstance(x, torch.Tensor) and x.is_cuda:
         dev = x.device.index
         xin = x.detach()
@@ -115,6 +122,8 @@ def _apply(plans: _Plans, x, out_shape, forward: bool, batch: int, default_devic
         return out
     was_torch = torch is not None and isinstance(x, torch.Tensor)
     xin = np.ascontiguousarray(x.numpy() if was_torch else np.asarray(x), dtype=np.float32)
+    if not wait and (out is None or xin is not (x.numpy() if was_torch else x)):
+        raise ValueError("wait=False needs a float32 C-contiguous host input used as is and an explicit out= buffer")
     if out is None:
         out = np.empty(out_shape, dtype=np.float32)
     elif not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == tuple(out_shape)
@@ -152,13 +161,21 @@ if torch is not None:
             return gx, None, None, None, None, None
 
 
-def _apply_ad(plans: _Plans, x, out_shape, forward: bool, batch: int, default_device: Optional[int], out=None):
+def _apply_ad(plans: _Plans, x, out_shape, forward: bool, batch: int, default_device: Optional[int], out=None,
+              wait: bool = True):
     """:func:`_apply`, recorded on the autograd tape when ``x`` is a tensor that requires grad."""
     if torch is not None and isinstance(x, torch.Tensor) and x.requires_grad and torch.is_grad_enabled():
         if out is not None:  # writing into a caller's buffer cannot be recorded: refuse rather than detach silently
             raise ValueError("'out=' cannot be combined with an input that requires grad (use torch.no_grad() or drop out=)")
         return _ProjectorFn.apply(x, plans, tuple(out_shape), forward, batch, default_device)
-    return _apply(plans, x, out_shape, forward, batch, default_device, out)
+    return _apply(plans, x, out_shape, forward, batch, default_device, out, wait)
+
+
+def _host_wait(plans: _Plans, device: Optional[int]):
+    """Block until every ``wait=False`` host-array application of this operator has delivered its result."""
+    dev = device if device is not None else (torch.cuda.current_device() if (torch is not None and torch.cuda.is_available()) else 0)
+    with plans.host_lock(dev):
+        _lib.check(_lib.lib().xct_host_wait(plans.get(dev)))
 
 
 def _analyse(fn, geom) -> dict:
@@ -390,17 +407,22 @@ class XRayTransform3D(LinearOperator):
     def plan_info(self, device: int = 0) -> dict:
         return self._plans.info(device)
 
-    def project(self, im, out=None):
-        """Compute X-ray projection (``out``: optional preallocated result, see :func:`_apply`)."""
+    def project(self, im, out=None, wait: bool = True):
+        """Compute X-ray projection (``out``: optional preallocated result; ``wait=False``: host arrays only,
+        enqueue and return, see :func:`_apply` and :meth:`host_wait`)."""
         if tuple(im.shape) != self.input_shape:
             raise ValueError(f"array of shape {tuple(im.shape)} does not match {self.input_shape}")
-        return _apply_ad(self._plans, im, self.output_shape, True, 1, _device_index(self.output_device), out)
+        return _apply_ad(self._plans, im, self.output_shape, True, 1, _device_index(self.output_device), out, wait)
 
-    def back_project(self, proj, out=None):
+    def back_project(self, proj, out=None, wait: bool = True):
         """Compute X-ray back projection (exact adjoint of :meth:`project`)."""
         if tuple(proj.shape) != self.output_shape:
             raise ValueError(f"array of shape {tuple(proj.shape)} does not match {self.output_shape}")
-        return _apply_ad(self._plans, proj, self.input_shape, False, 1, _device_index(self.input_device), out)
+        return _apply_ad(self._plans, proj, self.input_shape, False, 1, _device_index(self.input_device), out, wait)
+
+    def host_wait(self, device: Optional[int] = None):
+        """Wait for the ``wait=False`` applications of this operator on host arrays (``xct_host_wait``)."""
+        _host_wait(self._plans, device)
 
     def back_project_scatter(self, proj, ptrs, row_begin, store: bool = False) -> None:
         """Back projection fused with the view-block exchange: slice ``i`` of the result is added into (or,

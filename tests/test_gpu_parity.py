@@ -486,6 +486,22 @@ def test_pipelined_host_path_matches_device_path(torch_dev, N, D, spacing):
     op_out = torch.empty(H.output_shape, dtype=torch.float32, pin_memory=True)
     H.project(xp.numpy(), out=op_out.numpy())
     assert O.rel_l2(op_out.numpy(), fwd_dev) <= 1e-6
+    # a forward and an adjoint in flight together (xct_*_host_async), twice so that each direction's staging
+    # buffers are reused while the other direction still runs; results only after host_wait()
+    yp = torch.empty(H.output_shape, dtype=torch.float32, pin_memory=True)
+    yp.copy_(torch.from_numpy(y))
+    back_out = torch.empty(N, dtype=torch.float32, pin_memory=True)
+    for op in (H, H0):
+        for rep in range(2):
+            op_out.fill_(float("nan"))
+            back_out.fill_(float("nan"))
+            assert op.project(xp.numpy(), out=op_out.numpy(), wait=False) is not None
+            op.back_project(yp.numpy(), out=back_out.numpy(), wait=False)
+            op.host_wait()
+            assert O.rel_l2(op_out.numpy(), fwd_dev) <= 1e-6, rep
+            np.testing.assert_array_equal(back_out.numpy(), adj_dev)
+    with pytest.raises(ValueError):  # wait=False needs an explicit result buffer
+        H.project(xp.numpy(), wait=False)
 
 
 def test_forward_overwrites_output_and_is_linear(torch_dev):

@@ -142,7 +142,7 @@ def test_autograd_resolves_to_the_adjoint_kernel(monkeypatch):
     M = torch.from_numpy(rng.standard_normal((V * A.ny, nx[0] * nx[1])).astype(np.float32))
     calls = []
 
-    def fake_apply(plans, x, out_shape, forward, batch, default_device, out=None):
+    def fake_apply(plans, x, out_shape, forward, batch, default_device, out=None, wait=True):
         assert plans is A._plans
         assert out is not None or not (torch.is_grad_enabled() and x.requires_grad)  # kernels run off the tape
         x = x.detach()
