@@ -309,6 +309,32 @@ def view_block_configs(torch, dist, sb, sharded, dev, world, barrier, reduce_max
         "collective": "none (one rank)" if world == 1 else
                       "forward: ncclAllGather of the slab-sharded volume; adjoint: per-slab ncclReduce overlapped with the "
                       "next slab's kernel | fused peer exchange"}
+    del A, xs, ys
+    torch.cuda.empty_cache()
+
+    # separable 3D geometry in VIEW-BLOCK mode (C4's operator: 512^3, 720 views, det 512^2): what z-slab sharding
+    # does without any exchange, done the communicating way -- the routed epilogue of the walk adjoint
+    n, V = 512, 720
+    M = sb.matrices_from_euler_angles((n,) * 3, (n, n), "X", np.linspace(0, np.pi, V, endpoint=False)[:, None])
+    A = sharded.ViewShardedXRayTransform3D((n,) * 3, M, (n, n))
+    xs = torch.randn(A.local_input_shape, device=dev, generator=g)
+    ys = A.project(xs)
+    f_ms = timeit(lambda: A.project(xs))
+    a_nccl = timeit(lambda: A.back_project(ys))
+    a_peer = None
+    if world > 1:
+        P = sharded.ViewShardedXRayTransform3D((n,) * 3, M, (n, n), exchange="peer")
+        a_peer = timeit(lambda: P.back_project(ys))
+        P.close()
+        del P
+    upd = float(n) ** 3 * V
+    best = a_nccl if a_peer is None else min(a_nccl, a_peer)
+    out["C4 3D 512^3 x 720 views in view blocks (separable geometry, walk kernels)"] = {
+        "fwd_ms": f_ms, "adj_ms_nccl_reduce": a_nccl, "adj_ms_fused_peer_exchange": a_peer,
+        "pair_updates_per_s_nccl": 2 * upd / (f_ms + a_nccl) * 1e3, "pair_updates_per_s_best": 2 * upd / (f_ms + best) * 1e3,
+        "collective": "none (one rank)" if world == 1 else
+                      "forward: ncclAllGather of the volume slabs (512 MB); adjoint: per-slab ncclReduce | fused: the walk adjoint's "
+                      "routed epilogue stores into the owners' slots over NVLink, flag rendezvous, slot sum"}
     return out
 
 

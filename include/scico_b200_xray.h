@@ -186,6 +186,14 @@ XCT_API int xct_peer_copy_out(int32_t device, void *dst_dev, const void *src, si
 /* dst[i] = ((slot_0[i] + slot_1[i]) + ...) for i < n; slot s starts at slots + s * pitch (elements). */
 XCT_API int xct_sum_slots(int32_t device, float *dst_dev, const float *slots_dev, int32_t nslots, size_t n, size_t pitch,
                           void *stream);
+/* Rendezvous of the fused exchange without a collective library call: flag words in peer-mapped memory.
+ * xct_peer_signal: stream-ordered after the routed back projection, writes `epoch` into flag_ptrs[k] (this rank's
+ * word in rank k's flag array, k < nranks; release, system scope).  xct_peer_wait: stream-ordered, returns once
+ * flags[k] >= epoch for all k < nranks (this rank's own array: every peer has signalled), or sets *timed_out_dev = 1
+ * after timeout_s seconds (a peer died) instead of hanging the device.  Epochs must grow from call to call. */
+XCT_API int xct_peer_signal(int32_t device, int32_t *const *flag_ptrs, int32_t nranks, int32_t epoch, void *stream);
+XCT_API int xct_peer_wait(int32_t device, const int32_t *flags_dev, int32_t nranks, int32_t epoch, double timeout_s,
+                          int32_t *timed_out_dev, void *stream);
 XCT_API int xct_peer_close(int32_t device, void *ptr); /* unmap (xct_peer_open) */
 XCT_API int xct_peer_free(int32_t device, void *ptr);  /* release (xct_peer_alloc) */
 

@@ -59,6 +59,8 @@ EXPORTED_SYMBOLS = (
     "xct_peer_zero",
     "xct_peer_copy_out",
     "xct_sum_slots",
+    "xct_peer_signal",
+    "xct_peer_wait",
     "xct_peer_close",
     "xct_peer_free",
     "xct_launch_count",
@@ -202,6 +204,8 @@ def lib() -> ctypes.CDLL:
     L.xct_peer_zero.argtypes = [c_int32, c_void_p, ctypes.c_size_t, c_void_p]
     L.xct_peer_copy_out.argtypes = [c_int32, c_void_p, c_void_p, ctypes.c_size_t, c_void_p]
     L.xct_sum_slots.argtypes = [c_int32, c_void_p, c_void_p, c_int32, ctypes.c_size_t, ctypes.c_size_t, c_void_p]
+    L.xct_peer_signal.argtypes = [c_int32, POINTER(c_void_p), c_int32, c_int32, c_void_p]
+    L.xct_peer_wait.argtypes = [c_int32, c_void_p, c_int32, c_int32, ctypes.c_double, c_void_p, c_void_p]
     L.xct_peer_close.argtypes = [c_int32, c_void_p]
     L.xct_peer_free.argtypes = [c_int32, c_void_p]
     L.xct3d_debug_weights.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]

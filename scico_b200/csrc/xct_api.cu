@@ -327,7 +327,7 @@ int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* 
 // walk adjoint (3D separable geometry with unit rows; `in` must be 16-byte aligned)
 // Slices [s_begin, s_begin + s_count) of the plan only (s_count < 0: all); `out` is the full volume.
 int launch_walk_adjoint(const xct_plan* pl, const float* in, float* out, cudaStream_t st, int s_begin = 0,
-                        int s_count = -1) {
+                        int s_count = -1, const xct::OutRoute* route = nullptr) {
   xct::Walk2Params wp{};
   wp.p = plane_params(pl, 1);
   wp.rowoff = pl->d_rowoff;
@@ -336,15 +336,17 @@ int launch_walk_adjoint(const xct_plan* pl, const float* in, float* out, cudaStr
   wp.s_base = s_begin;
   xct::PlaneParams& p = wp.p;
   if (s_count >= 0) p.NS = s_count;
-  out += (size_t)s_begin * pl->n1 * pl->n2;
+  if (out) out += (size_t)s_begin * pl->n1 * pl->n2;
   p.tilesA = ceil_div(p.NA, kWAdjTA);
   p.tilesB = ceil_div(p.NB, 32);
   const long long tasks = (long long)ceil_div(p.NS, kWAdjS) * p.tilesA * p.tilesB;
   const int blocks = ceil_div(tasks, kWarps);
   const size_t smem = (size_t)kWarps * kWAdjStages * kWAdjS * kWAdjWin * sizeof(float);
+  const xct::OutRoute none{};
   CUtensorMap tmap;
   std::memset(&tmap, 0, sizeof(tmap));
-  if (pl->adj_tma) {
+  bool tma = pl->adj_tma;
+  if (tma) {
     // (V, d0, d1) fp32 sinogram, box = kWAdjWin bins x kWAdjS rows x 1 view, zero fill out of bounds
     const cuuint64_t dims[3] = {(cuuint64_t)pl->d1, (cuuint64_t)pl->d0, (cuuint64_t)pl->V};
     const cuuint64_t strides[2] = {(cuuint64_t)pl->d1 * sizeof(float), (cuuint64_t)pl->d0 * pl->d1 * sizeof(float)};
@@ -353,23 +355,19 @@ int launch_walk_adjoint(const xct_plan* pl, const float* in, float* out, cudaStr
     const CUresult r = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), dims, strides,
                                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r == CUDA_SUCCESS) {
-      const size_t smem_tma = smem + (size_t)kWarps * kWAdjStages * sizeof(unsigned long long);
-      auto kern = xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps, true>;
-      XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));  // > 48 KB
-      xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps, true>
-          <<<blocks, kWarps * 32, smem_tma, st>>>(wp, in, out, tmap);
-      return launch_ok("walk_adjoint_kernel<tma>");
-    }
-    // encoding refused (e.g. a stride the tensor map cannot express): cp.async staging below
+    if (r != CUDA_SUCCESS) tma = false;  // e.g. a stride the tensor map cannot express: cp.async staging below
   }
-  {
-    auto kern = xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps, false>;
-    if (smem > 48 * 1024) XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps, false>
-      <<<blocks, kWarps * 32, smem, st>>>(wp, in, out, tmap);
-  return launch_ok("walk_adjoint_kernel");
+  const size_t smem_all = smem + (tma ? (size_t)kWarps * kWAdjStages * sizeof(unsigned long long) : 0);
+#define XCT_WALK_ADJ(TMA_, ROUTE_)                                                                                                \
+  do {                                                                                                                            \
+    auto kern = xct::walk_adjoint_kernel<xct::Geom3, true, kWAdjS, kWAdjTA, kWAdjWin, kWAdjStages, kWarps, TMA_, ROUTE_>;         \
+    if (smem_all > 48 * 1024) XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));   \
+    kern<<<blocks, kWarps * 32, smem_all, st>>>(wp, in, out, tmap, route ? *route : none);                                        \
+  } while (0)
+  if (tma) { if (route) XCT_WALK_ADJ(true, true); else XCT_WALK_ADJ(true, false); }
+  else { if (route) XCT_WALK_ADJ(false, true); else XCT_WALK_ADJ(false, false); }
+#undef XCT_WALK_ADJ
+  return launch_ok(tma ? "walk_adjoint_kernel<tma>" : "walk_adjoint_kernel");
 }
 
 template <class G, bool IS3D, int S, int TN, int GS, bool MAJOR_B>
@@ -1143,8 +1141,8 @@ int xct_adjoint(const xct_plan* pl, const float* in, float* out, int32_t batch, 
 
 // Back projection of a view block whose result rows go straight to their owners (view-block sharding):
 // the kernels' epilogue adds each value into the row block that holds it, across NVLink for a peer's
-// block, instead of writing a partial volume for a reduce-scatter.  The walk adjoint has no routed
-// variant: separable 3D plans use the plane adjoint here (z-slab sharding is the mode for them).
+// block, instead of writing a partial volume for a reduce-scatter.  Every adjoint family has a routed
+// epilogue: walk (TMA or cp.async staging), plane, brick, thread-per-voxel.
 int xct_adjoint_scatter(const xct_plan* pl, const float* in, const xct_out_route* r, void* stream) {
   if (!pl || !in || !r) return fail(XCT_ERR_INVALID, "null argument");
   if (pl->dry) return fail(XCT_ERR_INVALID, "analysis-only plan");
@@ -1168,6 +1166,7 @@ int xct_adjoint_scatter(const xct_plan* pl, const float* in, const xct_out_route
   if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
   if (pl->ndim == 3) {
+    if (pl->adj_walk && (reinterpret_cast<uintptr_t>(in) & 15) == 0) return launch_walk_adjoint(pl, in, nullptr, st, 0, -1, &route);
     if (pl->adj_plane) return launch_plane_adjoint<xct::Geom3, true, kAdj3S, kAdj3TA>(pl, 1, in, nullptr, st, &route);
     if (pl->brick_adj) return launch_brick_adjoint(pl, in, nullptr, st, &route);
     xct::gen3d_adjoint_kernel<true><<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, nullptr, route);
@@ -1230,6 +1229,28 @@ int xct_sum_slots(int32_t device, float* dst, const float* slots, int32_t nslots
   if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
   xct::sum_slots_kernel<<<general_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(dst, slots, nslots, n, pitch);
   return launch_ok("sum_slots_kernel");
+}
+int xct_peer_signal(int32_t device, int32_t* const* flag_ptrs, int32_t nranks, int32_t epoch, void* stream) {
+  if (!flag_ptrs || nranks < 1 || nranks > XCT_MAX_ROUTE_PARTS) return fail(XCT_ERR_INVALID, "xct_peer_signal: bad argument");
+  xct::PeerFlagPtrs f{};
+  f.n = nranks;
+  for (int k = 0; k < nranks; ++k) {
+    if (!flag_ptrs[k]) return fail(XCT_ERR_INVALID, "xct_peer_signal: null flag pointer");
+    f.ptr[k] = flag_ptrs[k];
+  }
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
+  xct::peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, epoch);
+  return launch_ok("peer_signal_kernel");
+}
+int xct_peer_wait(int32_t device, const int32_t* flags, int32_t nranks, int32_t epoch, double timeout_s, int32_t* timed_out_dev,
+                  void* stream) {
+  if (!flags || !timed_out_dev || nranks < 1 || nranks > XCT_MAX_ROUTE_PARTS) return fail(XCT_ERR_INVALID, "xct_peer_wait: bad argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(XCT_ERR_CUDA, "cudaSetDevice failed");
+  const unsigned long long ns = (unsigned long long)(std::max(timeout_s, 1e-3) * 1e9);
+  xct::peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, nranks, epoch, ns, timed_out_dev);
+  return launch_ok("peer_wait_kernel");
 }
 int xct_peer_close(int32_t device, void* ptr) {
   if (!ptr) return XCT_OK;

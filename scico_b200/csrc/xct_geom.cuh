@@ -164,6 +164,46 @@ struct RouteCursor {
   }
 };
 
+// ---- rendezvous of the fused exchange through flags in peer memory (no collective library call) ----
+// Every rank owns `n` flag words (one per peer) in memory all GPUs of the node have mapped.  After its routed
+// back projection a rank SIGNALS: it writes the call's epoch into its word on every peer (release, system
+// scope; the kernel boundary before it has already made the back projection's peer stores visible).  It then
+// WAITS until all of its own words carry that epoch (acquire, system scope): every peer's back projection into
+// this rank's staging area has completed.  Epochs only grow, so the words are never reset.
+struct PeerFlagPtrs {
+  int* ptr[kMaxRouteParts];  // ptr[k]: this rank's flag word in rank k's flag array
+  int n;
+};
+__global__ void peer_signal_kernel(const __grid_constant__ PeerFlagPtrs f, int epoch) {
+  const int k = threadIdx.x;
+  if (k < f.n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f.ptr[k]), "r"(epoch) : "memory");
+  }
+}
+// flags[k] >= epoch for every k < n, or *timed_out = 1 after `timeout_ns` (a peer died: the caller reports it
+// instead of hanging the GPU)
+__global__ void peer_wait_kernel(const int* flags, int n, int epoch, unsigned long long timeout_ns, int* timed_out) {
+  const int k = threadIdx.x;
+  if (k < n) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      int v;
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + k) : "memory");
+      if (v - epoch >= 0) break;
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) {
+        *timed_out = 1;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+
 // dst[i] = ((slot_0[i] + slot_1[i]) + slot_2[i]) + ... : the owner's side of the store-mode exchange.
 __global__ void __launch_bounds__(256)
 sum_slots_kernel(float* __restrict__ dst, const float* __restrict__ slots, int nslots, size_t n, size_t pitch) {

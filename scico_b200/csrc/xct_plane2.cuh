@@ -107,10 +107,13 @@ __device__ __forceinline__ int window_start4(const ViewRec& vr, int a_lo, int a_
 // view), so the S x WIN window of a view is ONE box of the (V, D0, D1) sinogram: lane 0 issues a
 // single cp.async.bulk.tensor per view that completes on a per-stage mbarrier (hardware zero fill
 // outside the detector) instead of every lane issuing 16-byte cp.async with its own row lookups.
-template <class G, bool IS3D, int S, int TA, int WIN, int STAGES, int WARPS, bool TMA>
-__global__ void __launch_bounds__(WARPS * 32)
+// ROUTE: every result slice goes to the memory of the row block that owns it (view-block sharding fused with
+// its exchange, xct_adjoint_scatter): one owner lookup per slice, then TA stores (or system-scope RED.ADD)
+// at a fixed stride, as in plane_adjoint_kernel's routed epilogue.  The view loop is the plain kernel's.
+template <class G, bool IS3D, int S, int TA, int WIN, int STAGES, int WARPS, bool TMA, bool ROUTE = false>
+__global__ void __launch_bounds__(WARPS * 32, ROUTE ? 2 : 0)  // routed: the plain kernel's occupancy (0 = unspecified)
 walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __restrict__ out,
-                    const __grid_constant__ CUtensorMap tmap) {
+                    const __grid_constant__ CUtensorMap tmap, const __grid_constant__ OutRoute route) {
   static_assert(WIN % 64 == 0 || WIN == 32, "chunk indexing assumes a power-of-two window");
   constexpr int CPR = WIN / 4;                    // 16-byte chunks per staged row
   constexpr int CHUNKS = S * CPR;                 // chunks per view
@@ -315,6 +318,26 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
   }
   if (!TMA) cp_async_wait<0>();
 
+  if constexpr (ROUTE) {
+    if (b >= p.NB) return;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if (s0 + s >= p.NS) break;
+      RouteCursor cur;
+      cur.seek(route, wp.s_base + s0 + s, (long long)a0 * p.NB + b);  // the slice picks the owner
+      float* q = cur.q;
+      if (route.store) {
+#pragma unroll
+        for (int n = 0; n < TA; ++n)
+          if (a0 + n < p.NA) q[(size_t)n * p.NB] = ((s & 1) ? acc[n][s / 2].y : acc[n][s / 2].x) * wp.out_scale;
+      } else {
+#pragma unroll
+        for (int n = 0; n < TA; ++n)
+          if (a0 + n < p.NA) atomicAdd_system(q + (size_t)n * p.NB, ((s & 1) ? acc[n][s / 2].y : acc[n][s / 2].x) * wp.out_scale);
+      }
+    }
+    return;
+  }
   if (b < p.NB) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {

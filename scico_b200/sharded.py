@@ -182,8 +182,11 @@ class PeerBlocks:
        sends every result row to the rank that owns it --
        ``mode="store"`` (default): plain posted stores into THIS rank's slot of the owner's staging area
        ``(world, rows, *inner)``; ``mode="add"``: ``RED.ADD.F32`` (system scope) into the owner's block;
-    2. one stream-ordered rendezvous (a one-element NCCL all-reduce): when it completes on this rank's
-       stream, every rank's kernel has finished;
+    2. one stream-ordered rendezvous: when it completes on this rank's stream, every rank's kernel has
+       finished.  ``rendezvous="flags"`` (default): each rank writes the call's epoch into its flag word on
+       every peer (``xct_peer_signal``, release / system scope, ordered after its kernel) and waits until all of
+       its own words carry it (``xct_peer_wait``) -- two one-warp kernels, no collective library call;
+       ``rendezvous="collective"``: a one-element all-reduce of the process group instead;
     3. store: the owner sums its slots in rank order into ``out`` (``xct_sum_slots``: deterministic, unlike
        a sum of atomics); add: the block is copied to ``out`` and zeroed again for its next use.
 
@@ -195,10 +198,14 @@ class PeerBlocks:
 
     def __init__(self, slabs: Sequence[tuple[int, int]], inner_shape: Sequence[int], group=None,
                  rank: Optional[int] = None, world_size: Optional[int] = None, device: Optional[int] = None,
-                 mode: str = "store", mem=None):
+                 mode: str = "store", mem=None, rendezvous: str = "flags", timeout_s: float = 30.0):
         if mode not in ("store", "add"):
             raise ValueError("mode must be 'store' or 'add'")
+        if rendezvous not in ("flags", "collective"):
+            raise ValueError("rendezvous must be 'flags' or 'collective'")
         self.mode = mode
+        self.rendezvous = rendezvous
+        self.timeout_s = float(timeout_s)
         self.group = group
         r, w = _world(group)
         self.rank = r if rank is None else rank
@@ -228,6 +235,10 @@ class PeerBlocks:
             self.mem.zero(ptr, alloc)
             self._own.append(ptr)
             handles.append(handle)
+        # flag words of the rendezvous: COPIES x world int32, epochs only grow (never reset)
+        self._flags_own, fh = self.mem.alloc(max(4 * self.COPIES * self.world_size, 256))
+        self.mem.zero(self._flags_own, max(4 * self.COPIES * self.world_size, 256))
+        handles.append(fh)
         self.mem.sync()
         gathered = [None] * self.world_size
         if self.world_size > 1:
@@ -247,6 +258,20 @@ class PeerBlocks:
                     base = self.mem.offset(base, 4 * self.rank * self._block_elems[k])
                 row.append(base)
             self.ptrs.append(row)
+        # [copy][k]: this rank's flag word in rank k's flag array
+        self._flag_ptrs: list[list] = []
+        flag_bases = []
+        for k in range(self.world_size):
+            if k == self.rank:
+                flag_bases.append(self._flags_own)
+            else:
+                q = self.mem.open(gathered[k][self.COPIES])
+                self._mapped.append(q)
+                flag_bases.append(q)
+        for c in range(self.COPIES):
+            self._flag_ptrs.append([self.mem.offset(flag_bases[k], 4 * (c * self.world_size + self.rank))
+                                    for k in range(self.world_size)])
+        self._epoch = [0] * self.COPIES
         self._token = self.mem.token()
         self._turn = 0
         self._closed = False
@@ -260,7 +285,13 @@ class PeerBlocks:
         self._turn = (c + 1) % self.COPIES
         launch(self.ptrs[c], self.row_begin, self.mode == "store")
         if self.world_size > 1:
-            dist.all_reduce(self._token, group=self.group)  # stream-ordered: no host synchronisation
+            if self.rendezvous == "flags":  # stream-ordered, no host synchronisation, no collective call
+                self._epoch[c] += 1
+                self.mem.signal(self._flag_ptrs[c], self._epoch[c])
+                self.mem.wait_flags(self.mem.offset(self._flags_own, 4 * c * self.world_size), self.world_size,
+                                    self._epoch[c], self.timeout_s)
+            else:
+                dist.all_reduce(self._token, group=self.group)  # stream-ordered: no host synchronisation
         if self.nelems == 0:
             return out
         if self.mode == "store":
@@ -291,6 +322,7 @@ class PeerBlocks:
             dist.barrier(group=self.group)
         for q in self._own:
             self.mem.free(q)
+        self.mem.free(self._flags_own)
         self._mapped, self._own = [], []
 
     def __del__(self):
@@ -343,6 +375,22 @@ class _NativePeerMemory:
     def copy_out(self, out, ptr: int, nbytes: int):
         self._lib.check(self._L.xct_peer_copy_out(self.device, out.data_ptr(), ptr, nbytes, self._stream()))
 
+    def signal(self, flag_ptrs, epoch: int):
+        import ctypes
+
+        arr = (ctypes.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        self._lib.check(self._L.xct_peer_signal(self.device, arr, len(flag_ptrs), int(epoch), self._stream()))
+
+    def wait_flags(self, flags_ptr: int, n: int, epoch: int, timeout_s: float):
+        if not hasattr(self, "_timed_out"):
+            self._timed_out = torch.zeros(1, dtype=torch.int32, device=f"cuda:{self.device}")
+        self._lib.check(self._L.xct_peer_wait(self.device, flags_ptr, n, int(epoch), float(timeout_s),
+                                              self._timed_out.data_ptr(), self._stream()))
+
+    def timed_out(self) -> bool:
+        """True if a rendezvous gave up waiting for a peer (host synchronisation; call when diagnosing)."""
+        return hasattr(self, "_timed_out") and bool(self._timed_out.item())
+
     def token(self):
         return torch.zeros(1, dtype=torch.float32, device=f"cuda:{self.device}")
 
@@ -359,14 +407,15 @@ class _NativePeerMemory:
 class _ViewSharded:
     """Shared machinery of the view-block partitions (volume / image rows sharded on axis 0)."""
 
-    def _setup_exchange(self, exchange, inner_shape, peer_mem=None):
+    def _setup_exchange(self, exchange, inner_shape, peer_mem=None, rendezvous="flags", peer_timeout_s=30.0):
         if exchange not in ("nccl", "peer", "peer_add"):
             raise ValueError("exchange must be 'nccl', 'peer' (stores into per-rank slots) or 'peer_add' (atomics)")
         self.exchange = exchange
         self.peer = None
         if exchange != "nccl" and self.world_size > 1:
             self.peer = PeerBlocks(self.slabs, inner_shape, group=self.group, rank=self.rank, world_size=self.world_size,
-                                   mode="store" if exchange == "peer" else "add", mem=peer_mem)
+                                   mode="store" if exchange == "peer" else "add", mem=peer_mem, rendezvous=rendezvous,
+                                   timeout_s=peer_timeout_s)
 
     def close(self):
         if getattr(self, "peer", None) is not None:
@@ -428,12 +477,13 @@ class ViewShardedXRayTransform3D(_ViewSharded):
     of the per-slab NCCL reductions."""
 
     def __init__(self, input_shape, matrices, det_shape, group=None, op_factory: Optional[Callable] = None,
-                 rank: Optional[int] = None, world_size: Optional[int] = None, exchange: str = "nccl", peer_mem=None):
+                 rank: Optional[int] = None, world_size: Optional[int] = None, exchange: str = "nccl", peer_mem=None,
+                 rendezvous: str = "flags", peer_timeout_s: float = 30.0):
         self.input_shape = tuple(int(s) for s in input_shape)
         self.det_shape = tuple(int(s) for s in det_shape)
         self.matrices = np.asarray(matrices, dtype=np.float32)
         self._setup(len(self.matrices), self.input_shape[0], group, rank, world_size)
-        self._setup_exchange(exchange, self.input_shape[1:], peer_mem)  # peer_mem: CPU tests only
+        self._setup_exchange(exchange, self.input_shape[1:], peer_mem, rendezvous, peer_timeout_s)  # peer_mem: CPU tests only
         v0, v1 = self.views
         self.local_output_shape = (v1 - v0,) + self.det_shape
         z0, z1 = self.slab
@@ -489,11 +539,11 @@ class ViewShardedXRayTransform2D(_ViewSharded):
 
     def __init__(self, input_shape, angles, group=None, op_factory: Optional[Callable] = None,
                  rank: Optional[int] = None, world_size: Optional[int] = None, exchange: str = "nccl", peer_mem=None,
-                 **kw):
+                 rendezvous: str = "flags", peer_timeout_s: float = 30.0, **kw):
         self.input_shape = tuple(int(s) for s in input_shape)
         self.angles = np.asarray(angles, dtype=np.float64)
         self._setup(len(self.angles), self.input_shape[0], group, rank, world_size)
-        self._setup_exchange(exchange, self.input_shape[1:], peer_mem)  # peer_mem: CPU tests only
+        self._setup_exchange(exchange, self.input_shape[1:], peer_mem, rendezvous, peer_timeout_s)  # peer_mem: CPU tests only
         v0, v1 = self.views
         if kw.get("det_count") is None:  # the default depends on the image only, not on the views
             kw["det_count"] = int(np.ceil(np.linalg.norm(self.input_shape)))

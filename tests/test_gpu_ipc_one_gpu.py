@@ -3,8 +3,8 @@ memory on ONE GPU: several processes share ``cuda:0``, rendezvous over gloo, and
 exchange buffers through CUDA IPC (which works between processes on the same device exactly as it does
 across NVLink).  This is what the driver's one-GPU box can run of tests/test_gpu_multi.py: the protocol
 (slot addressing, double-buffered copies, rendezvous placement, re-zeroing), the routed kernels writing
-through IPC-mapped pointers, uneven row blocks, three ranks, a rank without views, store and add mode --
-all against the oracle.  NCCL itself needs one GPU per rank and stays in tests/test_gpu_multi.py.
+through IPC-mapped pointers, the flag rendezvous in peer memory, uneven row blocks, three ranks, a rank without
+views, store and add mode -- all against the oracle.  NCCL itself needs one GPU per rank and stays in tests/test_gpu_multi.py.
 """
 import os
 import socket
@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case, exchange):
+def _worker(rank, world, port, case, exchange, rendezvous="flags"):
     import torch
     import torch.distributed as dist
 
@@ -39,8 +39,11 @@ def _worker(rank, world, port, case, exchange):
         if case.startswith("view2d"):
             nx, V = {"view2d": ((200, 168), 48), "view2d_uneven": ((203, 168), 50), "view2d_idle_rank": ((96, 80), 2)}[case]
             angles = np.linspace(0, np.pi, V, endpoint=False)
-            op = sharded.ViewShardedXRayTransform2D(nx, angles, exchange=exchange)
+            # a short rendezvous timeout: ranks time-slice ONE GPU here, a rank that cannot make progress must
+            # fail the comparison below, not hang the box
+            op = sharded.ViewShardedXRayTransform2D(nx, angles, exchange=exchange, rendezvous=rendezvous, peer_timeout_s=5.0)
             assert op.peer is not None and isinstance(op.peer.mem, sharded._NativePeerMemory)
+            assert op.peer.rendezvous == rendezvous
             T = sb.XRayTransform2D(nx, angles).view_table
             (z0, z1), (v0, v1) = op.slab, op.views
             if case == "view2d_idle_rank":
@@ -63,8 +66,12 @@ def _worker(rank, world, port, case, exchange):
             else:  # separable plan in view-block mode (routed walk / plane adjoint)
                 N, D, V = (24, 96, 80), (24, 128), 12
                 M = sb.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, V, endpoint=False)[:, None])
-            op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange=exchange)
+            op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange=exchange, rendezvous=rendezvous, peer_timeout_s=5.0)
             assert op.peer is not None
+            if case == "view3d_sep":  # the routed epilogue of the walk adjoint (TMA-staged window)
+                assert op.full.plan_info(0)["adj_kernel"] == 2 and op.full.plan_info(0)["adj_tma"] == 1
+            else:                     # ... and of the brick adjoint
+                assert op.full.plan_info(0)["adj_kernel"] == 3
             (z0, z1), (v0, v1) = op.slab, op.views
             for it in range(4):
                 y = rng.standard_normal((V,) + D).astype(np.float32)
@@ -74,6 +81,7 @@ def _worker(rank, world, port, case, exchange):
             x = rng.standard_normal(N).astype(np.float32)
             got = op.project(torch.as_tensor(x[z0:z1], device=dev)).cpu().numpy()  # all-gather of the slabs
             assert O.rel_l2(got, C.project_3d(x, op.matrices, D)[v0:v1]) <= 1e-5
+            assert not op.peer.mem.timed_out()
             op.close()
         elif case == "pdhg_view3d":
             # TV-PDHG over the view-block partition of a tilted geometry: volume state in z-slabs, sinogram
@@ -90,7 +98,7 @@ def _worker(rank, world, port, case, exchange):
             y = full(torch.as_tensor(x_gt, device=dev)) + 0.05 * torch.as_tensor(noise, device=dev)
             ref = TVPDHG(full, y, 0.1, 0.05, 0.05, maxiter=20)
             ref.solve()
-            op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange=exchange)
+            op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange=exchange, rendezvous=rendezvous, peer_timeout_s=5.0)
             (z0, z1), (v0, v1) = op.slab, op.views
             S = TVPDHG(op, y[v0:v1].contiguous(), 0.1, 0.05, 0.05, maxiter=20)
             S.solve()
@@ -106,17 +114,20 @@ def _worker(rank, world, port, case, exchange):
         dist.destroy_process_group()
 
 
+# rendezvous: "flags" = epoch words in peer memory (xct_peer_signal / xct_peer_wait, the default);
+# "collective" = a one-element all-reduce of the process group
 CASES = [
-    ("view2d", 2, "peer"), ("view2d", 2, "peer_add"), ("view2d_uneven", 3, "peer"), ("view2d_uneven", 3, "peer_add"),
-    ("view2d_idle_rank", 3, "peer"), ("view2d_idle_rank", 3, "peer_add"),
-    ("view3d_tilt", 2, "peer"), ("view3d_tilt", 3, "peer"), ("view3d_tilt", 3, "peer_add"),
-    ("view3d_sep", 2, "peer"), ("view3d_sep", 3, "peer_add"),
-    ("pdhg_view3d", 2, "peer"),
+    ("view2d", 2, "peer", "flags"), ("view2d", 2, "peer_add", "flags"), ("view2d", 2, "peer", "collective"),
+    ("view2d_uneven", 3, "peer", "flags"), ("view2d_uneven", 3, "peer_add", "collective"),
+    ("view2d_idle_rank", 3, "peer", "flags"), ("view2d_idle_rank", 3, "peer_add", "flags"),
+    ("view3d_tilt", 2, "peer", "flags"), ("view3d_tilt", 3, "peer", "collective"), ("view3d_tilt", 3, "peer_add", "flags"),
+    ("view3d_sep", 2, "peer", "flags"), ("view3d_sep", 3, "peer_add", "flags"),
+    ("pdhg_view3d", 2, "peer", "flags"),
 ]
 
 
-@pytest.mark.parametrize("case,world,exchange", CASES, ids=[f"{c}-w{w}-{e}" for c, w, e in CASES])
-def test_fused_exchange_over_cuda_ipc_on_one_gpu(cuda_device, case, world, exchange):
+@pytest.mark.parametrize("case,world,exchange,rendezvous", CASES, ids=[f"{c}-w{w}-{e}-{r}" for c, w, e, r in CASES])
+def test_fused_exchange_over_cuda_ipc_on_one_gpu(cuda_device, case, world, exchange, rendezvous):
     import torch.multiprocessing as mp
 
-    mp.spawn(_worker, args=(world, _free_port(), case, exchange), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), case, exchange, rendezvous), nprocs=world, join=True)

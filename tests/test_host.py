@@ -284,7 +284,7 @@ def test_native_peer_memory_calls_the_c_abi_with_well_typed_arguments(monkeypatc
     for mode, per_call in (("store", ["xct_sum_slots"]), ("add", ["xct_peer_copy_out", "xct_peer_zero"])):
         calls.clear()
         pb = sharded.PeerBlocks([(0, 6)], (5,), rank=0, world_size=1, mode=mode)
-        assert calls == ["xct_peer_alloc", "xct_peer_zero"] * 2
+        assert calls == ["xct_peer_alloc", "xct_peer_zero"] * 3  # two block copies + the rendezvous flag words
         assert pb.ptrs[0][0] != pb.ptrs[1][0] and pb.local_shape == (6, 5) and pb.row_begin == [0, 6]
         seen = []
         out = torch.empty((6, 5))
@@ -292,10 +292,21 @@ def test_native_peer_memory_calls_the_c_abi_with_well_typed_arguments(monkeypatc
             pb.exchange(lambda ptrs, rb, store: seen.append((ptrs[0], store)), out)
         assert [p for p, _ in seen] == [pb.ptrs[0][0], pb.ptrs[1][0], pb.ptrs[0][0]]  # the copies alternate
         assert all(st == (mode == "store") for _, st in seen)
-        assert calls[4:] == per_call * 3
+        assert calls[6:] == per_call * 3  # world size 1: no rendezvous
         pb.close()
-        assert calls[-2:] == ["xct_peer_free", "xct_peer_free"]
+        assert calls[-3:] == ["xct_peer_free"] * 3
         pb.close()
+    # the flag rendezvous converts under the real argtypes too
+    mem = sharded._NativePeerMemory(0)
+    monkeypatch.setattr(torch, "zeros", lambda *a, **k: type("T", (), {"data_ptr": lambda self: 0x7100_0000_0000})())
+    calls.clear()
+    mem.signal([0x7000_0000_0000, 0x7000_0000_0040], 3)
+    mem.wait_flags(0x7000_0000_0100, 2, 3, 1.5)
+    assert calls == ["xct_peer_signal", "xct_peer_wait"]
+    monkeypatch.undo()
+    monkeypatch.setattr(_lib, "lib", lambda: Fake())
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
     # opening a peer's handle: 64 bytes in, device address out
     mem = sharded._NativePeerMemory(0)
     assert isinstance(mem.open(bytes(range(64))), (int, type(None)))

@@ -227,6 +227,19 @@ class ShmPeerMemory:
     def copy_out(self, out, ptr, nbytes):
         out.numpy().reshape(-1)[:] = self.view(ptr, nbytes // 4)
 
+    def signal(self, flag_ptrs, epoch):
+        for q in flag_ptrs:
+            np.ndarray((1,), np.int32, buffer=self._seg(q[0]).buf, offset=q[1])[0] = epoch
+
+    def wait_flags(self, flags_ptr, n, epoch, timeout_s):
+        import time
+
+        words = np.ndarray((n,), np.int32, buffer=self._seg(flags_ptr[0]).buf, offset=flags_ptr[1])
+        t0 = time.time()
+        while not np.all(words >= epoch):
+            assert time.time() - t0 < timeout_s, "rendezvous timed out"
+            time.sleep(1e-4)
+
     @staticmethod
     def token():
         return torch.zeros(1)
