@@ -251,11 +251,18 @@ brick_adjoint_kernel(BrickParams p, const float* __restrict__ sino, float* __res
     if constexpr (ROUTE) {
       RouteCursor cur;
       cur.seek(route, i, (long long)j * p.N2 + k0);
+      if (route.store && k0 + B <= p.N2 && (p.N2 & 3) == 0 && (reinterpret_cast<uintptr_t>(cur.q) & 15) == 0) {
+        // 32 contiguous bytes per lane as two 16-byte stores: scalar stores would cross NVLink as 4 useful
+        // bytes per 32-byte sector (measured: the fused exchange of the tilted case was 0.4 ms slower than NCCL)
+        reinterpret_cast<float4*>(cur.q)[0] = make_float4(4.0f * acc[q][0], 4.0f * acc[q][1], 4.0f * acc[q][2], 4.0f * acc[q][3]);
+        reinterpret_cast<float4*>(cur.q)[1] = make_float4(4.0f * acc[q][4], 4.0f * acc[q][5], 4.0f * acc[q][6], 4.0f * acc[q][7]);
+      } else {
 #pragma unroll
-      for (int n = 0; n < B; ++n) {
-        if (k0 + n >= p.N2) break;
-        if (route.store) cur.q[n] = 4.0f * acc[q][n];
-        else atomicAdd_system(cur.q + n, 4.0f * acc[q][n]);
+        for (int n = 0; n < B; ++n) {
+          if (k0 + n >= p.N2) break;
+          if (route.store) cur.q[n] = 4.0f * acc[q][n];
+          else atomicAdd_system(cur.q + n, 4.0f * acc[q][n]);
+        }
       }
     } else {
       float* o = vol + ((size_t)i * p.N1 + j) * (size_t)p.N2 + k0;
