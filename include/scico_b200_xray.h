@@ -197,6 +197,26 @@ XCT_API int xct_peer_wait(int32_t device, const int32_t *flags_dev, int32_t nran
 XCT_API int xct_peer_close(int32_t device, void *ptr); /* unmap (xct_peer_open) */
 XCT_API int xct_peer_free(int32_t device, void *ptr);  /* release (xct_peer_alloc) */
 
+/* ---- operator registry: for callers that can only carry an integer (XLA FFI custom-call attributes) ----
+ * scico wires an external projector as a pair of callables with custom VJP / transpose rules
+ * (scico/linop/xray/astra/_astra_3d.py:498-511); under jax.jit those become custom calls whose attributes are plain
+ * integers, which may execute on any device of the process and may outlive the Python operator.  The registry
+ * therefore owns a COPY of the geometry and one plan per device:
+ *   xct_op_register_2d/3d : validate + copy the geometry (geom->device is ignored), returns an id (never reused);
+ *   xct_op_plan           : the plan for a device, created on the first call for that device (allocates: call it
+ *                           from an initialize-stage FFI handler or once per device before the first execution);
+ *   xct_op_apply          : one application on a device's stream; the plan must exist (no allocation, no host
+ *                           sync); the batch is in_count / operator input size (leading batch axes of any rank);
+ *   xct_op_retain/release : reference count; the last release destroys the plans of every device.  Applying a
+ *                           released id returns XCT_ERR_INVALID (no dangling pointer). */
+XCT_API int xct_op_register_2d(const xct2d_geom *geom, int64_t *op_id);
+XCT_API int xct_op_register_3d(const xct3d_geom *geom, int64_t *op_id);
+XCT_API int xct_op_retain(int64_t op_id);
+XCT_API int xct_op_release(int64_t op_id);
+XCT_API int xct_op_plan(int64_t op_id, int32_t device, const xct_plan **plan);
+XCT_API int xct_op_apply(int64_t op_id, int32_t device, int32_t forward, const float *in_dev, float *out_dev, int64_t in_count,
+                         void *stream);
+
 /* Same two operators for HOST buffers: H2D copy, kernel(s), D2H copy, synchronous on return.
  * Device staging buffers are cached inside the plan (these two calls are therefore NOT
  * re-entrant on one plan).  3D separable plans on the walk kernels cut the volume into chunks of

@@ -61,6 +61,12 @@ EXPORTED_SYMBOLS = (
     "xct_sum_slots",
     "xct_peer_signal",
     "xct_peer_wait",
+    "xct_op_register_2d",
+    "xct_op_register_3d",
+    "xct_op_retain",
+    "xct_op_release",
+    "xct_op_plan",
+    "xct_op_apply",
     "xct_peer_close",
     "xct_peer_free",
     "xct_launch_count",
@@ -206,6 +212,12 @@ def lib() -> ctypes.CDLL:
     L.xct_sum_slots.argtypes = [c_int32, c_void_p, c_void_p, c_int32, ctypes.c_size_t, ctypes.c_size_t, c_void_p]
     L.xct_peer_signal.argtypes = [c_int32, POINTER(c_void_p), c_int32, c_int32, c_void_p]
     L.xct_peer_wait.argtypes = [c_int32, c_void_p, c_int32, c_int32, ctypes.c_double, c_void_p, c_void_p]
+    L.xct_op_register_2d.argtypes = [POINTER(Geom2D), POINTER(c_int64)]
+    L.xct_op_register_3d.argtypes = [POINTER(Geom3D), POINTER(c_int64)]
+    L.xct_op_retain.argtypes = [c_int64]
+    L.xct_op_release.argtypes = [c_int64]
+    L.xct_op_plan.argtypes = [c_int64, c_int32, POINTER(c_void_p)]
+    L.xct_op_apply.argtypes = [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]
     L.xct_peer_close.argtypes = [c_int32, c_void_p]
     L.xct_peer_free.argtypes = [c_int32, c_void_p]
     L.xct3d_debug_weights.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]

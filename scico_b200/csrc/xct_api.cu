@@ -3,7 +3,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -1400,6 +1403,134 @@ int xct_forward_host(xct_plan* pl, const float* in_host, float* out_host, int32_
 int xct_adjoint_host(xct_plan* pl, const float* in_host, float* out_host, int32_t batch) {
   int rc = enqueue_host(pl, in_host, out_host, batch, false);
   return rc ? rc : xct_host_wait(pl);
+}
+
+
+// ---------------------------------------------------------------- operator registry (XLA FFI callers)
+// An XLA FFI handler gets plain integer attributes, may be executed on ANY device of the process and may
+// outlive the Python object that described the geometry.  So the handler is given an operator id, not a
+// plan pointer: the registry owns a copy of the geometry and one plan per device, created on first use for
+// that device, and destroys them when the last reference is released.
+namespace {
+struct OpEntry {
+  int ndim = 0;
+  int refs = 1;
+  xct2d_geom g2{};
+  xct3d_geom g3{};
+  std::vector<float> table;           // 2D view table / 3D matrices (owned copy)
+  std::map<int, xct_plan*> plans;     // device ordinal -> plan
+};
+std::mutex g_op_mutex;
+std::map<int64_t, OpEntry> g_ops;
+std::atomic<int64_t> g_next_op{1};
+}  // namespace
+
+int xct_op_register_2d(const xct2d_geom* g, int64_t* op_id) {
+  if (!g || !op_id) return fail(XCT_ERR_INVALID, "null argument");
+  xct_plan_info info;
+  int rc = xct2d_plan_analyse(g, &info, nullptr);  // validates the geometry without a device
+  if (rc) return rc;
+  OpEntry e;
+  e.ndim = 2;
+  e.g2 = *g;
+  e.table.assign(g->view_table, g->view_table + 4 * (size_t)g->num_views);
+  std::lock_guard<std::mutex> lock(g_op_mutex);
+  const int64_t id = g_next_op++;
+  g_ops[id] = std::move(e);
+  *op_id = id;
+  return XCT_OK;
+}
+int xct_op_register_3d(const xct3d_geom* g, int64_t* op_id) {
+  if (!g || !op_id) return fail(XCT_ERR_INVALID, "null argument");
+  xct_plan_info info;
+  int rc = xct3d_plan_analyse(g, &info, nullptr);
+  if (rc) return rc;
+  OpEntry e;
+  e.ndim = 3;
+  e.g3 = *g;
+  e.table.assign(g->matrices, g->matrices + 8 * (size_t)g->num_views);
+  std::lock_guard<std::mutex> lock(g_op_mutex);
+  const int64_t id = g_next_op++;
+  g_ops[id] = std::move(e);
+  *op_id = id;
+  return XCT_OK;
+}
+int xct_op_retain(int64_t op_id) {
+  std::lock_guard<std::mutex> lock(g_op_mutex);
+  auto it = g_ops.find(op_id);
+  if (it == g_ops.end()) return fail(XCT_ERR_INVALID, "unknown or released operator id");
+  ++it->second.refs;
+  return XCT_OK;
+}
+int xct_op_release(int64_t op_id) {
+  std::map<int, xct_plan*> dead;
+  {
+    std::lock_guard<std::mutex> lock(g_op_mutex);
+    auto it = g_ops.find(op_id);
+    if (it == g_ops.end()) return fail(XCT_ERR_INVALID, "unknown or released operator id");
+    if (--it->second.refs > 0) return XCT_OK;
+    dead.swap(it->second.plans);
+    g_ops.erase(it);
+  }
+  for (auto& kv : dead) xct_plan_destroy(kv.second);
+  return XCT_OK;
+}
+// The plan of `op_id` on `device`; created (allocates and uploads the geometry tables) on the first call for
+// that device -- call it from an initialize-stage handler, or once before the first execution.
+int xct_op_plan(int64_t op_id, int32_t device, const xct_plan** plan) {
+  if (!plan) return fail(XCT_ERR_INVALID, "null argument");
+  *plan = nullptr;
+  std::lock_guard<std::mutex> lock(g_op_mutex);
+  auto it = g_ops.find(op_id);
+  if (it == g_ops.end()) return fail(XCT_ERR_INVALID, "unknown or released operator id");
+  OpEntry& e = it->second;
+  auto pit = e.plans.find(device);
+  if (pit == e.plans.end()) {
+    xct_plan* pl = nullptr;
+    int rc;
+    if (e.ndim == 2) {
+      xct2d_geom g = e.g2;
+      g.view_table = e.table.data();
+      g.device = device;
+      rc = xct2d_plan_create(&pl, &g);
+    } else {
+      xct3d_geom g = e.g3;
+      g.matrices = e.table.data();
+      g.device = device;
+      rc = xct3d_plan_create(&pl, &g);
+    }
+    if (rc) return rc;
+    pit = e.plans.emplace(device, pl).first;
+  }
+  *plan = pit->second;
+  return XCT_OK;
+}
+// One application on `device`: looks the plan up (it must exist: no allocation here), derives the batch from
+// the element count -- leading batch axes of any rank, as jax.vmap with vmap_method="expand_dims" produces --
+// and enqueues on `stream`.  2D plans take the batch natively; 3D plans run the items one after the other.
+int xct_op_apply(int64_t op_id, int32_t device, int32_t forward, const float* in, float* out, int64_t in_count, void* stream) {
+  const xct_plan* pl = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_op_mutex);
+    auto it = g_ops.find(op_id);
+    if (it == g_ops.end()) return fail(XCT_ERR_INVALID, "unknown or released operator id");
+    auto pit = it->second.plans.find(device);
+    if (pit == it->second.plans.end())
+      return fail(XCT_ERR_INVALID, "operator has no plan on this device (xct_op_plan was not called for it)");
+    pl = pit->second;
+  }
+  const int64_t per_in = forward ? (int64_t)in_elems(pl) : (int64_t)out_elems(pl);
+  const int64_t per_out = forward ? (int64_t)out_elems(pl) : (int64_t)in_elems(pl);
+  if (in_count < per_in || in_count % per_in != 0) return fail(XCT_ERR_INVALID, "operand size is not a multiple of the operator's input");
+  const int64_t batch = in_count / per_in;
+  if (batch > INT32_MAX) return fail(XCT_ERR_INVALID, "batch too large");
+  if (pl->ndim == 2) return forward ? xct_forward(pl, in, out, (int32_t)batch, stream) : xct_adjoint(pl, in, out, (int32_t)batch, stream);
+  for (int64_t b = 0; b < batch; ++b) {
+    const int rc = forward ? xct_forward(pl, in + b * per_in, out + b * per_out, 1, stream)
+                           : xct_adjoint(pl, in + b * per_in, out + b * per_out, 1, stream);
+    if (rc) return rc;
+  }
+  return XCT_OK;
 }
 
 // ---------------------------------------------------------------- TV / PDHG kernels (xct_tv.cuh)

@@ -430,3 +430,30 @@ def test_parallel3d_geometry_is_axis0_separable():
     np.testing.assert_allclose(M, M2, atol=1e-12)
     assert G.is_axis0_separable(M.astype(np.float32))  # exact zeros: no pseudo-inverse noise left
     np.testing.assert_allclose(M[:, 0], np.tile([1.0, 0.0, 0.0, 0.0], (10, 1)), atol=1e-12)
+
+
+def test_operator_registry_ids_lifetime_and_errors_without_a_device():
+    """xct_op_* (what the XLA FFI handlers call): registration validates and COPIES the geometry, ids are never
+    reused, retain / release count references, a released id is an error.  Plans need a device: without one
+    xct_op_plan reports XCT_ERR_NO_DEVICE (no CPU fallback), and applying without a plan is refused."""
+    from scico_b200.jax_ffi import RegisteredOperator
+
+    L = _lib.lib()
+    A = sb.XRayTransform2D((12, 10), np.linspace(0, np.pi, 5, endpoint=False))
+    r1, r2 = RegisteredOperator(A), RegisteredOperator(A)
+    assert r2.id == r1.id + 1 and r1.input_shape == (12, 10) and r1.output_shape == A.output_shape
+    assert L.xct_op_retain(r1.id) == 0
+    r1.release()                                   # one reference left (the retain above)
+    assert L.xct_op_retain(r1.id) == 0 and L.xct_op_release(r1.id) == 0
+    assert L.xct_op_release(r1.id) == 0            # last reference
+    assert L.xct_op_release(r1.id) == _lib.XCT_ERR_INVALID and L.xct_op_retain(r1.id) == _lib.XCT_ERR_INVALID
+    pl = ctypes.c_void_p()
+    if L.xct_device_count() == 0:
+        assert L.xct_op_plan(r2.id, 0, ctypes.byref(pl)) == _lib.XCT_ERR_NO_DEVICE
+    assert L.xct_op_apply(r2.id, 7, 1, None, None, 120, None) == _lib.XCT_ERR_INVALID  # no plan on device 7
+    assert b"no plan on this device" in L.xct_last_error()
+    r3 = RegisteredOperator(sb.XRayTransform3D((4, 5, 6), sb.matrices_from_euler_angles((4, 5, 6), (7, 8), "X", np.zeros((2, 1))), (7, 8)))
+    assert r3.id == r2.id + 1
+    g = _lib.Geom3D()                               # invalid geometry: refused at registration
+    oid = ctypes.c_int64()
+    assert L.xct_op_register_3d(ctypes.byref(g), ctypes.byref(oid)) == _lib.XCT_ERR_INVALID
