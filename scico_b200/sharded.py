@@ -33,6 +33,48 @@ except Exception:  # pragma: no cover
     dist = None
 
 
+class Partition:
+    """What the reference's ``input_device`` / ``output_device`` arguments carry when they are a sharding rather
+    than a device (``scico/linop/xray/_xray2d.py:60-61``, ``_xray3d.py:61-62,132,178``: the arrays are
+    ``jax.device_put`` with it), for one process per GPU: ``XRayTransform3D(..., input_device=Partition("slabs"))``
+    returns the z-slab operator of this rank, ``Partition("views")`` the view-block operator (volume in z-slabs,
+    sinogram in view blocks), ``Partition("auto")`` z-slabs when the geometry is axis-0 separable and view blocks
+    otherwise.  ``XRayTransform2D(..., output_device=Partition("views"))``: view blocks, image replicated.
+
+    group / rank / world_size: the ``torch.distributed`` group (default: the world); exchange / rendezvous: how
+    the view-block back projection meets its owners (``"nccl"``, ``"peer"``, ``"peer_add"``)."""
+
+    def __init__(self, kind: str = "auto", group=None, rank: Optional[int] = None, world_size: Optional[int] = None,
+                 exchange: str = "nccl", rendezvous: str = "flags"):
+        if kind not in ("auto", "slabs", "views"):
+            raise ValueError("Partition kind must be 'auto', 'slabs' or 'views'")
+        self.kind, self.group, self.rank, self.world_size = kind, group, rank, world_size
+        self.exchange, self.rendezvous = exchange, rendezvous
+
+    def __repr__(self):
+        return f"Partition({self.kind!r}, exchange={self.exchange!r})"
+
+
+def partitioned_3d(part: "Partition", input_shape, matrices, det_shape):
+    """The rank-local operator of ``XRayTransform3D`` under ``part`` (see :class:`Partition`)."""
+    kind = part.kind
+    if kind == "auto":
+        kind = "slabs" if geometry.is_axis0_separable(np.asarray(matrices, dtype=np.float32)) else "views"
+    if kind == "slabs":
+        return SlabShardedXRayTransform3D(input_shape, matrices, det_shape, group=part.group, rank=part.rank,
+                                          world_size=part.world_size)
+    return ViewShardedXRayTransform3D(input_shape, matrices, det_shape, group=part.group, rank=part.rank,
+                                      world_size=part.world_size, exchange=part.exchange, rendezvous=part.rendezvous)
+
+
+def partitioned_2d(part: "Partition", input_shape, angles, **kw):
+    """The rank-local operator of ``XRayTransform2D`` under ``part``: view blocks (the only 2D partition)."""
+    if part.kind == "slabs":
+        raise ValueError("a 2D projector has no z-slab partition: use Partition('views')")
+    return ViewShardedXRayTransform2D(input_shape, angles, group=part.group, rank=part.rank, world_size=part.world_size,
+                                      exchange=part.exchange, rendezvous=part.rendezvous, **kw)
+
+
 def block_bounds(n: int, parts: int, index: int) -> tuple[int, int]:
     """Contiguous block ``index`` of ``n`` items split into ``parts`` nearly equal blocks."""
     if not 0 <= index < parts:

@@ -30,6 +30,18 @@ def _is_scalar_equiv(v) -> bool:
     return np.isscalar(v) or (hasattr(v, "ndim") and v.ndim == 0)
 
 
+def _partition_of(input_device, output_device):
+    """The :class:`scico_b200.sharded.Partition` among the two device arguments (None: plain devices)."""
+    from .sharded import Partition
+
+    parts = [d for d in (input_device, output_device) if isinstance(d, Partition)]
+    if not parts:
+        return None
+    if len(parts) == 2 and parts[0] is not parts[1] and (parts[0].kind, parts[0].group) != (parts[1].kind, parts[1].group):
+        raise ValueError("input_device and output_device name different partitions")
+    return parts[0]
+
+
 def _device_index(dev) -> Optional[int]:
     """Ordinal of an ``input_device`` / ``output_device`` argument (None = follow the input)."""
     if dev is None:
@@ -224,6 +236,18 @@ class XRayTransform2D(LinearOperator):
     reference.  `x0`, `dx` and `y0` are in units of the detector spacing ``dy = 1``.
     """
 
+    def __new__(cls, input_shape=None, angles=None, x0=None, dx=None, y0=None, det_count=None,
+                input_device=None, output_device=None, _flags: int = 0):
+        # a sharding in place of a device (reference: jax.device_put(x, sharding), _xray2d.py:60-61,257,298):
+        # the constructor hands back this rank's partitioned operator (scico_b200.sharded.Partition)
+        part = _partition_of(input_device, output_device)
+        if part is not None:
+            from .sharded import partitioned_2d
+
+            kw = {k: v for k, v in dict(x0=x0, dx=dx, y0=y0, det_count=det_count).items() if v is not None}
+            return partitioned_2d(part, input_shape, angles, **kw)
+        return super().__new__(cls)
+
     def __init__(self, input_shape, angles, x0=None, dx=None, y0=None, det_count=None,
                  input_device=None, output_device=None, _flags: int = 0):
         self.input_shape = tuple(input_shape)
@@ -355,6 +379,18 @@ class XRayTransform3D(LinearOperator):
     ``slice_offset`` / ``det_row_offset`` / ``det_rows_total`` expose the reference's unused
     z-slab hook (``_xray3d.py:143,195,208-212``) for multi-GPU sharding.
     """
+
+    def __new__(cls, input_shape=None, matrices=None, det_shape=None, batch_size: int = 8,
+                input_dtype=np.float32, input_device=None, output_device=None, **kw):
+        # a sharding in place of a device (reference: _xray3d.py:61-62,132,178): this rank's partitioned operator
+        part = _partition_of(input_device, output_device)
+        if part is not None:
+            from .sharded import partitioned_3d
+
+            if kw:
+                raise ValueError(f"{sorted(kw)} cannot be combined with a Partition (the partition sets the offsets)")
+            return partitioned_3d(part, input_shape, matrices, det_shape)
+        return super().__new__(cls)
 
     def __init__(self, input_shape, matrices, det_shape, batch_size: int = 8,
                  input_dtype=np.float32, input_device=None, output_device=None, *,

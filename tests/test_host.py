@@ -457,3 +457,33 @@ def test_operator_registry_ids_lifetime_and_errors_without_a_device():
     g = _lib.Geom3D()                               # invalid geometry: refused at registration
     oid = ctypes.c_int64()
     assert L.xct_op_register_3d(ctypes.byref(g), ctypes.byref(oid)) == _lib.XCT_ERR_INVALID
+
+
+def test_device_arguments_accept_a_partition_like_the_reference_accepts_a_sharding():
+    """input_device / output_device (scico/linop/xray/_xray3d.py:61-62): a device ordinal places the arrays, a
+    scico_b200.sharded.Partition makes the constructor return this rank's partitioned operator."""
+    from scico_b200 import sharded
+
+    N, D, V = (16, 12, 10), (16, 14), 6
+    Mx = sb.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, V, endpoint=False)[:, None])
+    Mt = sb.matrices_from_euler_angles(N, D, "XY", np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, 0.4)], 1))
+    P = lambda kind, r: sharded.Partition(kind, rank=r, world_size=4)  # noqa: E731
+    A = sb.XRayTransform3D(N, Mx, D, input_device=P("auto", 1))
+    assert isinstance(A, sharded.SlabShardedXRayTransform3D) and A.slab == (4, 8) and A.rows == (4, 8)
+    assert isinstance(A.local, sb.XRayTransform3D) and A.local.slice_offset == 4 and A.local.det_row_offset == 4
+    B = sb.XRayTransform3D(N, Mt, D, output_device=P("auto", 3))
+    assert isinstance(B, sharded.ViewShardedXRayTransform3D) and B.views == (4, 6) and B.slab == (12, 16)
+    C_ = sb.XRayTransform3D(N, Mx, D, input_device=P("views", 0), output_device=P("views", 0))
+    assert isinstance(C_, sharded.ViewShardedXRayTransform3D) and C_.local_output_shape == (1,) + D
+    with pytest.raises(ValueError):
+        sb.XRayTransform3D(N, Mt, D, input_device=P("slabs", 0))       # not separable
+    with pytest.raises(ValueError):
+        sb.XRayTransform3D(N, Mx, D, input_device=P("slabs", 0), output_device=P("views", 0))
+    with pytest.raises(ValueError):
+        sb.XRayTransform3D(N, Mx, D, input_device=P("slabs", 0), slice_offset=2)
+    E = sb.XRayTransform2D((32, 24), np.linspace(0, np.pi, 8, endpoint=False), det_count=50, output_device=P("views", 2))
+    assert isinstance(E, sharded.ViewShardedXRayTransform2D) and E.views == (4, 6) and E.ny == 50
+    with pytest.raises(ValueError):
+        sb.XRayTransform2D((32, 24), np.linspace(0, np.pi, 8, endpoint=False), input_device=P("slabs", 0))
+    plain = sb.XRayTransform3D(N, Mx, D, input_device=0)
+    assert type(plain) is sb.XRayTransform3D and plain.input_device == 0
