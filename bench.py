@@ -530,7 +530,8 @@ def main():
                               "note": "SURVEY 8(d) per-view streaming model (4 B per update + the sinogram once): NOT a lower "
                                       "bound for kernels that keep voxels in registers across views; kept for reference"}}
 
-    fwd_name = (f"walk_forward_joint_kernel<Geom3> ({n_fwd_launch} class launches per application)" if info.get("fwd_joint")
+    fwd_name = (f"{'walk_forward_tile_kernel' if A.analyse().get('fwd_tile') else 'walk_forward_joint_kernel'}<Geom3> "
+                f"({n_fwd_launch} class launches per application)" if info.get("fwd_joint")
                 else f"{kname[info['fwd_kernel']]}_forward_kernel<Geom3> ({n_fwd_launch} launches per application, one per view class)")
     roofline = {"bound": "issue", "kernel": fwd_name, "sm_clock_mhz_in_timed_region": sm_mhz, "sms": n_sm,
                 "peak_source": "SMs x 4 warp schedulers x the SM clock nvidia-smi reported during the timed region",

@@ -62,6 +62,7 @@ typedef enum xct_status {
 #define XCT_FLAG_NO_HOST_PIPELINE 0x4u /* xct_*_host: one H2D, kernels, one D2H (testing / comparison) */
 #define XCT_FLAG_NO_TMA 0x10u       /* walk adjoint: stage the sinogram window with cp.async, not TMA (testing / comparison) */
 #define XCT_FLAG_NO_JOINT 0x8u      /* walk forward: one column per walk for every view (testing / comparison) */
+#define XCT_FLAG_NO_TILE 0x40u      /* 3D joint forward: register-stationary voxels (TN = 8) instead of the CTA-shared tile (testing / comparison) */
 #define XCT_FLAG_NO_BRICK 0x20u     /* general 3D matrices: thread-per-voxel kernels instead of the brick kernels (testing / comparison) */
 
 /* kernel families a plan can resolve to (xct_plan_info.path) */
@@ -126,6 +127,7 @@ typedef struct xct_plan_classes {
   int32_t rows_consecutive; /* 3D sep: local row = local slice + const per view (TMA box / krow flush) */
   int32_t fwd_cold;         /* some minor coefficient can move the bin by two per step */
   int32_t brick_views[6];   /* general 3D (brick forward): views per class [2*depth_axis + needs_shared_atomics] */
+  int32_t fwd_tile;         /* 3D joint forward runs on a CTA-shared tile of 64 x 32 x 4 voxels (walk_forward_tile_kernel) */
 } xct_plan_classes;
 
 XCT_API int xct_version(void);

@@ -27,6 +27,7 @@ FLAG_NO_WALK = 0x2
 FLAG_NO_HOST_PIPELINE = 0x4
 FLAG_NO_JOINT = 0x8
 FLAG_NO_BRICK = 0x20
+FLAG_NO_TILE = 0x40
 FLAG_NO_TMA = 0x10
 KERNEL_NAMES = {0: "general", 1: "plane", 2: "walk", 3: "brick"}
 
@@ -143,6 +144,7 @@ class PlanClasses(ctypes.Structure):
         ("rows_consecutive", c_int32),
         ("fwd_cold", c_int32),
         ("brick_views", c_int32 * 6),
+        ("fwd_tile", c_int32),
     ]
 
 

@@ -51,6 +51,7 @@ constexpr int kFwd2S = 1, kFwd2TN = 16;
 // walk kernels (xct_plane2.cuh)
 constexpr int kWAdjS = 8, kWAdjTA = 8, kWAdjWin = 64, kWAdjStages = 4;
 constexpr int kWFwdS = 4, kWFwdTN = 8;     // walk forward tile: 64 (major) x 8 (minor) x 4 slices
+constexpr int kWTileTN = 32;               // CTA-shared-tile joint forward: 64 (major) x 32 (minor) x 4 slices per CTA
 constexpr int kW2dTN = 8, kW2dWin = 160;  // 2D joint forward tile: 128 (major) x 8 (minor), one image
 // brick kernels (xct_brick.cuh): general 3D matrices
 constexpr int kBrAdjWR = 20, kBrAdjWC = 24, kBrAdjStages = 4;  // adjoint window of an 8^3 brick (columns start at a multiple of 4), ring depth
@@ -90,6 +91,7 @@ struct xct_plan {
   // joint-column walk forward: views with fjump == 0 by [4*major_b + 2*minor_up + major_positive],
   // the remaining ("risky") views by [2*major_b + minor_up] for walk_forward_kernel
   bool fwd_joint = false;
+  bool fwd_tile = false;     // joint forward with the CTA-shared tile (walk_forward_tile_kernel): unit rows, window fits TN = 32
   bool fwd_joint2d = false;  // 2D: every view inside walk2d_forward_joint_kernel's envelope
   int* d_listJ[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int n_listJ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -456,6 +458,57 @@ int launch_walk_forward_joint_class(const xct_plan* pl, const float* in, float* 
   return launch_ok("walk_forward_joint_kernel");
 }
 
+// joint forward on a CTA-shared tile: one launch per (major axis, minor sign, major sign) class
+template <bool MAJOR_B, bool MINOR_UP, bool MAJ_POS>
+int launch_walk_forward_tile_class(const xct_plan* pl, const float* in, float* out, cudaStream_t st, int s_begin, int s_count) {
+  const int cls = (MAJOR_B ? 4 : 0) + (MINOR_UP ? 2 : 0) + (MAJ_POS ? 1 : 0);
+  if (pl->n_listJ[cls] == 0) return XCT_OK;
+  xct::Walk2Params wp{};
+  wp.p = plane_params(pl, 1);
+  wp.rowoff = pl->d_rowoff;
+  wp.out_scale = 2.0f;
+  wp.row_stride = wp.p.NS;
+  wp.s_base = s_begin;
+  xct::PlaneParams& p = wp.p;
+  if (s_count >= 0) p.NS = s_count;
+  in += (size_t)s_begin * p.NA * p.NB;
+  p.view_list = pl->d_listJ[cls];
+  p.n_list = pl->n_listJ[cls];
+  p.tilesA = ceil_div(p.NA, MAJOR_B ? kWTileTN : 64);
+  p.tilesB = ceil_div(p.NB, MAJOR_B ? 64 : kWTileTN);
+  const long long tiles = (long long)ceil_div(p.NS, kWFwdS) * p.tilesA * p.tilesB;
+  if (tiles > 0x7fffffffLL) return fail(XCT_ERR_INVALID, "volume too large for the tile forward grid");
+  // small problems: split the view list over blockIdx.y so that the grid fills the SMs (8 views run per CTA at a time)
+  int chunks = 1;
+  if (tiles < 148LL * 3) chunks = (int)std::min<long long>((148LL * 3 + tiles - 1) / tiles, std::max(1, p.n_list / (2 * kWarps)));
+  p.views_per_chunk = ceil_div(p.n_list, chunks);
+  chunks = ceil_div(p.n_list, p.views_per_chunk);
+  const size_t smem = ((size_t)kWTileTN * 2 * 32 + (size_t)kWarps * kFwdWin) * sizeof(float4);
+  const dim3 grid((unsigned)tiles, chunks);
+  if (pl->rows_krow) {
+    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWFwdS, kWTileTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_KROW, kWarps>;
+    XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kWarps * 32, smem, st>>>(wp, in, out);
+  } else {
+    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWFwdS, kWTileTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_TABLE, kWarps>;
+    XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kWarps * 32, smem, st>>>(wp, in, out);
+  }
+  return launch_ok("walk_forward_tile_kernel");
+}
+
+int launch_walk_forward_tile(const xct_plan* pl, const float* in, float* out, cudaStream_t st, int s_begin, int s_count) {
+  int rc;
+  if ((rc = launch_walk_forward_tile_class<true, true, true>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_tile_class<true, true, false>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_tile_class<true, false, true>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_tile_class<true, false, false>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_tile_class<false, true, true>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_tile_class<false, true, false>(pl, in, out, st, s_begin, s_count))) return rc;
+  if ((rc = launch_walk_forward_tile_class<false, false, true>(pl, in, out, st, s_begin, s_count))) return rc;
+  return launch_walk_forward_tile_class<false, false, false>(pl, in, out, st, s_begin, s_count);
+}
+
 template <class G, bool IS3D, int S, int TN, int GS, bool MAJOR_B, bool MINOR_UP, bool COLD, bool UNIT4>
 int launch_walk_forward_class(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st,
                               int s_begin, int s_count, bool risky_only = false) {
@@ -547,6 +600,7 @@ int launch_walk_forward3(const xct_plan* pl, const float* in, float* out, cudaSt
   if (pl->fwd_cold) {
     return launch_walk_forward_v<xct::Geom3, true, kWFwdS, kWFwdTN, true, false>(pl, 1, in, out, st, s_begin, s_count);
   }
+  if (pl->fwd_tile && aligned16) return launch_walk_forward_tile(pl, in, out, st, s_begin, s_count);
   if (pl->fwd_joint && aligned16 && (pl->fwd_unit4 || pl->fwd_mix4)) {
     // joint-column kernel; views whose minor coefficient can reach one bin per voxel: 2-bin walk
     int rc = launch_walk_forward_joint(pl, in, out, st, s_begin, s_count);
@@ -983,6 +1037,15 @@ static int plan3d_create_impl(xct_plan** out, const xct3d_geom* g, bool dry) {
       pl->fwd_unit4 = env.fwd_unit4_ok && unit && (g->d1 % 4 == 0);
       pl->fwd_mix4 = env.fwd_unit4_ok && !unit && (g->d1 % 4 == 0);
       pl->fwd_joint = pl->fwd_walk && (pl->fwd_unit4 || pl->fwd_mix4) && !pl->fwd_cold && !(g->flags & XCT_FLAG_NO_JOINT);
+      {  // CTA-shared-tile variant of the joint forward: the window must hold 64 major x 32 minor voxels
+        bool ok = pl->fwd_joint && pl->fwd_unit4 && !(g->flags & XCT_FLAG_NO_TILE);
+        for (const auto& vr : views) {
+          const float mj = std::max(std::fabs(vr.ca), std::fabs(vr.cb)), mn = std::min(std::fabs(vr.ca), std::fabs(vr.cb));
+          if (!(mj * 63.f + mn * (kWTileTN - 1) + 7.f <= (float)kFwdWin)) ok = false;
+        }
+        for (int c = 0; c < 4; ++c) ok = ok && pl->n_listR[c] == 0;  // no view on the two-bin walk
+        pl->fwd_tile = ok;
+      }
       pl->adj_walk = env.adj_ok && env.adj_walk_ok && unit && (g->d1 % 4 == 0) && !(g->flags & XCT_FLAG_NO_WALK);
       pl->adj_tma = pl->adj_tma && pl->adj_walk;  // the TMA box is the walk adjoint's staging
       pl->gs = env.fwd_ok ? env.gs : 0;
@@ -1031,6 +1094,7 @@ static void fill_classes(const xct_plan* pl, xct_plan_classes* c) {
   c->rows_consecutive = pl->rows_krow ? 1 : 0;
   c->fwd_cold = pl->fwd_cold ? 1 : 0;
   for (int k = 0; k < 6; ++k) c->brick_views[k] = pl->n_listB[k];
+  c->fwd_tile = pl->fwd_tile ? 1 : 0;
 }
 int xct_plan_get_classes(const xct_plan* pl, xct_plan_classes* classes) {
   if (!pl || !classes) return fail(XCT_ERR_INVALID, "null argument");

@@ -820,6 +820,189 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
   }
 }
 
+// ----------------------------------------------------------- forward, joint columns, CTA-shared tile
+// walk_forward_joint_kernel keeps a warp's voxels in registers (64 of its 126), which caps a walk at TN = 8
+// steps: per (view, tile) of 2048 updates the window is zeroed and flushed (25 % of the kernel's time), three
+// end-of-walk read-modify-writes are paid (17 %) and the view preamble (8 %).  Here the CTA stages ONE tile of
+// 64 (major) x TN = 32 (minor) x 4 slices in shared memory and its 8 warps run 8 different VIEWS on it, each with
+// a private window: a walk is 32 steps, so the per-(view, tile) costs are spread over 8192 updates, and the
+// registers that held voxels are free (more resident warps).  Price: the two columns' voxels of a step are two
+// LDS.128 instead of register operands.  Layout of the tile: xt[n][column parity][lane] as float4 (4 slices):
+// the lanes of one LDS.128 read 512 contiguous bytes.  Everything else -- the carried triple, the per-view E2
+// variant, the vector flush -- is walk_forward_joint_kernel's.
+template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int ROWS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 3)
+walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __restrict__ sino) {
+  static_assert(WIN % 32 == 0 && S == 4, "float4 window slots, flushed 4 bins per lane");
+  using Vec = float4;
+  constexpr int GS = 2, H = S / 2, Q = WIN / 32, TM = 32 * GS;
+  constexpr int DF = MAJ_POS ? 0 : 1, DG = 1 - DF;
+  const PlaneParams& p = wp.p;
+  extern __shared__ __align__(128) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Vec* xt = reinterpret_cast<Vec*>(smem);                              // [TN][2][32]
+  Vec* winv = reinterpret_cast<Vec*>(smem) + TN * 2 * 32 + warp * WIN;  // [WIN]
+  long long task = blockIdx.x;
+  const int tb_ = (int)(task % p.tilesB);
+  task /= p.tilesB;
+  const int ta = (int)(task % p.tilesA);
+  const int sg = (int)(task / p.tilesA);
+  const int a0 = ta * (MAJOR_B ? TN : TM), b0 = tb_ * (MAJOR_B ? TM : TN), s0 = sg * S;
+
+  // ---- stage the tile (pre-multiplied by the axis-0 row weight), every warp takes TN / WARPS minor rows
+  for (int n = warp; n < TN; n += WARPS) {
+#pragma unroll
+    for (int d = 0; d < GS; ++d) {
+      const int a = MAJOR_B ? a0 + n : a0 + GS * lane + d;
+      const int b = MAJOR_B ? b0 + GS * lane + d : b0 + n;
+      const bool ok = a < p.NA && b < p.NB;
+      float v[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+        v[s] = (ok && s0 + s < p.NS) ? wp.out_scale * __ldg(in + ((size_t)(s0 + s) * p.NA + a) * (size_t)p.NB + b) : 0.f;
+      xt[(n * 2 + d) * 32 + lane] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+  __syncthreads();
+  const float xmin0 = MAJOR_B ? G::coordA(a0) : G::coordB(b0);
+
+  auto rmw = [&](int t, const float2 (&v)[H]) {  // win[t][:] += v   (one lane per address)
+    Vec* q = winv + t;
+    Vec cur = *q;
+    float2* c = reinterpret_cast<float2*>(&cur);
+#pragma unroll
+    for (int h = 0; h < H; ++h) c[h] = __fadd2_rn(c[h], v[h]);
+    *q = cur;
+  };
+  const Vec vzero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float2 zero2 = make_float2(0.f, 0.f);
+
+  const int v_begin = blockIdx.y * p.views_per_chunk;
+  const int v_end = min(p.n_list, v_begin + p.views_per_chunk);
+  for (int vi = v_begin + warp; vi < v_end; vi += WARPS) {
+    const int v = p.view_list ? __ldg(p.view_list + vi) : vi;
+    const ViewRec vr = load_view(p.views + v);
+    const int c0 = window_start<G>(vr, a0, a0 + (MAJOR_B ? TN : TM) - 1, b0, b0 + (MAJOR_B ? TM : TN) - 1) & ~3;
+
+#pragma unroll
+    for (int q = 0; q < Q; ++q) winv[lane + 32 * q] = vzero;
+    __syncwarp();
+
+    const float hF = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + DF) : G::hoistA(vr, a0 + GS * lane + DF);
+    const float hG = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + DG) : G::hoistA(vr, a0 + GS * lane + DG);
+    auto walk_view = [&](auto e2_c) {
+      constexpr bool E2 = decltype(e2_c)::value;
+      float2 A0[H], A1[H], A2[H];  // sums of bins tb, tb + 1, tb + 2
+#pragma unroll
+      for (int h = 0; h < H; ++h) A0[h] = A1[h] = A2[h] = zero2;
+      // bin of F at the first step: the triple starts there (the loop below then never moves at n = 0)
+      int tb;
+      {
+        const float hm = MAJOR_B ? G::hoistA_x(vr, xmin0) : G::hoistB_x(vr, xmin0);
+        const float uF = MAJOR_B ? G::combine(vr, hm, hF) : G::combine(vr, hF, hm);
+        tb = (int)min((unsigned)(__float2int_rd(uF) - c0), (unsigned)(WIN - (E2 ? 4 : 3)));
+      }
+      float xm = xmin0;  // minor-axis coordinate of the step; + 1 is exact
+#pragma unroll 8
+      for (int n = 0; n < TN; ++n, xm += 1.0f) {
+        const Vec xf4 = xt[(n * 2 + DF) * 32 + lane], xg4 = xt[(n * 2 + DG) * 32 + lane];
+        const float2 xF[H] = {make_float2(xf4.x, xf4.y), make_float2(xf4.z, xf4.w)};
+        const float2 xG[H] = {make_float2(xg4.x, xg4.y), make_float2(xg4.z, xg4.w)};
+        const float hm = MAJOR_B ? G::hoistA_x(vr, xm) : G::hoistB_x(vr, xm);
+        const float uF = MAJOR_B ? G::combine(vr, hm, hF) : G::combine(vr, hF, hm);
+        const float uG = MAJOR_B ? G::combine(vr, hm, hG) : G::combine(vr, hG, hm);
+        int cF, cG;
+        float wF0, wF1, wG0, wG1;
+        G::bins(vr, uF, cF, wF0, wF1);
+        G::bins(vr, uG, cG, wG0, wG1);
+        const int tF = (int)min((unsigned)(cF - c0), (unsigned)(WIN - (E2 ? 4 : 3)));
+        const bool e = cG != cF;  // G one bin further
+        if (E2) {
+          const bool far = cG - cF >= 2;
+          if (__any_sync(0xffffffffu, far)) {
+            if (far) {
+              float2 g0[H], g1[H];
+#pragma unroll
+              for (int h = 0; h < H; ++h) {
+                g0[h] = __fmul2_rn(xG[h], make_float2(wG0, wG0));
+                g1[h] = __fmul2_rn(xG[h], make_float2(wG1, wG1));
+              }
+              rmw(tF + 2, g0);
+              rmw(tF + 3, g1);
+            }
+            __syncwarp();
+          }
+          if (far) wG0 = wG1 = 0.f;  // G is accounted for
+        }
+        const float wa = e ? 0.f : wG0, wb = e ? wG0 : wG1, wc = e ? wG1 : 0.f;
+        const float2 wF0p = make_float2(wF0, wF0), wF1p = make_float2(wF1, wF1);
+        const float2 wap = make_float2(wa, wa), wbp = make_float2(wb, wb), wcp = make_float2(wc, wc);
+        if (tF != tb) {  // F moved by one bin: the bin leaving the carried triple is complete for this walk
+          if (MINOR_UP) {
+            rmw(tb, A0);
+#pragma unroll
+            for (int h = 0; h < H; ++h) { A0[h] = A1[h]; A1[h] = A2[h]; A2[h] = zero2; }
+          } else {
+            rmw(tb + 2, A2);
+#pragma unroll
+            for (int h = 0; h < H; ++h) { A2[h] = A1[h]; A1[h] = A0[h]; A0[h] = zero2; }
+          }
+          tb = tF;
+        }
+        __syncwarp();  // order this step's stores before the next step's loads of other lanes
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          A0[h] = __ffma2_rn(xG[h], wap, __ffma2_rn(xF[h], wF0p, A0[h]));
+          A1[h] = __ffma2_rn(xG[h], wbp, __ffma2_rn(xF[h], wF1p, A1[h]));
+          A2[h] = __ffma2_rn(xG[h], wcp, A2[h]);
+        }
+      }
+      rmw(tb, A0);
+      __syncwarp();
+      rmw(tb + 1, A1);
+      __syncwarp();
+      rmw(tb + 2, A2);
+      __syncwarp();
+    };
+    if (vr.fjump != 0.f) walk_view(std::true_type{});
+    else walk_view(std::false_type{});
+
+    // ---- flush the window: lane j owns bins 4j .. 4j+3 (entirely inside or outside [0, D1))
+    const int col = c0 + 4 * lane;
+    if (lane < WIN / 4 && (unsigned)col < (unsigned)p.D1) {
+      float blk[4][S];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const Vec r = winv[4 * lane + k];
+        blk[k][0] = r.x; blk[k][1] = r.y; blk[k][2] = r.z; blk[k][3] = r.w;
+      }
+      if (ROWS == ROWS_KROW) {
+        const int r0 = wp.s_base + s0 + vr.krow;  // local detector row of the group's first slice
+        float* y = sino + ((long long)v * p.D0 + r0) * (long long)p.D1 + col;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
+                               __float_as_uint(blk[3][s]);  // all four +0: nothing to add
+          const bool live = s0 + s < p.NS && (unsigned)(r0 + s) < (unsigned)p.D0 && any != 0u;
+          red_add_v4_if(live, y + (long long)s * p.D1, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+        }
+      } else {
+        const long long* ro = wp.rowoff + (size_t)v * wp.row_stride + wp.s_base;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int sl = min(s0 + s, p.NS - 1);
+          const long long off = __ldg(ro + sl);
+          const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
+                               __float_as_uint(blk[3][s]);
+          const bool live = s0 + s < p.NS && off >= 0 && any != 0u;
+          red_add_v4_if(live, sino + (live ? off : 0) + col, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+        }
+      }
+    }
+    __syncwarp();  // all window reads done before the next view zeroes it
+  }
+}
+
 // ----------------------------------------------------------------- 2D forward, joint column pairs
 // The joint-column walk for a single 2D image (S = 1, nothing to amortise coordinates over): a lane
 // owns FOUR major-axis columns, i.e. two adjacent pairs, 4 voxels apart from its neighbour lane

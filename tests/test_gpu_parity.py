@@ -204,6 +204,36 @@ def test_joint_forward_matches_single_column_walk_and_oracle(torch_dev):
             assert O.rel_l2(a[v], ref[v]) <= TOL, v
 
 
+def test_tile_forward_matches_register_stationary_joint_forward_and_oracle(torch_dev):
+    """walk_forward_tile_kernel (CTA-shared 64 x 32 x 4 tile in shared memory, 8 views per CTA at a time) against
+    walk_forward_joint_kernel (XCT_FLAG_NO_TILE) and the oracle: ragged tiles, a full turn (all eight view
+    classes, E2 views next to the axes), detector rows off centre, a slab with slice / row offsets, few views
+    (views split over blockIdx.y) and one view."""
+    torch, dev = torch_dev
+    rng = np.random.default_rng(31)
+    cases = {name: CASES_3D[name] for name in ("walk_basic", "walk_ragged_tiles", "walk_small_det", "walk_det_rows_offcentre",
+                                               "walk_one_view", "walk_many_slices")}
+    cases["full_turn"] = ((10, 150, 170), (10, 232), lambda: sb.matrices_from_euler_angles(
+        (10, 150, 170), (10, 232), "X", np.linspace(0, 2 * np.pi, 97, endpoint=False)[:, None]))
+    for name, (N, D, mk) in cases.items():
+        M = mk()
+        A, B = sb.XRayTransform3D(N, M, D), sb.XRayTransform3D(N, M, D, _flags=_lib.FLAG_NO_TILE)
+        assert A.analyse()["fwd_tile"] == 1 and B.analyse()["fwd_tile"] == 0 and B.plan_info()["fwd_joint"] == 1, name
+        x = rng.standard_normal(N).astype(np.float32)
+        ya, yb = _gpu(torch, dev, A, x), _gpu(torch, dev, B, x)
+        assert O.rel_l2(ya, yb) <= 1e-6, name
+        assert O.rel_l2(ya, C.project_3d(x, A.matrices, D)) <= TOL, name
+        np.testing.assert_array_equal(ya == 0, yb == 0)
+    # z-slab (what every rank of the slab-sharded operator runs)
+    N, D, V = (96, 70, 90), (96, 128), 21
+    M = _x_mats(N, D, V)
+    S = sb.XRayTransform3D((40,) + N[1:], M, (40, D[1]), slice_offset=30, det_row_offset=30, det_rows_total=D[0])
+    assert S.analyse()["fwd_tile"] == 1
+    x = rng.standard_normal(N).astype(np.float32)
+    want = C.project_3d(x[30:70], S.matrices, D, slice_offset=30)[:, 30:70]
+    assert O.rel_l2(_gpu(torch, dev, S, x[30:70]), want) <= TOL
+
+
 def test_tma_staged_adjoint_is_bit_identical_to_cp_async_staging(torch_dev):
     """The walk adjoint stages its sinogram window either with one TMA box per view (rows of
     consecutive slices consecutive; hardware zero fill at the detector edges) or with per-lane

@@ -21,6 +21,9 @@ def test_headline_geometry_takes_the_walk_joint_tma_path():
     a = sb.XRayTransform3D((n,) * 3, _x((n,) * 3, (n, n), V), (n, n)).analyse()
     assert a["path_name"] == "3d_sep" and a["fwd_kernel"] == 2 and a["adj_kernel"] == 2
     assert a["fwd_joint"] == 1 and a["adj_tma"] == 1 and a["rows_unit"] == 1 and a["rows_consecutive"] == 1
+    assert a["fwd_tile"] == 1  # joint forward on the CTA-shared tile
+    n_ = sb.XRayTransform3D((n,) * 3, _x((n,) * 3, (n, n), V), (n, n), _flags=_lib.FLAG_NO_TILE).analyse()
+    assert n_["fwd_tile"] == 0 and n_["fwd_joint"] == 1
     assert sum(a["joint_views"]) == V and a["two_bin_views"] == [0, 0, 0, 0] and a["fwd_cold"] == 0
     assert sum(1 for c in a["joint_views"] if c) == 4  # half a turn: four (major axis, signs) classes
     assert 0 < a["adj_jump_views"] < V // 16           # only the views next to an axis
