@@ -8,6 +8,7 @@
 #include <map>
 #include <mutex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -1346,7 +1347,12 @@ static int enqueue_host_pipelined(xct_plan* pl, const float* in_host, float* out
   if ((rc = ensure_stage(pl, dir, forward ? n_vol : n_sino, forward ? n_sino : n_vol))) return rc;
   const int NS = pl->n0, D0 = pl->d0, D1 = pl->d1, V = pl->V;
   int chunk = std::max(8, (NS + 15) / 16);
+  if (const char* env = std::getenv("XCT_HOST_CHUNK_SLICES")) {  // tuning / diagnosis (tools/bench_host_pipeline.py)
+    const int v = std::atoi(env);
+    if (v > 0) chunk = v;
+  }
   chunk = (chunk + 7) & ~7;  // whole slice groups of both kernels (S = 4 / 8)
+  chunk = std::max(chunk, ((NS + 63) / 64 + 7) & ~7);  // at most 64 chunks (event table)
   const int nchunks = ceil_div(NS, chunk);
   const size_t ev_base = dir ? 2 * 64 : 0;  // each direction owns its events
   while (pl->events.size() < 4 * 64) {
