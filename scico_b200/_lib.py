@@ -12,7 +12,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint32, c_voi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libscico_b200_xray.so"
-LIB_PATH = os.path.join(_HERE, LIB_NAME)
+# SCICO_B200_LIB: another build of the same library (kernel A/B runs, tools/); the product loads the in-tree one
+LIB_PATH = os.environ.get("SCICO_B200_LIB") or os.path.join(_HERE, LIB_NAME)
 
 XCT_OK = 0
 XCT_ERR_INVALID = -1

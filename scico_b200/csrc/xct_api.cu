@@ -52,7 +52,14 @@ constexpr int kFwd2S = 1, kFwd2TN = 16;
 // walk kernels (xct_plane2.cuh)
 constexpr int kWAdjS = 8, kWAdjTA = 8, kWAdjWin = 64, kWAdjStages = 4;
 constexpr int kWFwdS = 4, kWFwdTN = 8;     // walk forward tile: 64 (major) x 8 (minor) x 4 slices
-constexpr int kWTileTN = 32;               // CTA-shared-tile joint forward: 64 (major) x 32 (minor) x 4 slices per CTA
+// CTA-shared-tile joint forward: 64 (major) x kWTileTN (minor) x 4 slices per CTA, kWTileWarps views in flight per CTA
+#ifndef XCT_TILE_TN
+#define XCT_TILE_TN 64    // measured at C5 (tools/bench_fwd_ab.py, ms per application): TN 16: 359, 32: 319, 64: 304
+#define XCT_TILE_WIN 128  // window of the 64 x 64 tile: 63 (|c_major| + |c_minor|) + 7 <= 128 for every rotation
+#define XCT_TILE_WARPS 12 // views in flight per CTA; 2 CTAs per SM = 24 warps (24 warps in one CTA: 321)
+#define XCT_TILE_MINB 2
+#endif
+constexpr int kWTileTN = XCT_TILE_TN, kWTileWin = XCT_TILE_WIN, kWTileWarps = XCT_TILE_WARPS, kWTileMinB = XCT_TILE_MINB;
 constexpr int kW2dTN = 8, kW2dWin = 160;  // 2D joint forward tile: 128 (major) x 8 (minor), one image
 // brick kernels (xct_brick.cuh): general 3D matrices
 constexpr int kBrAdjWR = 20, kBrAdjWC = 24, kBrAdjStages = 4;  // adjoint window of an 8^3 brick (columns start at a multiple of 4), ring depth
@@ -481,19 +488,19 @@ int launch_walk_forward_tile_class(const xct_plan* pl, const float* in, float* o
   if (tiles > 0x7fffffffLL) return fail(XCT_ERR_INVALID, "volume too large for the tile forward grid");
   // small problems: split the view list over blockIdx.y so that the grid fills the SMs (8 views run per CTA at a time)
   int chunks = 1;
-  if (tiles < 148LL * 3) chunks = (int)std::min<long long>((148LL * 3 + tiles - 1) / tiles, std::max(1, p.n_list / (2 * kWarps)));
+  if (tiles < 148LL * 3) chunks = (int)std::min<long long>((148LL * 3 + tiles - 1) / tiles, std::max(1, p.n_list / (2 * kWTileWarps)));
   p.views_per_chunk = ceil_div(p.n_list, chunks);
   chunks = ceil_div(p.n_list, p.views_per_chunk);
-  const size_t smem = ((size_t)kWTileTN * 2 * 32 + (size_t)kWarps * kFwdWin) * sizeof(float4);
+  const size_t smem = ((size_t)kWTileTN * 2 * 32 + (size_t)kWTileWarps * kWTileWin) * sizeof(float4);
   const dim3 grid((unsigned)tiles, chunks);
   if (pl->rows_krow) {
-    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWFwdS, kWTileTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_KROW, kWarps>;
+    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWFwdS, kWTileTN, kWTileWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_KROW, kWTileWarps, kWTileMinB>;
     XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kWarps * 32, smem, st>>>(wp, in, out);
+    kern<<<grid, kWTileWarps * 32, smem, st>>>(wp, in, out);
   } else {
-    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWFwdS, kWTileTN, kFwdWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_TABLE, kWarps>;
+    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWFwdS, kWTileTN, kWTileWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_TABLE, kWTileWarps, kWTileMinB>;
     XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kWarps * 32, smem, st>>>(wp, in, out);
+    kern<<<grid, kWTileWarps * 32, smem, st>>>(wp, in, out);
   }
   return launch_ok("walk_forward_tile_kernel");
 }
@@ -1042,7 +1049,7 @@ static int plan3d_create_impl(xct_plan** out, const xct3d_geom* g, bool dry) {
         bool ok = pl->fwd_joint && pl->fwd_unit4 && !(g->flags & XCT_FLAG_NO_TILE);
         for (const auto& vr : views) {
           const float mj = std::max(std::fabs(vr.ca), std::fabs(vr.cb)), mn = std::min(std::fabs(vr.ca), std::fabs(vr.cb));
-          if (!(mj * 63.f + mn * (kWTileTN - 1) + 7.f <= (float)kFwdWin)) ok = false;
+          if (!(mj * 63.f + mn * (kWTileTN - 1) + 7.f <= (float)kWTileWin)) ok = false;
         }
         for (int c = 0; c < 4; ++c) ok = ok && pl->n_listR[c] == 0;  // no view on the two-bin walk
         pl->fwd_tile = ok;

@@ -824,16 +824,16 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
 // walk_forward_joint_kernel keeps a warp's voxels in registers (64 of its 126), which caps a walk at TN = 8
 // steps: per (view, tile) of 2048 updates the window is zeroed and flushed (25 % of the kernel's time), three
 // end-of-walk read-modify-writes are paid (17 %) and the view preamble (8 %).  Here the CTA stages ONE tile of
-// 64 (major) x TN = 32 (minor) x 4 slices in shared memory and its 8 warps run 8 different VIEWS on it, each with
-// a private window: a walk is 32 steps, so the per-(view, tile) costs are spread over 8192 updates, and the
+// 64 (major) x TN = 64 (minor) x 4 slices in shared memory and its 12 warps run 12 different VIEWS on it, each with
+// a private window: a walk is 64 steps, so the per-(view, tile) costs are spread over 16384 updates, and the
 // registers that held voxels are free (more resident warps).  Price: the two columns' voxels of a step are two
 // LDS.128 instead of register operands.  Layout of the tile: xt[n][column parity][lane] as float4 (4 slices):
 // the lanes of one LDS.128 read 512 contiguous bytes.  Everything else -- the carried triple, the per-view E2
 // variant, the vector flush -- is walk_forward_joint_kernel's.
-template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int ROWS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 3)
+template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int ROWS, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __restrict__ sino) {
-  static_assert(WIN % 32 == 0 && S == 4, "float4 window slots, flushed 4 bins per lane");
+  static_assert(WIN % 32 == 0 && WIN <= 128 && S == 4, "float4 window slots, flushed 4 bins per lane in one pass");
   using Vec = float4;
   constexpr int GS = 2, H = S / 2, Q = WIN / 32, TM = 32 * GS;
   constexpr int DF = MAJ_POS ? 0 : 1, DG = 1 - DF;
