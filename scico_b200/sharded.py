@@ -358,6 +358,11 @@ class PeerBlocks:
             pass
         if both:
             dist.barrier(group=self.group)
+        timed_out = False
+        try:  # a rendezvous that gave up on a peer has produced incomplete sums: say so, never silently
+            timed_out = bool(getattr(self.mem, "timed_out", lambda: False)())
+        except Exception:
+            pass
         for q in self._mapped:
             self.mem.close(q)
         if both:
@@ -366,6 +371,9 @@ class PeerBlocks:
             self.mem.free(q)
         self.mem.free(self._flags_own)
         self._mapped, self._own = [], []
+        if timed_out and collective:
+            raise RuntimeError(f"PeerBlocks: a flag rendezvous timed out after {self.timeout_s} s (a peer rank stopped "
+                               "taking part in the exchange); results since then are incomplete")
 
     def __del__(self):
         try:
