@@ -63,6 +63,7 @@ typedef enum xct_status {
 #define XCT_FLAG_NO_TMA 0x10u       /* walk adjoint: stage the sinogram window with cp.async, not TMA (testing / comparison) */
 #define XCT_FLAG_NO_JOINT 0x8u      /* walk forward: one column per walk for every view (testing / comparison) */
 #define XCT_FLAG_NO_TILE 0x40u      /* 3D joint forward: register-stationary voxels (TN = 8) instead of the CTA-shared tile (testing / comparison) */
+#define XCT_FLAG_2D_PER_CLASS 0x80u  /* 2D joint forward: one launch per view class even for small problems (testing / comparison) */
 #define XCT_FLAG_NO_BRICK 0x20u     /* general 3D matrices: thread-per-voxel kernels instead of the brick kernels (testing / comparison) */
 
 /* kernel families a plan can resolve to (xct_plan_info.path) */

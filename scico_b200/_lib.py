@@ -29,6 +29,7 @@ FLAG_NO_HOST_PIPELINE = 0x4
 FLAG_NO_JOINT = 0x8
 FLAG_NO_BRICK = 0x20
 FLAG_NO_TILE = 0x40
+FLAG_2D_PER_CLASS = 0x80
 FLAG_NO_TMA = 0x10
 KERNEL_NAMES = {0: "general", 1: "plane", 2: "walk", 3: "brick"}
 

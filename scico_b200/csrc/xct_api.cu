@@ -101,6 +101,7 @@ struct xct_plan {
   bool fwd_joint = false;
   bool fwd_tile = false;     // joint forward with the CTA-shared tile (walk_forward_tile_kernel): unit rows, window fits TN = 32
   bool fwd_joint2d = false;  // 2D: every view inside walk2d_forward_joint_kernel's envelope
+  bool fwd_2d_per_class = false;  // XCT_FLAG_2D_PER_CLASS: one launch per view class even for small problems (A/B)
   int* d_listJ[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int n_listJ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int* d_listR[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -575,7 +576,49 @@ int launch_walk2d_forward_class(const xct_plan* pl, int batch, const float* in, 
   return launch_ok("walk2d_forward_joint_kernel");
 }
 
+// Parameters of one class of the 2D joint forward (shared by the per-class and the one-launch path)
+template <bool MAJOR_B>
+int walk2d_class_params(const xct_plan* pl, int batch, int cls, xct::PlaneParams& p, int& blocks, int& chunks) {
+  p = plane_params(pl, batch);
+  p.view_list = pl->d_listJ[cls];
+  p.n_list = pl->n_listJ[cls];
+  p.tilesA = ceil_div(p.NA, MAJOR_B ? kW2dTN : 128);
+  p.tilesB = ceil_div(p.NB, MAJOR_B ? 128 : kW2dTN);
+  const long long tasks = (long long)p.NS * p.tilesA * p.tilesB;
+  blocks = ceil_div(tasks, kWarps);
+  const long long target_warps = 148LL * 32;
+  chunks = 1;
+  if (tasks < target_warps) chunks = (int)std::min<long long>((target_warps + tasks - 1) / tasks, std::max(1, p.n_list / 4));
+  p.views_per_chunk = ceil_div(p.n_list, chunks);
+  chunks = ceil_div(p.n_list, p.views_per_chunk);
+  return XCT_OK;
+}
+
+// small problems: all view classes in ONE launch (walk2d_forward_joint_all_kernel)
+int launch_walk2d_forward_all(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+  xct::Walk2dAllParams ap{};
+  int total = 0;
+  for (int cls = 0; cls < 8; ++cls) {
+    ap.block_begin[cls] = total;
+    ap.blocks_x[cls] = 1;
+    if (pl->n_listJ[cls] == 0) continue;
+    int blocks = 0, chunks = 0;
+    if (cls & 4) walk2d_class_params<true>(pl, batch, cls, ap.p[cls], blocks, chunks);
+    else walk2d_class_params<false>(pl, batch, cls, ap.p[cls], blocks, chunks);
+    ap.blocks_x[cls] = blocks;
+    total += blocks * chunks;
+  }
+  ap.block_begin[8] = total;
+  if (total == 0) return XCT_OK;
+  const size_t smem = (size_t)kWarps * kW2dWin * sizeof(float);
+  xct::walk2d_forward_joint_all_kernel<xct::Geom2, kW2dTN, kW2dWin, kWarps><<<total, kWarps * 32, smem, st>>>(ap, in, out);
+  return launch_ok("walk2d_forward_joint_all_kernel");
+}
+
 int launch_walk2d_forward(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+  // below ~2 waves of CTAs per class the per-launch ramp-up and tail dominate: one launch for all classes
+  if ((long long)batch * pl->n0 * pl->n1 * pl->V <= (1LL << 29) && !pl->fwd_2d_per_class)
+    return launch_walk2d_forward_all(pl, batch, in, out, st);
   int rc;
   if ((rc = launch_walk2d_forward_class<true, true, true>(pl, batch, in, out, st))) return rc;
   if ((rc = launch_walk2d_forward_class<true, true, false>(pl, batch, in, out, st))) return rc;
@@ -877,6 +920,7 @@ static int plan2d_create_impl(xct_plan** out, const xct2d_geom* g, bool dry) {
       if (vr.fjump != 0.f || 4.f * mj < 1.01f || mj * 127.f + mn * (kW2dTN - 1) + 4.f > (float)kW2dWin) ok = false;
     }
     pl->fwd_joint2d = ok;
+    pl->fwd_2d_per_class = (g->flags & XCT_FLAG_2D_PER_CLASS) != 0;
   }
 
   auto cleanup = [&](int code) { xct_plan_destroy(pl); return code; };

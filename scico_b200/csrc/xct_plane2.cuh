@@ -1015,15 +1015,16 @@ walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __
 // bank-conflict replays) the shared traffic drops to one RMW per bin change.
 // Window: WIN bins (floats) per warp; flushed with scalar RED (2D rows have no 16-byte alignment).
 // Only for plans whose every view has |coefficients| <= 1 - 5 ulp(u) (ViewRec::fjump == 0).
+// (body shared by the per-class kernel and by the one-launch kernel for small problems below; block_x / chunk_y
+// are the CTA's position in the class's own (blocks, view chunks) grid)
 template <class G, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-walk2d_forward_joint_kernel(PlaneParams p, const float* __restrict__ in, float* __restrict__ sino) {
+__device__ __forceinline__ void walk2d_forward_joint_body(const PlaneParams& p, const float* __restrict__ in,
+                                                          float* __restrict__ sino, float* smem, int block_x, int chunk_y) {
   static_assert(WIN % 32 == 0, "window is flushed 32 bins at a time");
   constexpr int GS = 4, TM = 32 * GS, Q = WIN / 32;
-  extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long ntasks = (long long)p.NS * p.tilesA * p.tilesB;
-  long long task = (long long)blockIdx.x * WARPS + warp;
+  long long task = (long long)block_x * WARPS + warp;
   if (task >= ntasks) return;
   const int tb_ = (int)(task % p.tilesB);
   task /= p.tilesB;
@@ -1045,7 +1046,7 @@ walk2d_forward_joint_kernel(PlaneParams p, const float* __restrict__ in, float* 
 
   auto rmw = [&](int t, float v) { win[t] += v; };  // one lane per address
 
-  const int v_begin = blockIdx.y * p.views_per_chunk;
+  const int v_begin = chunk_y * p.views_per_chunk;
   const int v_end = min(p.n_list, v_begin + p.views_per_chunk);
   for (int vi = v_begin; vi < v_end; ++vi) {
     const int v = p.view_list ? __ldg(p.view_list + vi) : vi;
@@ -1110,6 +1111,43 @@ walk2d_forward_joint_kernel(PlaneParams p, const float* __restrict__ in, float* 
       if (val != 0.f && (unsigned)col < (unsigned)p.D1) atomicAdd(y0 + col, val);
     }
     __syncwarp();  // all window reads done before the next view zeroes it
+  }
+}
+
+template <class G, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+walk2d_forward_joint_kernel(PlaneParams p, const float* __restrict__ in, float* __restrict__ sino) {
+  extern __shared__ __align__(128) float smem[];
+  walk2d_forward_joint_body<G, TN, WIN, MAJOR_B, MINOR_UP, MAJ_POS, WARPS>(p, in, sino, smem, blockIdx.x, blockIdx.y);
+}
+
+// Small problems (BASELINE.json configs[1]: 512^2 x 360 views is ~0.1 ms of work): ONE launch for all eight
+// (major axis, minor sign, major sign) view classes instead of one launch each -- every class brings its own
+// ramp-up and tail, and four to eight of them are a third of the operator's time at this size.  A CTA looks its
+// class up in a prefix table of CTA counts and runs that class's instantiation of the body.
+struct Walk2dAllParams {
+  PlaneParams p[8];      // per class: view list, tile grid, views per chunk
+  int block_begin[9];    // CTAs of class k: [block_begin[k], block_begin[k + 1])
+  int blocks_x[8];       // class k's CTA grid is blocks_x[k] (tiles) x chunks (view chunks)
+};
+template <class G, int TN, int WIN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+walk2d_forward_joint_all_kernel(const __grid_constant__ Walk2dAllParams ap, const float* __restrict__ in, float* __restrict__ sino) {
+  extern __shared__ __align__(128) float smem[];
+  int k = 0;
+#pragma unroll
+  for (int q = 1; q < 8; ++q) k += (int)blockIdx.x >= ap.block_begin[q] ? 1 : 0;
+  const int local = (int)blockIdx.x - ap.block_begin[k];
+  const int bx = local % ap.blocks_x[k], cy = local / ap.blocks_x[k];
+  switch (k) {  // k = 4 * major_b + 2 * minor_up + major_positive
+    case 0: walk2d_forward_joint_body<G, TN, WIN, false, false, false, WARPS>(ap.p[0], in, sino, smem, bx, cy); break;
+    case 1: walk2d_forward_joint_body<G, TN, WIN, false, false, true, WARPS>(ap.p[1], in, sino, smem, bx, cy); break;
+    case 2: walk2d_forward_joint_body<G, TN, WIN, false, true, false, WARPS>(ap.p[2], in, sino, smem, bx, cy); break;
+    case 3: walk2d_forward_joint_body<G, TN, WIN, false, true, true, WARPS>(ap.p[3], in, sino, smem, bx, cy); break;
+    case 4: walk2d_forward_joint_body<G, TN, WIN, true, false, false, WARPS>(ap.p[4], in, sino, smem, bx, cy); break;
+    case 5: walk2d_forward_joint_body<G, TN, WIN, true, false, true, WARPS>(ap.p[5], in, sino, smem, bx, cy); break;
+    case 6: walk2d_forward_joint_body<G, TN, WIN, true, true, false, WARPS>(ap.p[6], in, sino, smem, bx, cy); break;
+    default: walk2d_forward_joint_body<G, TN, WIN, true, true, true, WARPS>(ap.p[7], in, sino, smem, bx, cy); break;
   }
 }
 

@@ -367,6 +367,31 @@ def test_brick_kernels_selected_and_match_thread_per_voxel_kernels(torch_dev):
     assert O.rel_l2(_gpu(torch, dev, S, np.ascontiguousarray(full_y[:, r0:r1]), adj=True), want_a) <= TOL
 
 
+def test_2d_one_launch_forward_matches_per_class_launches(torch_dev):
+    """Small 2D problems run all eight view classes in ONE launch (walk2d_forward_joint_all_kernel); XCT_FLAG_2D_PER_CLASS
+    keeps one launch per class.  Same results (up to the order of the REDs), full turn = all eight classes, batch."""
+    torch, dev = torch_dev
+    rng = np.random.default_rng(41)
+    for nx, V, span, batch in (((512, 512), 360, np.pi, 1), ((96, 130), 64, 2 * np.pi, 1), ((130, 70), 40, 2 * np.pi, 3)):
+        ang = np.linspace(0, span, V, endpoint=False)
+        A, B = sb.XRayTransform2D(nx, ang), sb.XRayTransform2D(nx, ang, _flags=_lib.FLAG_2D_PER_CLASS)
+        assert A.plan_info()["fwd_joint"] == 1 and B.plan_info()["fwd_joint"] == 1
+        x = rng.standard_normal(((batch,) if batch > 1 else ()) + nx).astype(np.float32)
+        L = _lib.lib()
+        xt = torch.as_tensor(x, device=dev)
+        L.xct_launch_count_reset()
+        ya = A.project(xt).cpu().numpy()  # .project: accepts the leading batch axis
+        la = L.xct_launch_count()
+        L.xct_launch_count_reset()
+        yb = B.project(xt).cpu().numpy()
+        lb = L.xct_launch_count()
+        assert la == 1 and lb >= 4, (la, lb)
+        assert O.rel_l2(ya, yb) <= 1e-6
+        x0 = x if batch == 1 else x[1]
+        y0 = ya if batch == 1 else ya[1]
+        assert O.rel_l2(y0, C.project_2d(x0, A.view_table, A.ny)) <= TOL
+
+
 def test_3d_paths_selected(torch_dev):
     A = sb.XRayTransform3D((16,) * 3, _x_mats((16,) * 3, (16, 16), 4), (16, 16))
     assert A.plan_info()["path_name"] == "3d_sep" and A.plan_info()["row_aligned"] == 1
