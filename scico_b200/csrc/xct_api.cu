@@ -315,7 +315,8 @@ int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* 
   const long long tasks = (long long)ceil_div(p.NS, S) * p.tilesA * p.tilesB;
   const int blocks = ceil_div(tasks, kWarps);
   // small problems: split the views over blockIdx.y (partial sums meet in the zeroed output via RED)
-  const long long target_warps = 148LL * 32;
+  long long target_warps = 148LL * 64;  // two waves of resident warps; measured at C2: 1184 / 2368 / 3552 / 4736 / 7104 / 9472 / 14208 -> 134 / 103 / 98 / 90 / 85 / 82 / 83 us
+  if (const char* env = std::getenv("XCT_ADJ_TARGET_WARPS")) target_warps = std::max(1, std::atoi(env));  // tuning (tools/bench_c2.py)
   int chunks = 1;
   if (tasks < target_warps) chunks = (int)std::min<long long>((target_warps + tasks - 1) / tasks, std::max(1, p.n_list / 8));
   p.views_per_chunk = ceil_div(p.n_list, chunks);
@@ -597,14 +598,30 @@ int walk2d_class_params(const xct_plan* pl, int batch, int cls, xct::PlaneParams
 // small problems: all view classes in ONE launch (walk2d_forward_joint_all_kernel)
 int launch_walk2d_forward_all(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
   xct::Walk2dAllParams ap{};
+  // view chunks: the classes fill the GPU TOGETHER, so the warps of all classes are sized to a whole number of
+  // waves of resident warps (148 SMs x 24) instead of each class to its own wave
+  long long total_tasks = 0;
+  for (int cls = 0; cls < 8; ++cls) {
+    if (pl->n_listJ[cls] == 0) continue;
+    int blocks = 0, chunks = 0;
+    if (cls & 4) walk2d_class_params<true>(pl, batch, cls, ap.p[cls], blocks, chunks);
+    else walk2d_class_params<false>(pl, batch, cls, ap.p[cls], blocks, chunks);
+    total_tasks += (long long)blocks * kWarps;
+  }
+  double waves = 1.5;  // measured at C2 (tools/bench_c2.py): 0.5 / 1 / 2 / 3 / 4 / 6 waves -> 101 / 97 / 99 / 99 / 115 / 110 us
+  if (const char* env = std::getenv("XCT_2D_ALL_WAVES")) waves = std::max(0.25, std::atof(env));  // tuning (tools/bench_c2.py)
+  const int want_chunks = total_tasks > 0 ? (int)std::max<long long>(1, (long long)(waves * 148 * 24 + total_tasks / 2) / total_tasks) : 1;
   int total = 0;
   for (int cls = 0; cls < 8; ++cls) {
     ap.block_begin[cls] = total;
     ap.blocks_x[cls] = 1;
     if (pl->n_listJ[cls] == 0) continue;
-    int blocks = 0, chunks = 0;
-    if (cls & 4) walk2d_class_params<true>(pl, batch, cls, ap.p[cls], blocks, chunks);
-    else walk2d_class_params<false>(pl, batch, cls, ap.p[cls], blocks, chunks);
+    xct::PlaneParams& p = ap.p[cls];
+    const long long tasks = (long long)p.NS * p.tilesA * p.tilesB;
+    const int blocks = ceil_div(tasks, kWarps);
+    int chunks = std::min(want_chunks, std::max(1, p.n_list / 4));
+    p.views_per_chunk = ceil_div(p.n_list, chunks);
+    chunks = ceil_div(p.n_list, p.views_per_chunk);
     ap.blocks_x[cls] = blocks;
     total += blocks * chunks;
   }
