@@ -1402,7 +1402,7 @@ int xct_peer_free(int32_t device, void* ptr) {
 }
 
 // Pipelined host path for 3D separable plans with unit, monotone rows: the volume is cut into >= 8
-// chunks of slices (16 for the headline shapes); chunk k's kernels (stream hstream) overlap the H2D copy of
+// chunks of slices (32 for the headline shape, 16 for a 128-slice slab); chunk k's kernels (stream hstream) overlap the H2D copy of
 // chunk k+1 (stream s_in) and the D2H copy of what chunk k-1 completed (stream s_out).  Detector rows of a
 // slice chunk are a row block of every view: strided 2D copies with the view pitch.  Nothing here waits for
 // the device: the three streams carry the calls of a plan in order, so a forward and an adjoint enqueued back
@@ -1414,7 +1414,7 @@ static int enqueue_host_pipelined(xct_plan* pl, const float* in_host, float* out
   const size_t n_vol = in_elems(pl), n_sino = out_elems(pl);
   if ((rc = ensure_stage(pl, dir, forward ? n_vol : n_sino, forward ? n_sino : n_vol))) return rc;
   const int NS = pl->n0, D0 = pl->d0, D1 = pl->d1, V = pl->V;
-  int chunk = std::max(8, (NS + 15) / 16);
+  int chunk = std::max(8, (NS + 31) / 32);  // 1024 slices, one GPU: chunks of 8 / 16 / 32 / 64 slices -> 553.7 / 553.5 / 547.7 / 552.3 ms per pair
   if (const char* env = std::getenv("XCT_HOST_CHUNK_SLICES")) {  // tuning / diagnosis (tools/bench_host_pipeline.py)
     const int v = std::atoi(env);
     if (v > 0) chunk = v;
