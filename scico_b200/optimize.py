@@ -170,10 +170,11 @@ class _TVSolver:
 
     # -- operator applications -------------------------------------------------------------------
     def _fwd(self, x, out):
-        return self.A.project(x) if self.sharded else self.A.project(x, out=out)
+        return self.A.project(x, out=out)  # plain and sharded operators write into the solver's own buffer
 
     def _adj(self, y, out):
-        return self.A.back_project(y) if self.sharded else self.A.back_project(y, out=out)
+        res = self.A.back_project(y, out=out)
+        return res if res is not None else out
 
     #: an iteration never needs the host (no scalar read back): it can be captured in a CUDA graph
     _graphable = False

@@ -195,19 +195,20 @@ class SlabShardedXRayTransform3D:
             y[:, lo - self.rows[0]:hi - self.rows[0], :] += recv
         return y
 
-    def project(self, x_local):
+    def project(self, x_local, out=None):
+        """``out``: optional preallocated local sinogram block (solvers reuse one buffer per iteration)."""
         if tuple(x_local.shape) != self.local_input_shape:
             raise ValueError(f"local slab of shape {tuple(x_local.shape)} does not match {self.local_input_shape}")
         if self.local is None:
-            return x_local.new_zeros(self.local_output_shape)
-        return self._exchange_halo_sum(self.local.project(x_local))
+            return x_local.new_zeros(self.local_output_shape) if out is None else out.zero_()
+        return self._exchange_halo_sum(self.local.project(x_local, out=out) if out is not None else self.local.project(x_local))
 
-    def back_project(self, y_local):
+    def back_project(self, y_local, out=None):
         if tuple(y_local.shape) != self.local_output_shape:
             raise ValueError(f"local sinogram of shape {tuple(y_local.shape)} does not match {self.local_output_shape}")
         if self.local is None:
-            return y_local.new_zeros(self.local_input_shape)
-        return self.local.back_project(y_local)
+            return y_local.new_zeros(self.local_input_shape) if out is None else out.zero_()
+        return self.local.back_project(y_local, out=out) if out is not None else self.local.back_project(y_local)
 
     __call__ = project
     adj = back_project
@@ -487,9 +488,18 @@ class _ViewSharded:
         if self.world_size == 1:
             return x_slab
         pad = max(z1 - z0 for z0, z1 in self.slabs)
-        buf = x_slab.new_zeros((pad,) + tuple(x_slab.shape[1:]))
-        buf[: x_slab.shape[0]] = x_slab
-        out = x_slab.new_empty((self.world_size * pad,) + tuple(x_slab.shape[1:]))
+        even = all(z1 - z0 == pad for z0, z1 in self.slabs)
+        key = (tuple(x_slab.shape), x_slab.device, x_slab.dtype)
+        if getattr(self, "_gather_key", None) != key:  # one padded send buffer and one gather buffer per operator
+            self._gather_key = key
+            self._gather_pad = None if even else x_slab.new_zeros((pad,) + tuple(x_slab.shape[1:]))
+            self._gather_out = x_slab.new_empty((self.world_size * pad,) + tuple(x_slab.shape[1:]))
+        if even:
+            buf = x_slab.contiguous()
+        else:
+            buf = self._gather_pad
+            buf[: x_slab.shape[0]] = x_slab
+        out = self._gather_out
         dist.all_gather_into_tensor(out, buf, group=self.group)
         if all(z1 - z0 == pad for z0, z1 in self.slabs):
             return out
@@ -546,20 +556,21 @@ class ViewShardedXRayTransform3D(_ViewSharded):
             for a, b in self.slabs
         ]
 
-    def project(self, x_slab):
+    def project(self, x_slab, out=None):
         if tuple(x_slab.shape) != self.local_input_shape:
             raise ValueError(f"local slab of shape {tuple(x_slab.shape)} does not match {self.local_input_shape}")
         x = self._gather_volume(x_slab)
         if self.full is None:
-            return x_slab.new_zeros(self.local_output_shape)
-        return self.full.project(x)
+            return x_slab.new_zeros(self.local_output_shape) if out is None else out.zero_()
+        return self.full.project(x, out=out) if out is not None else self.full.project(x)
 
-    def back_project(self, y_views):
+    def back_project(self, y_views, out=None):
         if tuple(y_views.shape) != self.local_output_shape:
             raise ValueError(f"local views of shape {tuple(y_views.shape)} do not match {self.local_output_shape}")
 
         if self.peer is not None:  # fused: the kernel adds every slice into its owner's slab over NVLink
-            out = y_views.new_empty(self.local_input_shape)
+            if out is None:
+                out = y_views.new_empty(self.local_input_shape)
             launch = (lambda ptrs, rb, st: self.full.back_project_scatter(y_views, ptrs, rb, st)) if self.full is not None \
                 else (lambda ptrs, rb, st: None)
             return self.peer.exchange(launch, out)
@@ -570,7 +581,11 @@ class ViewShardedXRayTransform3D(_ViewSharded):
                 return y_views.new_zeros((b - a,) + self.input_shape[1:])
             return self.per_slab[j].back_project(y_views)
 
-        return self._reduce_slabs(part)
+        res = self._reduce_slabs(part)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
 
     __call__ = project
     adj = back_project
@@ -602,18 +617,26 @@ class ViewShardedXRayTransform2D(_ViewSharded):
         factory = op_factory or _native_2d
         self.local = factory(self.input_shape, self.angles[v0:v1], **kw) if v1 > v0 else None
 
-    def project(self, x):
+    def project(self, x, out=None):
         if tuple(x.shape) != self.input_shape:
             raise ValueError(f"image of shape {tuple(x.shape)} does not match {self.input_shape}")
         if self.local is None:
-            return x.new_zeros(self.local_output_shape)
-        return self.local.project(x)
+            return x.new_zeros(self.local_output_shape) if out is None else out.zero_()
+        return self.local.project(x, out=out) if out is not None else self.local.project(x)
 
-    def back_project(self, y_views, scatter: bool = True):
+    def back_project(self, y_views, scatter: bool = True, out=None):
+        res = self._back_project(y_views, scatter, out)
+        if out is not None and res is not out:
+            out.copy_(res)
+            return out
+        return res
+
+    def _back_project(self, y_views, scatter, out):
         if tuple(y_views.shape) != self.local_output_shape:
             raise ValueError(f"local views of shape {tuple(y_views.shape)} do not match {self.local_output_shape}")
         if self.peer is not None and scatter:  # fused: image rows are added into their owners over NVLink
-            out = y_views.new_empty((self.slab[1] - self.slab[0],) + self.input_shape[1:])
+            if out is None:
+                out = y_views.new_empty((self.slab[1] - self.slab[0],) + self.input_shape[1:])
             launch = (lambda ptrs, rb, st: self.local.back_project_scatter(y_views, ptrs, rb, st)) if self.local is not None \
                 else (lambda ptrs, rb, st: None)
             return self.peer.exchange(launch, out)
