@@ -50,7 +50,19 @@ constexpr int kFwdWin = 96;
 constexpr int kFwd3S = 2, kFwd3TN = 16;
 constexpr int kFwd2S = 1, kFwd2TN = 16;
 // walk kernels (xct_plane2.cuh)
-constexpr int kWAdjS = 8, kWAdjTA = 8, kWAdjWin = 64, kWAdjStages = 4;
+// walk adjoint tile: 32 columns x TA rows x S slices per warp.  The coordinates of a row step are shared by its S
+// slices and the per-view preamble by its TA rows; measured at C5 (tools/bench_adj_ab.py, ms per application):
+// S x TA x ring stages  8 x 8 x 4: 229.6   12 x 6 x 3: 219.2   16 x 4 x 4: 214.9   16 x 4 x 3: 212.9   16 x 4 x 2: 212.6
+// (window of 40 / 48 / 64 bins: no difference -- the L2 -> shared traffic of the windows is not the limiter)
+#ifndef XCT_WADJ_S
+#define XCT_WADJ_S 16
+#define XCT_WADJ_TA 4
+#define XCT_WADJ_STAGES 2
+#endif
+#ifndef XCT_WADJ_WIN
+#define XCT_WADJ_WIN 64
+#endif
+constexpr int kWAdjS = XCT_WADJ_S, kWAdjTA = XCT_WADJ_TA, kWAdjWin = XCT_WADJ_WIN, kWAdjStages = XCT_WADJ_STAGES;
 constexpr int kWFwdS = 4, kWFwdTN = 8;     // walk forward tile: 64 (major) x 8 (minor) x 4 slices
 // CTA-shared-tile joint forward: 64 (major) x kWTileTN (minor) x 4 slices per CTA, kWTileWarps views in flight per CTA
 #ifndef XCT_TILE_TN
@@ -59,7 +71,11 @@ constexpr int kWFwdS = 4, kWFwdTN = 8;     // walk forward tile: 64 (major) x 8 
 #define XCT_TILE_WARPS 12 // views in flight per CTA; 2 CTAs per SM = 24 warps (24 warps in one CTA: 321)
 #define XCT_TILE_MINB 2
 #endif
+#ifndef XCT_TILE_S
+#define XCT_TILE_S 4      // slices per tile (4 or 8): coordinates / bins / weights of a walk step are shared by all of them
+#endif
 constexpr int kWTileTN = XCT_TILE_TN, kWTileWin = XCT_TILE_WIN, kWTileWarps = XCT_TILE_WARPS, kWTileMinB = XCT_TILE_MINB;
+constexpr int kWTileS = XCT_TILE_S;
 constexpr int kW2dTN = 8, kW2dWin = 160;  // 2D joint forward tile: 128 (major) x 8 (minor), one image
 // brick kernels (xct_brick.cuh): general 3D matrices
 constexpr int kBrAdjWR = 20, kBrAdjWC = 24, kBrAdjStages = 4;  // adjoint window of an 8^3 brick (columns start at a multiple of 4), ring depth
@@ -486,21 +502,21 @@ int launch_walk_forward_tile_class(const xct_plan* pl, const float* in, float* o
   p.n_list = pl->n_listJ[cls];
   p.tilesA = ceil_div(p.NA, MAJOR_B ? kWTileTN : 64);
   p.tilesB = ceil_div(p.NB, MAJOR_B ? 64 : kWTileTN);
-  const long long tiles = (long long)ceil_div(p.NS, kWFwdS) * p.tilesA * p.tilesB;
+  const long long tiles = (long long)ceil_div(p.NS, kWTileS) * p.tilesA * p.tilesB;
   if (tiles > 0x7fffffffLL) return fail(XCT_ERR_INVALID, "volume too large for the tile forward grid");
   // small problems: split the view list over blockIdx.y so that the grid fills the SMs (8 views run per CTA at a time)
   int chunks = 1;
   if (tiles < 148LL * 3) chunks = (int)std::min<long long>((148LL * 3 + tiles - 1) / tiles, std::max(1, p.n_list / (2 * kWTileWarps)));
   p.views_per_chunk = ceil_div(p.n_list, chunks);
   chunks = ceil_div(p.n_list, p.views_per_chunk);
-  const size_t smem = ((size_t)kWTileTN * 2 * 32 + (size_t)kWTileWarps * kWTileWin) * sizeof(float4);
+  const size_t smem = ((size_t)kWTileTN * 2 * 32 + (size_t)kWTileWarps * kWTileWin) * (kWTileS / 4) * sizeof(float4);
   const dim3 grid((unsigned)tiles, chunks);
   if (pl->rows_krow) {
-    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWFwdS, kWTileTN, kWTileWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_KROW, kWTileWarps, kWTileMinB>;
+    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWTileS, kWTileTN, kWTileWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_KROW, kWTileWarps, kWTileMinB>;
     XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kWTileWarps * 32, smem, st>>>(wp, in, out);
   } else {
-    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWFwdS, kWTileTN, kWTileWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_TABLE, kWTileWarps, kWTileMinB>;
+    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWTileS, kWTileTN, kWTileWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_TABLE, kWTileWarps, kWTileMinB>;
     XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kWTileWarps * 32, smem, st>>>(wp, in, out);
   }

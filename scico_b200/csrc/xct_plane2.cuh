@@ -111,10 +111,10 @@ __device__ __forceinline__ int window_start4(const ViewRec& vr, int a_lo, int a_
 // its exchange, xct_adjoint_scatter): one owner lookup per slice, then TA stores (or system-scope RED.ADD)
 // at a fixed stride, as in plane_adjoint_kernel's routed epilogue.  The view loop is the plain kernel's.
 template <class G, bool IS3D, int S, int TA, int WIN, int STAGES, int WARPS, bool TMA, bool ROUTE = false>
-__global__ void __launch_bounds__(WARPS * 32, ROUTE ? 2 : 0)  // routed: the plain kernel's occupancy (0 = unspecified)
+__global__ void __launch_bounds__(WARPS * 32, 2)  // two CTAs (16 warps) per SM: at most 128 registers
 walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __restrict__ out,
                     const __grid_constant__ CUtensorMap tmap, const __grid_constant__ OutRoute route) {
-  static_assert(WIN % 64 == 0 || WIN == 32, "chunk indexing assumes a power-of-two window");
+  static_assert(WIN % 4 == 0, "rows are staged in 16-byte chunks");
   constexpr int CPR = WIN / 4;                    // 16-byte chunks per staged row
   constexpr int CHUNKS = S * CPR;                 // chunks per view
   constexpr int CPL = (CHUNKS + 31) / 32;         // chunks per lane
@@ -833,15 +833,20 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
 template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int ROWS, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __restrict__ sino) {
-  static_assert(WIN % 32 == 0 && WIN <= 128 && S == 4, "float4 window slots, flushed 4 bins per lane in one pass");
+  static_assert(WIN % 32 == 0 && WIN <= 128 && (S == 4 || S == 8), "float4 window slots, flushed 4 bins per lane in one pass");
   using Vec = float4;
+  // S slices = NV planes of 4: the tile and the windows are arrays of float4 per plane, so every shared access
+  // stays a conflict-free LDS.128 / STS.128 over 512 contiguous bytes; the coordinates, bins and weights of a
+  // walk step are evaluated once for all S slices (S = 8: half the per-update arithmetic of S = 4)
+  constexpr int NV = S / 4;
   constexpr int GS = 2, H = S / 2, Q = WIN / 32, TM = 32 * GS;
   constexpr int DF = MAJ_POS ? 0 : 1, DG = 1 - DF;
+  constexpr int XPLANE = TN * 2 * 32;  // float4 slots per tile plane
   const PlaneParams& p = wp.p;
   extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  Vec* xt = reinterpret_cast<Vec*>(smem);                              // [TN][2][32]
-  Vec* winv = reinterpret_cast<Vec*>(smem) + TN * 2 * 32 + warp * WIN;  // [WIN]
+  Vec* xt = reinterpret_cast<Vec*>(smem);                                       // [NV][TN][2][32]
+  Vec* winv = reinterpret_cast<Vec*>(smem) + NV * XPLANE + warp * (NV * WIN);   // [NV][WIN]
   long long task = blockIdx.x;
   const int tb_ = (int)(task % p.tilesB);
   task /= p.tilesB;
@@ -860,19 +865,24 @@ walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __
 #pragma unroll
       for (int s = 0; s < S; ++s)
         v[s] = (ok && s0 + s < p.NS) ? wp.out_scale * __ldg(in + ((size_t)(s0 + s) * p.NA + a) * (size_t)p.NB + b) : 0.f;
-      xt[(n * 2 + d) * 32 + lane] = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+      for (int pv = 0; pv < NV; ++pv)
+        xt[pv * XPLANE + (n * 2 + d) * 32 + lane] = make_float4(v[4 * pv], v[4 * pv + 1], v[4 * pv + 2], v[4 * pv + 3]);
     }
   }
   __syncthreads();
   const float xmin0 = MAJOR_B ? G::coordA(a0) : G::coordB(b0);
 
   auto rmw = [&](int t, const float2 (&v)[H]) {  // win[t][:] += v   (one lane per address)
-    Vec* q = winv + t;
-    Vec cur = *q;
-    float2* c = reinterpret_cast<float2*>(&cur);
 #pragma unroll
-    for (int h = 0; h < H; ++h) c[h] = __fadd2_rn(c[h], v[h]);
-    *q = cur;
+    for (int pv = 0; pv < NV; ++pv) {
+      Vec* q = winv + pv * WIN + t;
+      Vec cur = *q;
+      float2* c = reinterpret_cast<float2*>(&cur);
+      c[0] = __fadd2_rn(c[0], v[2 * pv]);
+      c[1] = __fadd2_rn(c[1], v[2 * pv + 1]);
+      *q = cur;
+    }
   };
   const Vec vzero = make_float4(0.f, 0.f, 0.f, 0.f);
   const float2 zero2 = make_float2(0.f, 0.f);
@@ -885,7 +895,7 @@ walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __
     const int c0 = window_start<G>(vr, a0, a0 + (MAJOR_B ? TN : TM) - 1, b0, b0 + (MAJOR_B ? TM : TN) - 1) & ~3;
 
 #pragma unroll
-    for (int q = 0; q < Q; ++q) winv[lane + 32 * q] = vzero;
+    for (int q = 0; q < NV * Q; ++q) winv[lane + 32 * q] = vzero;
     __syncwarp();
 
     const float hF = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + DF) : G::hoistA(vr, a0 + GS * lane + DF);
@@ -903,11 +913,17 @@ walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __
         tb = (int)min((unsigned)(__float2int_rd(uF) - c0), (unsigned)(WIN - (E2 ? 4 : 3)));
       }
       float xm = xmin0;  // minor-axis coordinate of the step; + 1 is exact
-#pragma unroll 8
+#pragma unroll(S == 4 ? 8 : 4)
       for (int n = 0; n < TN; ++n, xm += 1.0f) {
-        const Vec xf4 = xt[(n * 2 + DF) * 32 + lane], xg4 = xt[(n * 2 + DG) * 32 + lane];
-        const float2 xF[H] = {make_float2(xf4.x, xf4.y), make_float2(xf4.z, xf4.w)};
-        const float2 xG[H] = {make_float2(xg4.x, xg4.y), make_float2(xg4.z, xg4.w)};
+        float2 xF[H], xG[H];
+#pragma unroll
+        for (int pv = 0; pv < NV; ++pv) {
+          const Vec xf4 = xt[pv * XPLANE + (n * 2 + DF) * 32 + lane], xg4 = xt[pv * XPLANE + (n * 2 + DG) * 32 + lane];
+          xF[2 * pv] = make_float2(xf4.x, xf4.y);
+          xF[2 * pv + 1] = make_float2(xf4.z, xf4.w);
+          xG[2 * pv] = make_float2(xg4.x, xg4.y);
+          xG[2 * pv + 1] = make_float2(xg4.z, xg4.w);
+        }
         const float hm = MAJOR_B ? G::hoistA_x(vr, xm) : G::hoistB_x(vr, xm);
         const float uF = MAJOR_B ? G::combine(vr, hm, hF) : G::combine(vr, hF, hm);
         const float uG = MAJOR_B ? G::combine(vr, hm, hG) : G::combine(vr, hG, hm);
@@ -970,32 +986,35 @@ walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __
     // ---- flush the window: lane j owns bins 4j .. 4j+3 (entirely inside or outside [0, D1))
     const int col = c0 + 4 * lane;
     if (lane < WIN / 4 && (unsigned)col < (unsigned)p.D1) {
-      float blk[4][S];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const Vec r = winv[4 * lane + k];
-        blk[k][0] = r.x; blk[k][1] = r.y; blk[k][2] = r.z; blk[k][3] = r.w;
-      }
-      if (ROWS == ROWS_KROW) {
-        const int r0 = wp.s_base + s0 + vr.krow;  // local detector row of the group's first slice
-        float* y = sino + ((long long)v * p.D0 + r0) * (long long)p.D1 + col;
+      for (int pv = 0; pv < NV; ++pv) {
+        float blk[4][4];
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
-                               __float_as_uint(blk[3][s]);  // all four +0: nothing to add
-          const bool live = s0 + s < p.NS && (unsigned)(r0 + s) < (unsigned)p.D0 && any != 0u;
-          red_add_v4_if(live, y + (long long)s * p.D1, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+        for (int k = 0; k < 4; ++k) {
+          const Vec r = winv[pv * WIN + 4 * lane + k];
+          blk[k][0] = r.x; blk[k][1] = r.y; blk[k][2] = r.z; blk[k][3] = r.w;
         }
-      } else {
-        const long long* ro = wp.rowoff + (size_t)v * wp.row_stride + wp.s_base;
+        if (ROWS == ROWS_KROW) {
+          const int r0 = wp.s_base + s0 + 4 * pv + vr.krow;  // local detector row of the plane's first slice
+          float* y = sino + ((long long)v * p.D0 + r0) * (long long)p.D1 + col;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          const int sl = min(s0 + s, p.NS - 1);
-          const long long off = __ldg(ro + sl);
-          const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
-                               __float_as_uint(blk[3][s]);
-          const bool live = s0 + s < p.NS && off >= 0 && any != 0u;
-          red_add_v4_if(live, sino + (live ? off : 0) + col, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+          for (int s = 0; s < 4; ++s) {
+            const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
+                                 __float_as_uint(blk[3][s]);  // all four +0: nothing to add
+            const bool live = s0 + 4 * pv + s < p.NS && (unsigned)(r0 + s) < (unsigned)p.D0 && any != 0u;
+            red_add_v4_if(live, y + (long long)s * p.D1, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+          }
+        } else {
+          const long long* ro = wp.rowoff + (size_t)v * wp.row_stride + wp.s_base;
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const int sl = min(s0 + 4 * pv + s, p.NS - 1);
+            const long long off = __ldg(ro + sl);
+            const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
+                                 __float_as_uint(blk[3][s]);
+            const bool live = s0 + 4 * pv + s < p.NS && off >= 0 && any != 0u;
+            red_add_v4_if(live, sino + (live ? off : 0) + col, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+          }
         }
       }
     }
