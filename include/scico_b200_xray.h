@@ -64,6 +64,7 @@ typedef enum xct_status {
 #define XCT_FLAG_NO_JOINT 0x8u      /* walk forward: one column per walk for every view (testing / comparison) */
 #define XCT_FLAG_NO_TILE 0x40u      /* 3D joint forward: register-stationary voxels (TN = 8) instead of the CTA-shared tile (testing / comparison) */
 #define XCT_FLAG_2D_PER_CLASS 0x80u  /* 2D joint forward: one launch per view class even for small problems (testing / comparison) */
+#define XCT_FLAG_NO_ADJ_VEC 0x100u   /* walk adjoint: scalar taps from the (V, D0, D1) sinogram instead of the slice-interleaved copy (testing / comparison) */
 #define XCT_FLAG_NO_BRICK 0x20u     /* general 3D matrices: thread-per-voxel kernels instead of the brick kernels (testing / comparison) */
 
 /* kernel families a plan can resolve to (xct_plan_info.path) */
@@ -128,7 +129,8 @@ typedef struct xct_plan_classes {
   int32_t rows_consecutive; /* 3D sep: local row = local slice + const per view (TMA box / krow flush) */
   int32_t fwd_cold;         /* some minor coefficient can move the bin by two per step */
   int32_t brick_views[6];   /* general 3D (brick forward): views per class [2*depth_axis + needs_shared_atomics] */
-  int32_t fwd_tile;         /* 3D joint forward runs on a CTA-shared tile of 64 x 32 x 4 voxels (walk_forward_tile_kernel) */
+  int32_t fwd_tile;         /* 3D joint forward runs on a CTA-shared tile of 64 x 64 x 4 voxels (walk_forward_tile_kernel) */
+  int32_t adj_interleaved;  /* walk adjoint reads a slice-interleaved (V, D0 / 4, D1, 4) copy of the sinogram (walk_adjoint_vec_kernel) */
 } xct_plan_classes;
 
 XCT_API int xct_version(void);

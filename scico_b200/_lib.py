@@ -31,6 +31,7 @@ FLAG_NO_BRICK = 0x20
 FLAG_NO_TILE = 0x40
 FLAG_2D_PER_CLASS = 0x80
 FLAG_NO_TMA = 0x10
+FLAG_NO_ADJ_VEC = 0x100
 KERNEL_NAMES = {0: "general", 1: "plane", 2: "walk", 3: "brick"}
 
 PATH_NAMES = {1: "2d_plane", 2: "2d_general", 3: "3d_sep", 4: "3d_general"}
@@ -147,6 +148,7 @@ class PlanClasses(ctypes.Structure):
         ("fwd_cold", c_int32),
         ("brick_views", c_int32 * 6),
         ("fwd_tile", c_int32),
+        ("adj_interleaved", c_int32),
     ]
 
 

@@ -63,6 +63,14 @@ constexpr int kFwd2S = 1, kFwd2TN = 16;
 #define XCT_WADJ_WIN 64
 #endif
 constexpr int kWAdjS = XCT_WADJ_S, kWAdjTA = XCT_WADJ_TA, kWAdjWin = XCT_WADJ_WIN, kWAdjStages = XCT_WADJ_STAGES;
+// slice-interleaved walk adjoint (walk_adjoint_vec_kernel): window of TA + 31 + 2 bins, no 4-bin alignment
+#ifndef XCT_WVEC_S
+#define XCT_WVEC_S 16
+#define XCT_WVEC_TA 4
+#define XCT_WVEC_WIN 40
+#define XCT_WVEC_STAGES 3
+#endif
+constexpr int kWVecS = XCT_WVEC_S, kWVecTA = XCT_WVEC_TA, kWVecWin = XCT_WVEC_WIN, kWVecStages = XCT_WVEC_STAGES;
 constexpr int kWFwdS = 4, kWFwdTN = 8;     // walk forward tile: 64 (major) x 8 (minor) x 4 slices
 // CTA-shared-tile joint forward: 64 (major) x kWTileTN (minor) x 4 slices per CTA, kWTileWarps views in flight per CTA
 #ifndef XCT_TILE_TN
@@ -106,6 +114,10 @@ struct xct_plan {
   bool adj_walk = false;
   bool rows_krow = false;  // local detector row of slice i is i + ViewRec::krow in every view (or none)
   bool adj_tma = false;    // walk adjoint stages its sinogram window with one TMA box per view (rows = slice + krow)
+  bool adj_vec = false;    // slice-interleaved walk adjoint possible (adj_tma and every view's window fits kWVecWin)
+  float* d_sinoT = nullptr;             // (V, ceil(n0 / 4), d1, 4) interleaved copy of the sinogram, made per call
+  cudaEvent_t sinoT_ev = nullptr;       // last reader of d_sinoT (orders its reuse across streams)
+  bool sinoT_failed = false;            // the scratch could not be allocated: scalar-tap kernel from then on
   bool fwd_walk = false;
   bool fwd_cold = false;   // some view's minor-axis coefficient can move the bin by more than one per step
   bool fwd_unit4 = false;  // vector flush possible (unit rows, D1 % 4 == 0, window fits with 4-bin alignment)
@@ -178,7 +190,7 @@ int check_device(int device) {
 // Split the views into the two classes of the forward kernel and pick its lane stride.
 // Returns false when some view is outside the plane kernels' envelope.
 struct Envelope {
-  bool adj_ok = true, fwd_ok = true, adj_walk_ok = true, fwd_unit4_ok = true;
+  bool adj_ok = true, fwd_ok = true, adj_walk_ok = true, adj_vec_ok = true, fwd_unit4_ok = true;
   float max_minor = 0.f;
   int gs = 2;
   std::vector<int> list[2];
@@ -195,13 +207,15 @@ Envelope analyse_views(const std::vector<xct::ViewRec>& views, int adjTA, int fw
   for (size_t v = 0; v < views.size(); ++v) {
     const float a = std::fabs(views[v].ca), b = std::fabs(views[v].cb);
     if (!std::isfinite(a) || !std::isfinite(b)) {
-      env.adj_ok = env.fwd_ok = env.adj_walk_ok = false;
+      env.adj_ok = env.fwd_ok = env.adj_walk_ok = env.adj_vec_ok = false;
       continue;
     }
     // adjoint window: tile adjTA x 32, needs floor(max u) - floor(min u) + 2 <= WIN
     if (a * (adjTA - 1) + b * 31.f + 3.f > (float)kAdjWin) env.adj_ok = false;
     // walk adjoint: window start is rounded down to a multiple of 4 bins (+3)
     if (a * (kWAdjTA - 1) + b * 31.f + 6.f > (float)kWAdjWin) env.adj_walk_ok = false;
+    // slice-interleaved walk adjoint: exact window start, two taps, one bin of rounding slack
+    if (a * (kWVecTA - 1) + b * 31.f + 3.f > (float)kWVecWin) env.adj_vec_ok = false;
     const bool major_b = b >= a;
     env.list[major_b ? 1 : 0].push_back((int)v);
     const float minor = major_b ? views[v].ca : views[v].cb;
@@ -355,10 +369,95 @@ int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* 
   return launch_ok("plane_adjoint_kernel");
 }
 
+// Slice-interleaved walk adjoint: interleave the detector rows of the launch's slices four by four into the plan's
+// scratch (sino_interleave4_kernel), then walk_adjoint_vec_kernel with one TMA box of that copy per (view, tile).
+// Returns 1 when this path cannot be taken (no scratch memory, stream capture in progress before the scratch
+// exists, tensor map not encodable): the caller then launches the scalar-tap kernel.
+int launch_walk_adjoint_vec(const xct_plan* cpl, const float* in, float* out, cudaStream_t st, int s_begin, int s_count,
+                            const xct::OutRoute* route) {
+  xct_plan* pl = const_cast<xct_plan*>(cpl);  // the scratch and its event are caches, not plan state
+  const int g_total = ceil_div(pl->n0, 4);
+  if (pl->sinoT_failed) return 1;
+  // inside a stream capture (CUDA graphs, XLA command buffers) nothing is allocated and the cross-stream event is
+  // neither waited on nor recorded: a replayed graph is ordered by its own stream like any other kernel sequence
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
+    cudaGetLastError();
+    return 1;
+  }
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
+  if (!pl->d_sinoT) {
+    if (capturing) return 1;  // an uncaptured call creates the scratch
+    const size_t bytes = (size_t)pl->V * g_total * pl->d1 * 4 * sizeof(float);
+    if (cudaMalloc(&pl->d_sinoT, bytes) != cudaSuccess || cudaEventCreateWithFlags(&pl->sinoT_ev, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(pl->d_sinoT);
+      pl->d_sinoT = nullptr;
+      pl->sinoT_failed = true;
+      return 1;
+    }
+    XCT_CUDA(cudaEventRecord(pl->sinoT_ev, st));
+  }
+  xct::Walk2Params wp{};
+  wp.p = plane_params(pl, 1);
+  wp.rowoff = pl->d_rowoff;
+  wp.out_scale = 2.0f;
+  wp.row_stride = pl->n0;
+  wp.s_base = s_begin;
+  xct::PlaneParams& p = wp.p;
+  if (s_count >= 0) p.NS = s_count;
+  if (out) out += (size_t)s_begin * pl->n1 * pl->n2;
+  p.tilesA = ceil_div(p.NA, kWVecTA);
+  p.tilesB = ceil_div(p.NB, 32);
+  const long long tasks = (long long)ceil_div(p.NS, kWVecS) * p.tilesA * p.tilesB;
+  const int blocks = ceil_div(tasks, kWarps);
+  // (V, g_total, 4 * d1) fp32, box = 4 * kWVecWin floats x kWVecS / 4 groups x 1 view, zero fill out of bounds
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)pl->d1 * 4, (cuuint64_t)g_total, (cuuint64_t)pl->V};
+    const cuuint64_t strides[2] = {(cuuint64_t)pl->d1 * 4 * sizeof(float), (cuuint64_t)g_total * pl->d1 * 4 * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)kWVecWin * 4, (cuuint32_t)kWVecS / 4, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, pl->d_sinoT, dims, strides, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1;
+  }
+  // the previous reader of the scratch (possibly on another stream) must have finished
+  if (!capturing) XCT_CUDA(cudaStreamWaitEvent(st, pl->sinoT_ev, 0));
+  {
+    const int g_begin = s_begin / 4, g_count = ceil_div(p.NS, 4);
+    const dim3 grid(ceil_div(pl->d1, 256), g_count, pl->V);
+    xct::sino_interleave4_kernel<<<grid, 256, 0, st>>>(pl->d_views, in, pl->d_sinoT, pl->d0, pl->d1, g_begin, g_count, g_total);
+    int rc = launch_ok("sino_interleave4_kernel");
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)kWarps * kWVecStages * kWVecS * kWVecWin * sizeof(float) + (size_t)kWarps * kWVecStages * sizeof(unsigned long long);
+  const xct::OutRoute none{};
+  if (route) {
+    auto kern = xct::walk_adjoint_vec_kernel<xct::Geom3, kWVecS, kWVecTA, kWVecWin, kWVecStages, kWarps, true>;
+    if (smem > 48 * 1024) XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kWarps * 32, smem, st>>>(wp, out, tmap, *route);
+  } else {
+    auto kern = xct::walk_adjoint_vec_kernel<xct::Geom3, kWVecS, kWVecTA, kWVecWin, kWVecStages, kWarps, false>;
+    if (smem > 48 * 1024) XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kWarps * 32, smem, st>>>(wp, out, tmap, none);
+  }
+  int rc = launch_ok("walk_adjoint_vec_kernel");
+  if (rc) return rc;
+  if (!capturing) XCT_CUDA(cudaEventRecord(pl->sinoT_ev, st));
+  return XCT_OK;
+}
+
 // walk adjoint (3D separable geometry with unit rows; `in` must be 16-byte aligned)
 // Slices [s_begin, s_begin + s_count) of the plan only (s_count < 0: all); `out` is the full volume.
 int launch_walk_adjoint(const xct_plan* pl, const float* in, float* out, cudaStream_t st, int s_begin = 0,
                         int s_count = -1, const xct::OutRoute* route = nullptr) {
+  if (pl->adj_vec && (s_begin & 3) == 0) {
+    const int rc = launch_walk_adjoint_vec(pl, in, out, st, s_begin, s_count, route);
+    if (rc != 1) return rc;
+  }
   xct::Walk2Params wp{};
   wp.p = plane_params(pl, 1);
   wp.rowoff = pl->d_rowoff;
@@ -1133,6 +1232,7 @@ static int plan3d_create_impl(xct_plan** out, const xct3d_geom* g, bool dry) {
       }
       pl->adj_walk = env.adj_ok && env.adj_walk_ok && unit && (g->d1 % 4 == 0) && !(g->flags & XCT_FLAG_NO_WALK);
       pl->adj_tma = pl->adj_tma && pl->adj_walk;  // the TMA box is the walk adjoint's staging
+      pl->adj_vec = pl->adj_tma && env.adj_vec_ok && !(g->flags & XCT_FLAG_NO_ADJ_VEC);
       pl->gs = env.fwd_ok ? env.gs : 0;
       pl->pipe_ok = pl->pipe_ok && pl->fwd_walk && pl->adj_walk && !(g->flags & XCT_FLAG_NO_HOST_PIPELINE);
       if (pl->adj_plane && pl->fwd_plane) pl->path = XCT_PATH_3D_SEP;
@@ -1180,6 +1280,7 @@ static void fill_classes(const xct_plan* pl, xct_plan_classes* c) {
   c->fwd_cold = pl->fwd_cold ? 1 : 0;
   for (int k = 0; k < 6; ++k) c->brick_views[k] = pl->n_listB[k];
   c->fwd_tile = pl->fwd_tile ? 1 : 0;
+  c->adj_interleaved = pl->adj_vec ? 1 : 0;
 }
 int xct_plan_get_classes(const xct_plan* pl, xct_plan_classes* classes) {
   if (!pl || !classes) return fail(XCT_ERR_INVALID, "null argument");
@@ -1223,6 +1324,8 @@ void xct_plan_destroy(xct_plan* pl) {
   for (int c = 0; c < 4; ++c) cudaFree(pl->d_listR[c]);
   for (int c = 0; c < 6; ++c) cudaFree(pl->d_listB[c]);
   cudaFree(pl->d_mats_t);
+  cudaFree(pl->d_sinoT);
+  if (pl->sinoT_ev) cudaEventDestroy(pl->sinoT_ev);
   for (int d = 0; d < 2; ++d) { cudaFree(pl->stage_in[d]); cudaFree(pl->stage_out[d]); }
   if (pl->hstream) cudaStreamDestroy(pl->hstream);
   if (pl->s_in) cudaStreamDestroy(pl->s_in);
@@ -1430,13 +1533,13 @@ static int enqueue_host_pipelined(xct_plan* pl, const float* in_host, float* out
   const size_t n_vol = in_elems(pl), n_sino = out_elems(pl);
   if ((rc = ensure_stage(pl, dir, forward ? n_vol : n_sino, forward ? n_sino : n_vol))) return rc;
   const int NS = pl->n0, D0 = pl->d0, D1 = pl->d1, V = pl->V;
-  int chunk = std::max(8, (NS + 31) / 32);  // 1024 slices, one GPU: chunks of 8 / 16 / 32 / 64 slices -> 553.7 / 553.5 / 547.7 / 552.3 ms per pair
+  int chunk = std::max(16, (NS + 31) / 32);  // 1024 slices, one GPU: chunks of 8 / 16 / 32 / 64 slices -> 553.7 / 553.5 / 547.7 / 552.3 ms per pair
   if (const char* env = std::getenv("XCT_HOST_CHUNK_SLICES")) {  // tuning / diagnosis (tools/bench_host_pipeline.py)
     const int v = std::atoi(env);
     if (v > 0) chunk = v;
   }
-  chunk = (chunk + 7) & ~7;  // whole slice groups of both kernels (S = 4 / 8)
-  chunk = std::max(chunk, ((NS + 63) / 64 + 7) & ~7);  // at most 64 chunks (event table)
+  chunk = (chunk + 15) & ~15;  // whole slice groups of both kernels (4 slices forward, 16 adjoint)
+  chunk = std::max(chunk, ((NS + 63) / 64 + 15) & ~15);  // at most 64 chunks (event table)
   const int nchunks = ceil_div(NS, chunk);
   const size_t ev_base = dir ? 2 * 64 : 0;  // each direction owns its events
   while (pl->events.size() < 4 * 64) {

@@ -352,6 +352,207 @@ walk_adjoint_kernel(Walk2Params wp, const float* __restrict__ sino, float* __res
   }
 }
 
+// ---------------------------------------------------------- adjoint, slice-interleaved window
+// walk_adjoint_kernel reads one scalar tap per (row step, slice): with S slices per thread a row step is S LDS.32.
+// Here the sinogram is first re-laid out by sino_interleave4_kernel as (V, G, D1, 4): the four detector rows that
+// four consecutive slices project onto become the four components of one float4 per bin.  A view's window is then
+// ONE TMA box of (4 WIN floats, S / 4 groups, 1 view) and a row step reads the new tap of FOUR slices with one
+// LDS.128 (a quarter-warp's 8 lanes sit on <= 8 consecutive bins = 128 contiguous bytes: conflict-free), i.e.
+// S / 4 shared loads per row step instead of S -- same bytes, a quarter of the LSU issue slots.  The window needs
+// no 4-bin alignment any more (bin c sits at byte 16 c of a row), so it shrinks to TA + 31 + 2 bins.  Everything
+// else -- the carried (z[c], z[c+1]) pair, the packed row-pair coordinates, the per-view jump variant, the order
+// of accumulation (views ascending, tap c then c + 1) -- is walk_adjoint_kernel's: results are bit-identical.
+//
+// out[v][g][c][j] = sino[v][4 g + j + krow(v)][c]  (0 outside the detector; g = slice group of the PLAN)
+__global__ void __launch_bounds__(256)
+sino_interleave4_kernel(const ViewRec* __restrict__ views, const float* __restrict__ sino, float* __restrict__ out, int D0,
+                        int D1, int g_begin, int g_count, int g_total) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = g_begin + blockIdx.y, v = blockIdx.z;
+  if (c >= D1) return;
+  const int krow = load_view(views + v).krow;
+  const float* y = sino + (size_t)v * D0 * (size_t)D1 + c;
+  float q[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = 4 * g + j + krow;
+    q[j] = (unsigned)r < (unsigned)D0 ? __ldg(y + (size_t)r * D1) : 0.f;
+  }
+  reinterpret_cast<float4*>(out)[((size_t)v * g_total + g) * (size_t)D1 + c] = make_float4(q[0], q[1], q[2], q[3]);
+}
+
+template <class G, int S, int TA, int WIN, int STAGES, int WARPS, bool ROUTE = false>
+__global__ void __launch_bounds__(WARPS * 32, 2)  // two CTAs (16 warps) per SM: at most 128 registers
+walk_adjoint_vec_kernel(Walk2Params wp, float* __restrict__ out, const __grid_constant__ CUtensorMap tmap,
+                        const __grid_constant__ OutRoute route) {
+  static_assert(S % 4 == 0 && TA % 2 == 0 && 4 * WIN <= 256, "float4 slice groups, row pairs, TMA box <= 256 elements");
+  constexpr int NG = S / 4, H = S / 2;
+  constexpr int STAGE_VEC = NG * WIN;  // float4 slots per stage: [NG][WIN]
+  const PlaneParams& p = wp.p;
+  extern __shared__ __align__(128) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sgroups = (p.NS + S - 1) / S;
+  const long long ntasks = (long long)sgroups * p.tilesA * p.tilesB;
+  long long task = (long long)blockIdx.x * WARPS + warp;
+  if (task >= ntasks) return;  // warp-uniform; no block barrier below
+  const int tb = (int)(task % p.tilesB);
+  task /= p.tilesB;
+  const int ta = (int)(task % p.tilesA);
+  const int sg = (int)(task / p.tilesA);
+  const int a0 = ta * TA, b0 = tb * 32, s0 = sg * S;
+  const int b = b0 + lane;
+  const float4* ring = reinterpret_cast<const float4*>(smem) + (size_t)warp * (STAGES * STAGE_VEC);
+  const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring);
+  const unsigned bars_sa =
+      (unsigned)__cvta_generic_to_shared(reinterpret_cast<const float4*>(smem) + (size_t)WARPS * (STAGES * STAGE_VEC)) +
+      warp * STAGES * 8u;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) mbar_init(bars_sa + 8u * i, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  float2 acc[TA][H];
+#pragma unroll
+  for (int n = 0; n < TA; ++n)
+#pragma unroll
+    for (int h = 0; h < H; ++h) acc[n][h] = make_float2(0.f, 0.f);
+
+  // producer: the whole [NG][WIN] x 4 window of view v in one bulk tensor copy (one elected lane)
+  const int g_base = (wp.s_base + s0) >> 2;  // slice group of the plan (the launcher guarantees s_base % 4 == 0)
+  auto fetch_tma = [&](int v, int stage) {
+    const ViewRec vr = load_view(p.views + v);
+    const int c0 = window_start<G>(vr, a0, a0 + TA - 1, b0, b0 + 31);
+    if (elect_one()) {
+      const unsigned bar = bars_sa + 8u * stage;
+      mbar_expect_tx(bar, STAGE_VEC * (unsigned)sizeof(float4));
+      tma_load_3d(ring_sa + stage * (STAGE_VEC * (unsigned)sizeof(float4)), &tmap, 4 * c0, g_base, v, bar);
+    }
+    return c0;
+  };
+
+  const float xa0 = G::coordA(a0);
+  auto walk = [&](auto up_c, auto cold_c, const float4* zb, const ViewRec& vr, int c0, float hB) {
+    constexpr bool UP = decltype(up_c)::value;
+    constexpr bool COLD = decltype(cold_c)::value;
+    float4 lo[NG], hi[NG];
+    int tp = 0;
+    int cc[2];
+    float2 ww0, ww1;
+#pragma unroll
+    for (int n = 0; n < TA; ++n) {
+      if ((n & 1) == 0) {  // coordinates and weights of rows n, n + 1 in packed fp32
+        const float2 hA = make_float2(G::hoistA_x(vr, xa0 + (float)n), G::hoistA_x(vr, xa0 + (float)(n + 1)));
+        G::bins2(vr, G::combine2(vr, hA, make_float2(hB, hB)), cc[0], cc[1], ww0, ww1);
+      }
+      const int c = cc[n & 1];
+      const float w0 = (n & 1) ? ww0.y : ww0.x, w1 = (n & 1) ? ww1.y : ww1.x;
+      const int t = (int)min((unsigned)(c - c0), (unsigned)(WIN - 2));
+      const float4* z = zb + t;
+      if (n == 0) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          lo[g] = z[g * WIN];
+          hi[g] = z[g * WIN + 1];
+        }
+      } else {
+        const bool moved = t != tp;
+        if (UP) {
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            lo[g].x = moved ? hi[g].x : lo[g].x;
+            lo[g].y = moved ? hi[g].y : lo[g].y;
+            lo[g].z = moved ? hi[g].z : lo[g].z;
+            lo[g].w = moved ? hi[g].w : lo[g].w;
+            hi[g] = z[g * WIN + 1];
+          }
+          if (COLD && moved && t != tp + 1) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) lo[g] = z[g * WIN];
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            hi[g].x = moved ? lo[g].x : hi[g].x;
+            hi[g].y = moved ? lo[g].y : hi[g].y;
+            hi[g].z = moved ? lo[g].z : hi[g].z;
+            hi[g].w = moved ? lo[g].w : hi[g].w;
+            lo[g] = z[g * WIN];
+          }
+          if (COLD && moved && t != tp - 1) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) hi[g] = z[g * WIN + 1];
+          }
+        }
+      }
+      tp = t;
+      const float2 w0p = make_float2(w0, w0), w1p = make_float2(w1, w1);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        acc[n][2 * g] = __ffma2_rn(make_float2(hi[g].x, hi[g].y), w1p, __ffma2_rn(make_float2(lo[g].x, lo[g].y), w0p, acc[n][2 * g]));
+        acc[n][2 * g + 1] =
+            __ffma2_rn(make_float2(hi[g].z, hi[g].w), w1p, __ffma2_rn(make_float2(lo[g].z, lo[g].w), w0p, acc[n][2 * g + 1]));
+      }
+    }
+  };
+
+  int c0q[STAGES];
+#pragma unroll
+  for (int i = 0; i < STAGES; ++i) c0q[i] = 0;
+#pragma unroll
+  for (int i = 0; i < STAGES - 1; ++i)
+    if (i < p.n_list) c0q[i] = fetch_tma(i, i);
+
+  int st_c = 0, st_p = STAGES - 1;
+  unsigned par = 0;
+  for (int v = 0; v < p.n_list; ++v) {
+    __syncwarp();  // all lanes have finished reading the stage that is refilled now
+    if (v + STAGES - 1 < p.n_list) c0q[STAGES - 1] = fetch_tma(v + STAGES - 1, st_p);
+    mbar_wait(bars_sa + 8u * st_c, par);
+    const float4* zb = ring + st_c * STAGE_VEC;
+    st_p = st_c;
+    if (++st_c == STAGES) { st_c = 0; par ^= 1u; }
+    const ViewRec vr = load_view(p.views + v);
+    const int c0 = c0q[0];
+#pragma unroll
+    for (int i = 0; i + 1 < STAGES; ++i) c0q[i] = c0q[i + 1];
+    const float hB = G::hoistB(vr, b);
+    if (vr.jump != 0.f) {  // rare (|ca| within rounding distance of 1)
+      if (vr.ca >= 0.f) walk(std::true_type{}, std::true_type{}, zb, vr, c0, hB);
+      else walk(std::false_type{}, std::true_type{}, zb, vr, c0, hB);
+    } else if (vr.ca >= 0.f) {
+      walk(std::true_type{}, std::false_type{}, zb, vr, c0, hB);
+    } else {
+      walk(std::false_type{}, std::false_type{}, zb, vr, c0, hB);
+    }
+  }
+
+  if (b >= p.NB) return;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    if (s0 + s >= p.NS) break;
+    if constexpr (ROUTE) {
+      RouteCursor cur;
+      cur.seek(route, wp.s_base + s0 + s, (long long)a0 * p.NB + b);  // the slice picks the owner
+      float* q = cur.q;
+#pragma unroll
+      for (int n = 0; n < TA; ++n) {
+        if (a0 + n >= p.NA) break;
+        const float val = ((s & 1) ? acc[n][s / 2].y : acc[n][s / 2].x) * wp.out_scale;
+        if (route.store) q[(size_t)n * p.NB] = val;
+        else atomicAdd_system(q + (size_t)n * p.NB, val);
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < TA; ++n) {
+        if (a0 + n < p.NA)
+          out[((size_t)(s0 + s) * p.NA + (a0 + n)) * (size_t)p.NB + b] = ((s & 1) ? acc[n][s / 2].y : acc[n][s / 2].x) * wp.out_scale;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ forward
 // Tile: 32*GS points along the view's MAJOR axis (lane l owns points GS*l .. GS*l+GS-1) x TN points
 // along the MINOR axis x S slices, voxels register-stationary for every view of the launch (as in

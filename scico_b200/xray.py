@@ -198,7 +198,7 @@ def _analyse(fn, geom) -> dict:
     d["joint_views"] = list(cls.joint_views)
     d["two_bin_views"] = list(cls.two_bin_views)
     d["brick_views"] = list(cls.brick_views)
-    for name in ("adj_jump_views", "rows_unit", "rows_consecutive", "fwd_cold", "fwd_tile"):
+    for name in ("adj_jump_views", "rows_unit", "rows_consecutive", "fwd_cold", "fwd_tile", "adj_interleaved"):
         d[name] = getattr(cls, name)
     return d
 

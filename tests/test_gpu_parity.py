@@ -263,6 +263,41 @@ def test_tma_staged_adjoint_is_bit_identical_to_cp_async_staging(torch_dev):
         assert O.rel_l2(got, full[z0:z1]) <= TOL
 
 
+def test_interleaved_adjoint_is_bit_identical_to_scalar_tap_adjoint(torch_dev):
+    """walk_adjoint_vec_kernel (sinogram rows of four consecutive slices interleaved per bin by
+    sino_interleave4_kernel, one LDS.128 per four slices and row step, 16 slices x 4 rows per thread)
+    against walk_adjoint_kernel (XCT_FLAG_NO_ADJ_VEC) and the oracle: same taps in the same order, so the
+    results must be bit-identical; ragged tiles, slice counts that are not multiples of 4 or 16, detector
+    rows off centre (krow != 0, rows outside the detector), z-slab plans, repeated calls on new data
+    (the interleaved scratch is reused), and slice sub-ranges through the pipelined host path."""
+    torch, dev = torch_dev
+    rng = np.random.default_rng(11)
+    for name in ("walk_basic", "walk_ragged_tiles", "walk_small_det", "walk_det_rows_offcentre", "walk_many_slices",
+                 "walk_one_view", "walk_two_views"):
+        N, D, mk = CASES_3D[name]
+        M = mk()
+        A = sb.XRayTransform3D(N, M, D)
+        B = sb.XRayTransform3D(N, M, D, _flags=_lib.FLAG_NO_ADJ_VEC)
+        assert A.analyse()["adj_interleaved"] == 1 and B.analyse()["adj_interleaved"] == 0, name
+        for _ in range(2):
+            y = rng.standard_normal(A.output_shape).astype(np.float32)
+            a, b = _gpu(torch, dev, A, y, adj=True), _gpu(torch, dev, B, y, adj=True)
+            np.testing.assert_array_equal(a, b)
+        assert O.rel_l2(a, C.back_project_3d(y, A.matrices, N)) <= TOL
+        # host arrays: slice chunks of the pipelined path (sub-range launches at multiples of 4 slices)
+        np.testing.assert_array_equal(np.asarray(A.T(y)), a)
+    N, D = (24, 40, 48), (24, 64)
+    M = _x_mats(N, D, 9)
+    y = rng.standard_normal((9,) + D).astype(np.float32)
+    full = C.back_project_3d(y, M.astype(np.float32), N)
+    for z0, z1 in ((0, 10), (10, 24), (3, 19)):
+        kw = dict(slice_offset=z0, det_row_offset=z0, det_rows_total=D[0])
+        A = sb.XRayTransform3D((z1 - z0,) + N[1:], M, (z1 - z0, D[1]), **kw)
+        assert A.analyse()["adj_interleaved"] == 1
+        got = _gpu(torch, dev, A, np.ascontiguousarray(y[:, z0:z1]), adj=True)
+        assert O.rel_l2(got, full[z0:z1]) <= TOL
+
+
 def test_pair_is_cuda_graph_capturable(torch_dev):
     """xct_forward / xct_adjoint enqueue everything on the caller's stream without allocation or host
     synchronisation (the XLA FFI contract): a forward + adjoint pair captured into a CUDA

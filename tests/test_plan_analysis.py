@@ -22,6 +22,7 @@ def test_headline_geometry_takes_the_walk_joint_tma_path():
     assert a["path_name"] == "3d_sep" and a["fwd_kernel"] == 2 and a["adj_kernel"] == 2
     assert a["fwd_joint"] == 1 and a["adj_tma"] == 1 and a["rows_unit"] == 1 and a["rows_consecutive"] == 1
     assert a["fwd_tile"] == 1  # joint forward on the CTA-shared tile
+    assert a["adj_interleaved"] == 1  # adjoint reads the slice-interleaved copy of the sinogram
     n_ = sb.XRayTransform3D((n,) * 3, _x((n,) * 3, (n, n), V), (n, n), _flags=_lib.FLAG_NO_TILE).analyse()
     assert n_["fwd_tile"] == 0 and n_["fwd_joint"] == 1
     assert sum(a["joint_views"]) == V and a["two_bin_views"] == [0, 0, 0, 0] and a["fwd_cold"] == 0
