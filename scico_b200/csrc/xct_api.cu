@@ -76,14 +76,21 @@ constexpr int kWFwdS = 4, kWFwdTN = 8;     // walk forward tile: 64 (major) x 8 
 #ifndef XCT_TILE_TN
 #define XCT_TILE_TN 64    // measured at C5 (tools/bench_fwd_ab.py, ms per application): TN 16: 359, 32: 319, 64: 304
 #define XCT_TILE_WIN 128  // window of the 64 x 64 tile: 63 (|c_major| + |c_minor|) + 7 <= 128 for every rotation
-#define XCT_TILE_WARPS 12 // views in flight per CTA; 2 CTAs per SM = 24 warps (24 warps in one CTA: 321)
+#define XCT_TILE_WARPS 10 // warps per CTA, 2 CTAs per SM; with two views per warp pass 20 views are in flight per CTA
 #define XCT_TILE_MINB 2
 #endif
 #ifndef XCT_TILE_S
 #define XCT_TILE_S 4      // slices per tile (4 or 8): coordinates / bins / weights of a walk step are shared by all of them
 #endif
+#ifndef XCT_TILE_NVW
+// views a warp walks together over the tile (1 or 2): the voxel loads of a step are shared.  Measured at C5
+// (ms per application; one view x 12 warps: 305.4 -> 301.1 with the two columns' coordinates in packed fp32):
+// two views x 12 warps 295.8, two views x 10 warps 291.3; 8 slices x two views x 12 warps (1 CTA per SM) 296.3;
+// shared-memory data pipe 89 % -> 71 % busy, issue slots 78 % -> 80 % (profiles/ncu_r02_walk.md)
+#define XCT_TILE_NVW 2
+#endif
 constexpr int kWTileTN = XCT_TILE_TN, kWTileWin = XCT_TILE_WIN, kWTileWarps = XCT_TILE_WARPS, kWTileMinB = XCT_TILE_MINB;
-constexpr int kWTileS = XCT_TILE_S;
+constexpr int kWTileS = XCT_TILE_S, kWTileNVW = XCT_TILE_NVW;
 constexpr int kW2dTN = 8, kW2dWin = 160;  // 2D joint forward tile: 128 (major) x 8 (minor), one image
 // brick kernels (xct_brick.cuh): general 3D matrices
 constexpr int kBrAdjWR = 20, kBrAdjWC = 24, kBrAdjStages = 4;  // adjoint window of an 8^3 brick (columns start at a multiple of 4), ring depth
@@ -605,17 +612,17 @@ int launch_walk_forward_tile_class(const xct_plan* pl, const float* in, float* o
   if (tiles > 0x7fffffffLL) return fail(XCT_ERR_INVALID, "volume too large for the tile forward grid");
   // small problems: split the view list over blockIdx.y so that the grid fills the SMs (8 views run per CTA at a time)
   int chunks = 1;
-  if (tiles < 148LL * 3) chunks = (int)std::min<long long>((148LL * 3 + tiles - 1) / tiles, std::max(1, p.n_list / (2 * kWTileWarps)));
+  if (tiles < 148LL * 3) chunks = (int)std::min<long long>((148LL * 3 + tiles - 1) / tiles, std::max(1, p.n_list / (2 * kWTileWarps * kWTileNVW)));
   p.views_per_chunk = ceil_div(p.n_list, chunks);
   chunks = ceil_div(p.n_list, p.views_per_chunk);
-  const size_t smem = ((size_t)kWTileTN * 2 * 32 + (size_t)kWTileWarps * kWTileWin) * (kWTileS / 4) * sizeof(float4);
+  const size_t smem = ((size_t)kWTileTN * 2 * 32 + (size_t)kWTileWarps * kWTileNVW * kWTileWin) * (kWTileS / 4) * sizeof(float4);
   const dim3 grid((unsigned)tiles, chunks);
   if (pl->rows_krow) {
-    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWTileS, kWTileTN, kWTileWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_KROW, kWTileWarps, kWTileMinB>;
+    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWTileS, kWTileTN, kWTileWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_KROW, kWTileWarps, kWTileMinB, kWTileNVW>;
     XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kWTileWarps * 32, smem, st>>>(wp, in, out);
   } else {
-    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWTileS, kWTileTN, kWTileWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_TABLE, kWTileWarps, kWTileMinB>;
+    auto kern = xct::walk_forward_tile_kernel<xct::Geom3, kWTileS, kWTileTN, kWTileWin, MAJOR_B, MINOR_UP, MAJ_POS, xct::ROWS_TABLE, kWTileWarps, kWTileMinB, kWTileNVW>;
     XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kWTileWarps * 32, smem, st>>>(wp, in, out);
   }

@@ -1031,14 +1031,21 @@ walk_forward_joint_kernel(Walk2Params wp, const float* __restrict__ in, float* _
 // LDS.128 instead of register operands.  Layout of the tile: xt[n][column parity][lane] as float4 (4 slices):
 // the lanes of one LDS.128 read 512 contiguous bytes.  Everything else -- the carried triple, the per-view E2
 // variant, the vector flush -- is walk_forward_joint_kernel's.
-template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int ROWS, int WARPS, int MINB>
+// NVW views per warp pass (1 or 2): the kernel is bound by shared-memory wavefronts (ncu: l1tex data pipe ~90 % busy;
+// per walk step of 256 updates 8 wavefronts are the two LDS.128 of the voxels and ~10 the window read-modify-writes).
+// With NVW = 2 a warp walks TWO views of its class over the tile together: the voxels of a step are loaded once and
+// feed both views' carried triples, i.e. 4 instead of 8 voxel wavefronts per 256 updates; the two walks are
+// independent instruction streams (more ILP per warp), each with its own window.
+template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int ROWS, int WARPS, int MINB, int NVW = 1>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __restrict__ sino) {
   static_assert(WIN % 32 == 0 && WIN <= 128 && (S == 4 || S == 8), "float4 window slots, flushed 4 bins per lane in one pass");
+  static_assert(NVW == 1 || NVW == 2, "one or two views per warp pass");
   using Vec = float4;
   // S slices = NV planes of 4: the tile and the windows are arrays of float4 per plane, so every shared access
   // stays a conflict-free LDS.128 / STS.128 over 512 contiguous bytes; the coordinates, bins and weights of a
-  // walk step are evaluated once for all S slices (S = 8: half the per-update arithmetic of S = 4)
+  // walk step are evaluated once for all S slices (measured at C5: S = 8 is not faster than S = 4 -- the shared
+  // wavefronts per update are the same)
   constexpr int NV = S / 4;
   constexpr int GS = 2, H = S / 2, Q = WIN / 32, TM = 32 * GS;
   constexpr int DF = MAJ_POS ? 0 : 1, DG = 1 - DF;
@@ -1046,8 +1053,8 @@ walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __
   const PlaneParams& p = wp.p;
   extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  Vec* xt = reinterpret_cast<Vec*>(smem);                                       // [NV][TN][2][32]
-  Vec* winv = reinterpret_cast<Vec*>(smem) + NV * XPLANE + warp * (NV * WIN);   // [NV][WIN]
+  Vec* xt = reinterpret_cast<Vec*>(smem);                                             // [NV][TN][2][32]
+  Vec* win0 = reinterpret_cast<Vec*>(smem) + NV * XPLANE + warp * (NVW * NV * WIN);   // [NVW][NV][WIN]
   long long task = blockIdx.x;
   const int tb_ = (int)(task % p.tilesB);
   task /= p.tilesB;
@@ -1074,7 +1081,7 @@ walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __
   __syncthreads();
   const float xmin0 = MAJOR_B ? G::coordA(a0) : G::coordB(b0);
 
-  auto rmw = [&](int t, const float2 (&v)[H]) {  // win[t][:] += v   (one lane per address)
+  auto rmw = [&](Vec* winv, int t, const float2 (&v)[H]) {  // win[t][:] += v   (one lane per address)
 #pragma unroll
     for (int pv = 0; pv < NV; ++pv) {
       Vec* q = winv + pv * WIN + t;
@@ -1090,31 +1097,43 @@ walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __
 
   const int v_begin = blockIdx.y * p.views_per_chunk;
   const int v_end = min(p.n_list, v_begin + p.views_per_chunk);
-  for (int vi = v_begin + warp; vi < v_end; vi += WARPS) {
-    const int v = p.view_list ? __ldg(p.view_list + vi) : vi;
-    const ViewRec vr = load_view(p.views + v);
-    const int c0 = window_start<G>(vr, a0, a0 + (MAJOR_B ? TN : TM) - 1, b0, b0 + (MAJOR_B ? TM : TN) - 1) & ~3;
+  for (int vi = v_begin + NVW * warp; vi < v_end; vi += NVW * WARPS) {
+    // the pass's views; a missing second view (odd count) repeats the first one and is not flushed
+    int v[NVW];
+    ViewRec vr[NVW];
+    int c0[NVW];
+    float hF[NVW], hG[NVW];
+    bool e2 = false;
+#pragma unroll
+    for (int w = 0; w < NVW; ++w) {
+      const int vj = min(vi + w, v_end - 1);
+      v[w] = p.view_list ? __ldg(p.view_list + vj) : vj;
+      vr[w] = load_view(p.views + v[w]);
+      c0[w] = window_start<G>(vr[w], a0, a0 + (MAJOR_B ? TN : TM) - 1, b0, b0 + (MAJOR_B ? TM : TN) - 1) & ~3;
+      hF[w] = MAJOR_B ? G::hoistB(vr[w], b0 + GS * lane + DF) : G::hoistA(vr[w], a0 + GS * lane + DF);
+      hG[w] = MAJOR_B ? G::hoistB(vr[w], b0 + GS * lane + DG) : G::hoistA(vr[w], a0 + GS * lane + DG);
+      e2 = e2 || vr[w].fjump != 0.f;
+    }
 
 #pragma unroll
-    for (int q = 0; q < NV * Q; ++q) winv[lane + 32 * q] = vzero;
+    for (int q = 0; q < NVW * NV * Q; ++q) win0[lane + 32 * q] = vzero;
     __syncwarp();
 
-    const float hF = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + DF) : G::hoistA(vr, a0 + GS * lane + DF);
-    const float hG = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + DG) : G::hoistA(vr, a0 + GS * lane + DG);
-    auto walk_view = [&](auto e2_c) {
+    auto walk_views = [&](auto e2_c) {
       constexpr bool E2 = decltype(e2_c)::value;
-      float2 A0[H], A1[H], A2[H];  // sums of bins tb, tb + 1, tb + 2
+      float2 A0[NVW][H], A1[NVW][H], A2[NVW][H];  // per view: sums of bins tb, tb + 1, tb + 2
+      int tb[NVW];
 #pragma unroll
-      for (int h = 0; h < H; ++h) A0[h] = A1[h] = A2[h] = zero2;
-      // bin of F at the first step: the triple starts there (the loop below then never moves at n = 0)
-      int tb;
-      {
-        const float hm = MAJOR_B ? G::hoistA_x(vr, xmin0) : G::hoistB_x(vr, xmin0);
-        const float uF = MAJOR_B ? G::combine(vr, hm, hF) : G::combine(vr, hF, hm);
-        tb = (int)min((unsigned)(__float2int_rd(uF) - c0), (unsigned)(WIN - (E2 ? 4 : 3)));
+      for (int w = 0; w < NVW; ++w) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) A0[w][h] = A1[w][h] = A2[w][h] = zero2;
+        // bin of F at the first step: the triple starts there (the loop below then never moves at n = 0)
+        const float hm = MAJOR_B ? G::hoistA_x(vr[w], xmin0) : G::hoistB_x(vr[w], xmin0);
+        const float uF = MAJOR_B ? G::combine(vr[w], hm, hF[w]) : G::combine(vr[w], hF[w], hm);
+        tb[w] = (int)min((unsigned)(__float2int_rd(uF) - c0[w]), (unsigned)(WIN - (E2 ? 4 : 3)));
       }
       float xm = xmin0;  // minor-axis coordinate of the step; + 1 is exact
-#pragma unroll(S == 4 ? 8 : 4)
+#pragma unroll(S == 4 && NVW == 1 ? 8 : 4)
       for (int n = 0; n < TN; ++n, xm += 1.0f) {
         float2 xF[H], xG[H];
 #pragma unroll
@@ -1125,101 +1144,118 @@ walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __
           xG[2 * pv] = make_float2(xg4.x, xg4.y);
           xG[2 * pv + 1] = make_float2(xg4.z, xg4.w);
         }
-        const float hm = MAJOR_B ? G::hoistA_x(vr, xm) : G::hoistB_x(vr, xm);
-        const float uF = MAJOR_B ? G::combine(vr, hm, hF) : G::combine(vr, hF, hm);
-        const float uG = MAJOR_B ? G::combine(vr, hm, hG) : G::combine(vr, hG, hm);
-        int cF, cG;
-        float wF0, wF1, wG0, wG1;
-        G::bins(vr, uF, cF, wF0, wF1);
-        G::bins(vr, uG, cG, wG0, wG1);
-        const int tF = (int)min((unsigned)(cF - c0), (unsigned)(WIN - (E2 ? 4 : 3)));
-        const bool e = cG != cF;  // G one bin further
-        if (E2) {
-          const bool far = cG - cF >= 2;
-          if (__any_sync(0xffffffffu, far)) {
-            if (far) {
-              float2 g0[H], g1[H];
 #pragma unroll
-              for (int h = 0; h < H; ++h) {
-                g0[h] = __fmul2_rn(xG[h], make_float2(wG0, wG0));
-                g1[h] = __fmul2_rn(xG[h], make_float2(wG1, wG1));
+        for (int w = 0; w < NVW; ++w) {
+          Vec* winv = win0 + w * (NV * WIN);
+          // the two columns' coordinates, bins and weights in packed fp32 (component-wise the scalar expressions of
+          // Geom3::combine / bins; the products stay scalar, see the CAUTION in xct_geom.cuh)
+          const float hm = MAJOR_B ? G::hoistA_x(vr[w], xm) : G::hoistB_x(vr[w], xm);
+          const float2 hm2 = make_float2(hm, hm), hFG = make_float2(hF[w], hG[w]);
+          const float2 u2 = MAJOR_B ? G::combine2(vr[w], hm2, hFG) : G::combine2(vr[w], hFG, hm2);
+          int cF, cG;
+          float2 w0_2, w1_2;
+          G::bins2(vr[w], u2, cF, cG, w0_2, w1_2);
+          const float wF0 = w0_2.x, wF1 = w1_2.x;
+          float wG0 = w0_2.y, wG1 = w1_2.y;
+          const int tF = (int)min((unsigned)(cF - c0[w]), (unsigned)(WIN - (E2 ? 4 : 3)));
+          const bool e = cG != cF;  // G one bin further
+          if (E2) {
+            const bool far = cG - cF >= 2;
+            if (__any_sync(0xffffffffu, far)) {
+              if (far) {
+                float2 g0[H], g1[H];
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                  g0[h] = __fmul2_rn(xG[h], make_float2(wG0, wG0));
+                  g1[h] = __fmul2_rn(xG[h], make_float2(wG1, wG1));
+                }
+                rmw(winv, tF + 2, g0);
+                rmw(winv, tF + 3, g1);
               }
-              rmw(tF + 2, g0);
-              rmw(tF + 3, g1);
+              __syncwarp();
             }
-            __syncwarp();
+            if (far) wG0 = wG1 = 0.f;  // G is accounted for
           }
-          if (far) wG0 = wG1 = 0.f;  // G is accounted for
-        }
-        const float wa = e ? 0.f : wG0, wb = e ? wG0 : wG1, wc = e ? wG1 : 0.f;
-        const float2 wF0p = make_float2(wF0, wF0), wF1p = make_float2(wF1, wF1);
-        const float2 wap = make_float2(wa, wa), wbp = make_float2(wb, wb), wcp = make_float2(wc, wc);
-        if (tF != tb) {  // F moved by one bin: the bin leaving the carried triple is complete for this walk
-          if (MINOR_UP) {
-            rmw(tb, A0);
+          const float wa = e ? 0.f : wG0, wb = e ? wG0 : wG1, wc = e ? wG1 : 0.f;
+          const float2 wF0p = make_float2(wF0, wF0), wF1p = make_float2(wF1, wF1);
+          const float2 wap = make_float2(wa, wa), wbp = make_float2(wb, wb), wcp = make_float2(wc, wc);
+          if (tF != tb[w]) {  // F moved by one bin: the bin leaving the carried triple is complete for this walk
+            if (MINOR_UP) {
+              rmw(winv, tb[w], A0[w]);
 #pragma unroll
-            for (int h = 0; h < H; ++h) { A0[h] = A1[h]; A1[h] = A2[h]; A2[h] = zero2; }
-          } else {
-            rmw(tb + 2, A2);
+              for (int h = 0; h < H; ++h) { A0[w][h] = A1[w][h]; A1[w][h] = A2[w][h]; A2[w][h] = zero2; }
+            } else {
+              rmw(winv, tb[w] + 2, A2[w]);
 #pragma unroll
-            for (int h = 0; h < H; ++h) { A2[h] = A1[h]; A1[h] = A0[h]; A0[h] = zero2; }
+              for (int h = 0; h < H; ++h) { A2[w][h] = A1[w][h]; A1[w][h] = A0[w][h]; A0[w][h] = zero2; }
+            }
+            tb[w] = tF;
           }
-          tb = tF;
-        }
-        __syncwarp();  // order this step's stores before the next step's loads of other lanes
+          // order this step's stores before the next step's loads of other lanes (windows are per view: one
+          // barrier per step after the last view's stores is enough)
+          if (w == NVW - 1) __syncwarp();
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-          A0[h] = __ffma2_rn(xG[h], wap, __ffma2_rn(xF[h], wF0p, A0[h]));
-          A1[h] = __ffma2_rn(xG[h], wbp, __ffma2_rn(xF[h], wF1p, A1[h]));
-          A2[h] = __ffma2_rn(xG[h], wcp, A2[h]);
+          for (int h = 0; h < H; ++h) {
+            A0[w][h] = __ffma2_rn(xG[h], wap, __ffma2_rn(xF[h], wF0p, A0[w][h]));
+            A1[w][h] = __ffma2_rn(xG[h], wbp, __ffma2_rn(xF[h], wF1p, A1[w][h]));
+            A2[w][h] = __ffma2_rn(xG[h], wcp, A2[w][h]);
+          }
         }
       }
-      rmw(tb, A0);
+#pragma unroll
+      for (int w = 0; w < NVW; ++w) rmw(win0 + w * (NV * WIN), tb[w], A0[w]);
       __syncwarp();
-      rmw(tb + 1, A1);
+#pragma unroll
+      for (int w = 0; w < NVW; ++w) rmw(win0 + w * (NV * WIN), tb[w] + 1, A1[w]);
       __syncwarp();
-      rmw(tb + 2, A2);
+#pragma unroll
+      for (int w = 0; w < NVW; ++w) rmw(win0 + w * (NV * WIN), tb[w] + 2, A2[w]);
       __syncwarp();
     };
-    if (vr.fjump != 0.f) walk_view(std::true_type{});
-    else walk_view(std::false_type{});
+    if (e2) walk_views(std::true_type{});
+    else walk_views(std::false_type{});
 
-    // ---- flush the window: lane j owns bins 4j .. 4j+3 (entirely inside or outside [0, D1))
-    const int col = c0 + 4 * lane;
-    if (lane < WIN / 4 && (unsigned)col < (unsigned)p.D1) {
+    // ---- flush the windows: lane j owns bins 4j .. 4j+3 (entirely inside or outside [0, D1))
 #pragma unroll
-      for (int pv = 0; pv < NV; ++pv) {
-        float blk[4][4];
+    for (int w = 0; w < NVW; ++w) {
+      if (w > 0 && vi + w >= v_end) break;  // repeated view of an odd tail
+      const Vec* winv = win0 + w * (NV * WIN);
+      const int col = c0[w] + 4 * lane;
+      if (lane < WIN / 4 && (unsigned)col < (unsigned)p.D1) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const Vec r = winv[pv * WIN + 4 * lane + k];
-          blk[k][0] = r.x; blk[k][1] = r.y; blk[k][2] = r.z; blk[k][3] = r.w;
-        }
-        if (ROWS == ROWS_KROW) {
-          const int r0 = wp.s_base + s0 + 4 * pv + vr.krow;  // local detector row of the plane's first slice
-          float* y = sino + ((long long)v * p.D0 + r0) * (long long)p.D1 + col;
+        for (int pv = 0; pv < NV; ++pv) {
+          float blk[4][4];
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
-                                 __float_as_uint(blk[3][s]);  // all four +0: nothing to add
-            const bool live = s0 + 4 * pv + s < p.NS && (unsigned)(r0 + s) < (unsigned)p.D0 && any != 0u;
-            red_add_v4_if(live, y + (long long)s * p.D1, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+          for (int k = 0; k < 4; ++k) {
+            const Vec r = winv[pv * WIN + 4 * lane + k];
+            blk[k][0] = r.x; blk[k][1] = r.y; blk[k][2] = r.z; blk[k][3] = r.w;
           }
-        } else {
-          const long long* ro = wp.rowoff + (size_t)v * wp.row_stride + wp.s_base;
+          if (ROWS == ROWS_KROW) {
+            const int r0 = wp.s_base + s0 + 4 * pv + vr[w].krow;  // local detector row of the plane's first slice
+            float* y = sino + ((long long)v[w] * p.D0 + r0) * (long long)p.D1 + col;
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const int sl = min(s0 + 4 * pv + s, p.NS - 1);
-            const long long off = __ldg(ro + sl);
-            const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
-                                 __float_as_uint(blk[3][s]);
-            const bool live = s0 + 4 * pv + s < p.NS && off >= 0 && any != 0u;
-            red_add_v4_if(live, sino + (live ? off : 0) + col, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+            for (int s = 0; s < 4; ++s) {
+              const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
+                                   __float_as_uint(blk[3][s]);  // all four +0: nothing to add
+              const bool live = s0 + 4 * pv + s < p.NS && (unsigned)(r0 + s) < (unsigned)p.D0 && any != 0u;
+              red_add_v4_if(live, y + (long long)s * p.D1, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+            }
+          } else {
+            const long long* ro = wp.rowoff + (size_t)v[w] * wp.row_stride + wp.s_base;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              const int sl = min(s0 + 4 * pv + s, p.NS - 1);
+              const long long off = __ldg(ro + sl);
+              const unsigned any = __float_as_uint(blk[0][s]) | __float_as_uint(blk[1][s]) | __float_as_uint(blk[2][s]) |
+                                   __float_as_uint(blk[3][s]);
+              const bool live = s0 + 4 * pv + s < p.NS && off >= 0 && any != 0u;
+              red_add_v4_if(live, sino + (live ? off : 0) + col, blk[0][s], blk[1][s], blk[2][s], blk[3][s]);
+            }
           }
         }
       }
     }
-    __syncwarp();  // all window reads done before the next view zeroes it
+    __syncwarp();  // all window reads done before the next pass zeroes them
   }
 }
 
