@@ -47,6 +47,9 @@ CASES = {
     "3d_plane": (lambda: sb.XRayTransform3D((17, 18, 19), _x_mats((17, 18, 19), (20, 21), 5), (20, 21)), 1, [0, 8, 17]),
     "3d_sep_walk_plan": (lambda: sb.XRayTransform3D((24, 96, 80), _x_mats((24, 96, 80), (24, 128), 12), (24, 128)), 2,
                          [0, 6, 12, 18, 24]),
+    # the scalar-tap walk adjoint (the default plan above routes through the slice-interleaved kernel)
+    "3d_sep_walk_plan_scalar_taps": (lambda: sb.XRayTransform3D((24, 96, 80), _x_mats((24, 96, 80), (24, 128), 12), (24, 128),
+                                                                 _flags=_lib.FLAG_NO_ADJ_VEC), 2, [0, 6, 12, 18, 24]),
     "3d_general": (lambda: sb.XRayTransform3D((17, 18, 19), _tilt_mats((17, 18, 19), (20, 21), 5), (20, 21)), 3,
                    [0, 5, 11, 17]),  # brick adjoint, cp.async-staged window (odd detector width)
     "3d_general_tma": (lambda: sb.XRayTransform3D((21, 30, 37), _tilt_mats((21, 30, 37), (44, 48), 7), (44, 48)), 3,
