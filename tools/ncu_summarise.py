@@ -22,6 +22,7 @@ KEYS = {
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue active %",
     "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_active": "LSU writeback %",
     "l1tex__data_pipe_lsu_wavefronts.sum": "LSU wavefronts",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1tex data pipe % (shared-memory wavefronts)",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "shared wavefronts",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "shared bank-conflict wavefronts",
     "lts__t_sector_hit_rate.pct": "L2 hit %",
