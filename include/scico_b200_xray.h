@@ -153,7 +153,11 @@ XCT_API int xct3d_plan_analyse(const xct3d_geom *geom, xct_plan_info *info, xct_
  * `batch` must be 1 for 3D plans.  `out` is fully overwritten (it may be uninitialised). */
 XCT_API int xct_forward(const xct_plan *plan, const float *in_dev, float *out_dev, int32_t batch,
                         void *stream);
-/* Back projection (exact adjoint).  in: (batch, *output_shape)  out: (batch, *input_shape). */
+/* Back projection (exact adjoint).  in: (batch, *output_shape)  out: (batch, *input_shape).
+ * 3D separable plans whose classes report adj_interleaved own a scratch of the sinogram's size (the detector rows
+ * of four consecutive slices interleaved per bin), allocated by xct3d_plan_create and rewritten by every call:
+ * xct_adjoint itself never allocates; calls on different streams are ordered on the scratch by an event (not inside
+ * a stream capture, where the graph's own order applies). */
 XCT_API int xct_adjoint(const xct_plan *plan, const float *in_dev, float *out_dev, int32_t batch,
                         void *stream);
 

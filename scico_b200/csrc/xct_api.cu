@@ -122,9 +122,8 @@ struct xct_plan {
   bool rows_krow = false;  // local detector row of slice i is i + ViewRec::krow in every view (or none)
   bool adj_tma = false;    // walk adjoint stages its sinogram window with one TMA box per view (rows = slice + krow)
   bool adj_vec = false;    // slice-interleaved walk adjoint possible (adj_tma and every view's window fits kWVecWin)
-  float* d_sinoT = nullptr;             // (V, ceil(n0 / 4), d1, 4) interleaved copy of the sinogram, made per call
+  float* d_sinoT = nullptr;             // (V, ceil(n0 / 4), d1, 4) interleaved copy of the sinogram, made per call; allocated with the plan
   cudaEvent_t sinoT_ev = nullptr;       // last reader of d_sinoT (orders its reuse across streams)
-  bool sinoT_failed = false;            // the scratch could not be allocated: scalar-tap kernel from then on
   bool fwd_walk = false;
   bool fwd_cold = false;   // some view's minor-axis coefficient can move the bin by more than one per step
   bool fwd_unit4 = false;  // vector flush possible (unit rows, D1 % 4 == 0, window fits with 4-bin alignment)
@@ -378,33 +377,20 @@ int launch_plane_adjoint(const xct_plan* pl, int batch, const float* in, float* 
 
 // Slice-interleaved walk adjoint: interleave the detector rows of the launch's slices four by four into the plan's
 // scratch (sino_interleave4_kernel), then walk_adjoint_vec_kernel with one TMA box of that copy per (view, tile).
-// Returns 1 when this path cannot be taken (no scratch memory, stream capture in progress before the scratch
-// exists, tensor map not encodable): the caller then launches the scalar-tap kernel.
+// Returns 1 when this path cannot be taken (tensor map not encodable): the caller then launches the scalar-tap kernel.
 int launch_walk_adjoint_vec(const xct_plan* cpl, const float* in, float* out, cudaStream_t st, int s_begin, int s_count,
                             const xct::OutRoute* route) {
   xct_plan* pl = const_cast<xct_plan*>(cpl);  // the scratch and its event are caches, not plan state
   const int g_total = ceil_div(pl->n0, 4);
-  if (pl->sinoT_failed) return 1;
-  // inside a stream capture (CUDA graphs, XLA command buffers) nothing is allocated and the cross-stream event is
-  // neither waited on nor recorded: a replayed graph is ordered by its own stream like any other kernel sequence
+  if (!pl->d_sinoT) return 1;
+  // inside a stream capture (CUDA graphs, XLA command buffers) the cross-stream event is neither waited on nor
+  // recorded: a replayed graph is ordered by its own stream like any other kernel sequence
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
     cudaGetLastError();
     return 1;
   }
   const bool capturing = cap != cudaStreamCaptureStatusNone;
-  if (!pl->d_sinoT) {
-    if (capturing) return 1;  // an uncaptured call creates the scratch
-    const size_t bytes = (size_t)pl->V * g_total * pl->d1 * 4 * sizeof(float);
-    if (cudaMalloc(&pl->d_sinoT, bytes) != cudaSuccess || cudaEventCreateWithFlags(&pl->sinoT_ev, cudaEventDisableTiming) != cudaSuccess) {
-      cudaGetLastError();
-      cudaFree(pl->d_sinoT);
-      pl->d_sinoT = nullptr;
-      pl->sinoT_failed = true;
-      return 1;
-    }
-    XCT_CUDA(cudaEventRecord(pl->sinoT_ev, st));
-  }
   xct::Walk2Params wp{};
   wp.p = plane_params(pl, 1);
   wp.rowoff = pl->d_rowoff;
@@ -1240,6 +1226,19 @@ static int plan3d_create_impl(xct_plan** out, const xct3d_geom* g, bool dry) {
       pl->adj_walk = env.adj_ok && env.adj_walk_ok && unit && (g->d1 % 4 == 0) && !(g->flags & XCT_FLAG_NO_WALK);
       pl->adj_tma = pl->adj_tma && pl->adj_walk;  // the TMA box is the walk adjoint's staging
       pl->adj_vec = pl->adj_tma && env.adj_vec_ok && !(g->flags & XCT_FLAG_NO_ADJ_VEC);
+      if (pl->adj_vec && !dry) {
+        // the interleaved copy of the sinogram is made by every adjoint call into this scratch: allocated HERE, so
+        // that xct_adjoint itself never allocates (XLA execute stage, stream capture); without the memory the plan
+        // keeps the scalar-tap kernel
+        const size_t bytes = (size_t)V * ceil_div(g->n0, 4) * g->d1 * 4 * sizeof(float);
+        if (cudaMalloc(&pl->d_sinoT, bytes) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pl->sinoT_ev, cudaEventDisableTiming) != cudaSuccess) {
+          cudaGetLastError();
+          cudaFree(pl->d_sinoT);
+          pl->d_sinoT = nullptr;
+          pl->adj_vec = false;
+        }
+      }
       pl->gs = env.fwd_ok ? env.gs : 0;
       pl->pipe_ok = pl->pipe_ok && pl->fwd_walk && pl->adj_walk && !(g->flags & XCT_FLAG_NO_HOST_PIPELINE);
       if (pl->adj_plane && pl->fwd_plane) pl->path = XCT_PATH_3D_SEP;
