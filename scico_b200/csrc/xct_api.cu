@@ -383,6 +383,7 @@ int launch_walk_adjoint_vec(const xct_plan* cpl, const float* in, float* out, cu
   xct_plan* pl = const_cast<xct_plan*>(cpl);  // the scratch and its event are caches, not plan state
   const int g_total = ceil_div(pl->n0, 4);
   if (!pl->d_sinoT) return 1;
+  if (pl->V > 65535 || ceil_div(pl->n0, 4) > 65535) return 1;  // grid limits of the interleaving pass
   // inside a stream capture (CUDA graphs, XLA command buffers) the cross-stream event is neither waited on nor
   // recorded: a replayed graph is ordered by its own stream like any other kernel sequence
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
