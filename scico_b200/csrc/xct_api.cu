@@ -92,6 +92,13 @@ constexpr int kWFwdS = 4, kWFwdTN = 8;     // walk forward tile: 64 (major) x 8 
 constexpr int kWTileTN = XCT_TILE_TN, kWTileWin = XCT_TILE_WIN, kWTileWarps = XCT_TILE_WARPS, kWTileMinB = XCT_TILE_MINB;
 constexpr int kWTileS = XCT_TILE_S, kWTileNVW = XCT_TILE_NVW;
 constexpr int kW2dTN = 8, kW2dWin = 160;  // 2D joint forward tile: 128 (major) x 8 (minor), one image
+// 2D joint forward on a CTA-shared tile: 128 (major) x kW2dTileTN (minor) pixels, kW2dTileWarps views in flight per CTA
+#ifndef XCT_TILE2D_TN
+#define XCT_TILE2D_TN 64
+#define XCT_TILE2D_WIN 192   // 127 |c_major| + 63 |c_minor| + 4 <= 192 for every pixel size up to one bin per pixel
+#define XCT_TILE2D_WARPS 8
+#endif
+constexpr int kW2dTileTN = XCT_TILE2D_TN, kW2dTileWin = XCT_TILE2D_WIN, kW2dTileWarps = XCT_TILE2D_WARPS;
 // brick kernels (xct_brick.cuh): general 3D matrices
 constexpr int kBrAdjWR = 20, kBrAdjWC = 24, kBrAdjStages = 4;  // adjoint window of an 8^3 brick (columns start at a multiple of 4), ring depth
 constexpr int kBrFwdWR = 24, kBrFwdWC = 24;                    // forward window of an 8 x 16 x 4 brick
@@ -135,6 +142,7 @@ struct xct_plan {
   bool fwd_joint = false;
   bool fwd_tile = false;     // joint forward with the CTA-shared tile (walk_forward_tile_kernel): unit rows, window fits TN = 32
   bool fwd_joint2d = false;  // 2D: every view inside walk2d_forward_joint_kernel's envelope
+  bool fwd_tile2d = false;   // 2D: ... and inside walk2d_forward_tile_kernel's window (large problems run on the CTA-shared tile)
   bool fwd_2d_per_class = false;  // XCT_FLAG_2D_PER_CLASS: one launch per view class even for small problems (A/B)
   int* d_listJ[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int n_listJ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -741,11 +749,48 @@ int launch_walk2d_forward_all(const xct_plan* pl, int batch, const float* in, fl
   return launch_ok("walk2d_forward_joint_all_kernel");
 }
 
+// 2D joint forward on a CTA-shared tile: one launch per (major axis, minor sign, major sign) class
+template <bool MAJOR_B, bool MINOR_UP, bool MAJ_POS>
+int launch_walk2d_forward_tile_class(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
+  const int cls = (MAJOR_B ? 4 : 0) + (MINOR_UP ? 2 : 0) + (MAJ_POS ? 1 : 0);
+  if (pl->n_listJ[cls] == 0) return XCT_OK;
+  xct::PlaneParams p = plane_params(pl, batch);
+  p.view_list = pl->d_listJ[cls];
+  p.n_list = pl->n_listJ[cls];
+  p.tilesA = ceil_div(p.NA, MAJOR_B ? kW2dTileTN : 128);
+  p.tilesB = ceil_div(p.NB, MAJOR_B ? 128 : kW2dTileTN);
+  const long long tiles = (long long)p.NS * p.tilesA * p.tilesB;
+  if (tiles > 0x7fffffffLL) return fail(XCT_ERR_INVALID, "image batch too large for the 2D tile forward grid");
+  // split the view list over blockIdx.y until the grid is ~8 waves of resident CTAs (5 per SM): a CTA that runs all
+  // views of its class is long, and a last wave that is 3/4 full costs its whole duration
+  long long target = 148LL * 40;
+  if (const char* env = std::getenv("XCT_2D_TILE_TARGET_CTAS")) target = std::max(1, std::atoi(env));  // tuning (tools/bench_2d.py)
+  int chunks = 1;
+  if (tiles < target) chunks = (int)std::min<long long>((target + tiles - 1) / tiles, std::max(1, p.n_list / (2 * kW2dTileWarps)));
+  p.views_per_chunk = ceil_div(p.n_list, chunks);
+  chunks = ceil_div(p.n_list, p.views_per_chunk);
+  const size_t smem = ((size_t)kW2dTileTN * 32 * 4 + (size_t)kW2dTileWarps * kW2dTileWin) * sizeof(float);
+  auto kern = xct::walk2d_forward_tile_kernel<xct::Geom2, kW2dTileTN, kW2dTileWin, MAJOR_B, MINOR_UP, MAJ_POS, kW2dTileWarps>;
+  if (smem > 48 * 1024) XCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3((unsigned)tiles, chunks), kW2dTileWarps * 32, smem, st>>>(p, in, out);
+  return launch_ok("walk2d_forward_tile_kernel");
+}
+
 int launch_walk2d_forward(const xct_plan* pl, int batch, const float* in, float* out, cudaStream_t st) {
   // below ~2 waves of CTAs per class the per-launch ramp-up and tail dominate: one launch for all classes
   if ((long long)batch * pl->n0 * pl->n1 * pl->V <= (1LL << 29) && !pl->fwd_2d_per_class)
     return launch_walk2d_forward_all(pl, batch, in, out, st);
   int rc;
+  if (pl->fwd_tile2d) {  // large problems: the CTA-shared tile (64-step walks)
+    if ((rc = launch_walk2d_forward_tile_class<true, true, true>(pl, batch, in, out, st))) return rc;
+    if ((rc = launch_walk2d_forward_tile_class<true, true, false>(pl, batch, in, out, st))) return rc;
+    if ((rc = launch_walk2d_forward_tile_class<true, false, true>(pl, batch, in, out, st))) return rc;
+    if ((rc = launch_walk2d_forward_tile_class<true, false, false>(pl, batch, in, out, st))) return rc;
+    if ((rc = launch_walk2d_forward_tile_class<false, true, true>(pl, batch, in, out, st))) return rc;
+    if ((rc = launch_walk2d_forward_tile_class<false, true, false>(pl, batch, in, out, st))) return rc;
+    if ((rc = launch_walk2d_forward_tile_class<false, false, true>(pl, batch, in, out, st))) return rc;
+    return launch_walk2d_forward_tile_class<false, false, false>(pl, batch, in, out, st);
+  }
   if ((rc = launch_walk2d_forward_class<true, true, true>(pl, batch, in, out, st))) return rc;
   if ((rc = launch_walk2d_forward_class<true, true, false>(pl, batch, in, out, st))) return rc;
   if ((rc = launch_walk2d_forward_class<true, false, true>(pl, batch, in, out, st))) return rc;
@@ -1047,6 +1092,12 @@ static int plan2d_create_impl(xct_plan** out, const xct2d_geom* g, bool dry) {
     }
     pl->fwd_joint2d = ok;
     pl->fwd_2d_per_class = (g->flags & XCT_FLAG_2D_PER_CLASS) != 0;
+    bool tile_ok = ok && !(g->flags & XCT_FLAG_NO_TILE);
+    for (const auto& vr : views) {
+      const float mj = std::max(std::fabs(vr.ca), std::fabs(vr.cb)), mn = std::min(std::fabs(vr.ca), std::fabs(vr.cb));
+      if (!(mj * 127.f + mn * (kW2dTileTN - 1) + 4.f <= (float)kW2dTileWin)) tile_ok = false;
+    }
+    pl->fwd_tile2d = tile_ok;
   }
 
   auto cleanup = [&](int code) { xct_plan_destroy(pl); return code; };
@@ -1286,7 +1337,7 @@ static void fill_classes(const xct_plan* pl, xct_plan_classes* c) {
   c->rows_consecutive = pl->rows_krow ? 1 : 0;
   c->fwd_cold = pl->fwd_cold ? 1 : 0;
   for (int k = 0; k < 6; ++k) c->brick_views[k] = pl->n_listB[k];
-  c->fwd_tile = pl->fwd_tile ? 1 : 0;
+  c->fwd_tile = (pl->fwd_tile || pl->fwd_tile2d) ? 1 : 0;
   c->adj_interleaved = pl->adj_vec ? 1 : 0;
 }
 int xct_plan_get_classes(const xct_plan* pl, xct_plan_classes* classes) {

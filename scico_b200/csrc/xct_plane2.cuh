@@ -1377,6 +1377,137 @@ walk2d_forward_joint_kernel(PlaneParams p, const float* __restrict__ in, float* 
   walk2d_forward_joint_body<G, TN, WIN, MAJOR_B, MINOR_UP, MAJ_POS, WARPS>(p, in, sino, smem, blockIdx.x, blockIdx.y);
 }
 
+// ----------------------------------------------------- 2D forward, joint column pairs, CTA-shared tile
+// walk2d_forward_joint_kernel keeps a warp's pixels in registers, which caps a walk at TN = 8 steps: per (view, tile)
+// of 1024 updates the window is zeroed and flushed, six end-of-walk read-modify-writes are paid and the view
+// preamble -- ~16 % of its instructions (it is issue-bound: ncu issue active 85 %).  Here, as in
+// walk_forward_tile_kernel, the CTA stages ONE tile of 128 (major) x TN = 64 (minor) pixels in shared memory
+// (xt[step][lane] as float4 = the lane's four columns: one conflict-free LDS.128 per step) and its warps run different
+// VIEWS on it, each with a private window: the per-(view, tile) costs are spread over 8192 updates.  The two column
+// pairs of a lane are walked together step by step (pair-major order would load the tile twice).
+template <class G, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ_POS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+walk2d_forward_tile_kernel(PlaneParams p, const float* __restrict__ in, float* __restrict__ sino) {
+  static_assert(WIN % 32 == 0, "window is flushed 32 bins at a time");
+  constexpr int GS = 4, TM = 32 * GS, Q = WIN / 32;
+  constexpr int DF0 = MAJ_POS ? 0 : 1;
+  extern __shared__ __align__(128) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* xt = reinterpret_cast<float4*>(smem);       // [TN][32]
+  float* win = smem + TN * 32 * 4 + warp * WIN;       // [WIN]
+  long long task = blockIdx.x;
+  const int tb_ = (int)(task % p.tilesB);
+  task /= p.tilesB;
+  const int ta = (int)(task % p.tilesA);
+  const int sl = (int)(task / p.tilesA);  // image of the batch
+  const int a0 = ta * (MAJOR_B ? TN : TM), b0 = tb_ * (MAJOR_B ? TM : TN);
+
+  // ---- stage the tile: xt[n][l] = the four major-axis columns 4l .. 4l+3 of minor row n
+  const float* img = in + (size_t)sl * p.NA * (size_t)p.NB;
+  if (MAJOR_B) {  // columns are consecutive in memory: one (vector) load per slot
+    const bool vec = (p.NB & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    for (int n = warp; n < TN; n += WARPS) {
+      const int a = a0 + n, b = b0 + GS * lane;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a < p.NA) {
+        const float* q = img + (size_t)a * p.NB + b;
+        if (vec && b + 3 < p.NB) {
+          v = __ldg(reinterpret_cast<const float4*>(q));
+        } else {
+          if (b < p.NB) v.x = __ldg(q);
+          if (b + 1 < p.NB) v.y = __ldg(q + 1);
+          if (b + 2 < p.NB) v.z = __ldg(q + 2);
+          if (b + 3 < p.NB) v.w = __ldg(q + 3);
+        }
+      }
+      xt[n * 32 + lane] = v;
+    }
+  } else {  // minor axis is the contiguous one: coalesced reads along it, scattered shared stores (once per tile)
+    float* xs = smem;
+    for (int e = threadIdx.x; e < TM * TN; e += WARPS * 32) {
+      const int n = e % TN, am = e / TN;  // minor index (contiguous in memory), major index
+      const int a = a0 + am, b = b0 + n;
+      xs[(n * 32 + (am >> 2)) * 4 + (am & 3)] = (a < p.NA && b < p.NB) ? __ldg(img + (size_t)a * p.NB + b) : 0.f;
+    }
+  }
+  __syncthreads();
+  const float xmin0 = MAJOR_B ? G::coordA(a0) : G::coordB(b0);
+
+  auto rmw = [&](int t, float v) { win[t] += v; };  // one lane per address
+
+  const int v_begin = blockIdx.y * p.views_per_chunk;
+  const int v_end = min(p.n_list, v_begin + p.views_per_chunk);
+  for (int vi = v_begin + warp; vi < v_end; vi += WARPS) {
+    const int v = p.view_list ? __ldg(p.view_list + vi) : vi;
+    const ViewRec vr = load_view(p.views + v);
+    const int c0 = window_start<G>(vr, a0, a0 + (MAJOR_B ? TN : TM) - 1, b0, b0 + (MAJOR_B ? TM : TN) - 1);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) win[lane + 32 * q] = 0.f;
+    __syncwarp();
+
+    float2 hFG[2];
+    float A0[2], A1[2], A2[2];  // per pair: sums of bins tb, tb + 1, tb + 2
+    int tb[2];
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {
+      const int dF = 2 * pr + DF0, dG = 2 * pr + (1 - DF0);
+      const float hF = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + dF) : G::hoistA(vr, a0 + GS * lane + dF);
+      const float hG = MAJOR_B ? G::hoistB(vr, b0 + GS * lane + dG) : G::hoistA(vr, a0 + GS * lane + dG);
+      hFG[pr] = make_float2(hF, hG);
+      A0[pr] = A1[pr] = A2[pr] = 0.f;
+      // bin of F at the first step: the triple starts there (the loop below then never moves at n = 0)
+      const float hm = MAJOR_B ? G::hoistA_x(vr, xmin0) : G::hoistB_x(vr, xmin0);
+      tb[pr] = (int)min((unsigned)(__float2int_rd(G::combine(vr, MAJOR_B ? hm : hF, MAJOR_B ? hF : hm)) - c0), (unsigned)(WIN - 3));
+    }
+    float xm = xmin0;  // minor-axis coordinate of the step; + 1 is exact
+#pragma unroll 4
+    for (int n = 0; n < TN; ++n, xm += 1.0f) {
+      const float4 xv = xt[n * 32 + lane];
+      const float hm = MAJOR_B ? G::hoistA_x(vr, xm) : G::hoistB_x(vr, xm);
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+        const float x0 = pr ? xv.z : xv.x, x1 = pr ? xv.w : xv.y;
+        const float xF = DF0 ? x1 : x0, xG = DF0 ? x0 : x1;
+        const float2 u = __fadd2_rn(hFG[pr], make_float2(hm, hm));  // Geom2::combine: hA + hB (commutative)
+        int cF, cG;
+        float2 w0, w1;
+        G::bins2(vr, u, cF, cG, w0, w1);
+        const int tF = (int)min((unsigned)(cF - c0), (unsigned)(WIN - 3));
+        const bool e = cG != cF;  // G one bin further
+        const float wa = e ? 0.f : w0.y, wb = e ? w0.y : w1.y, wc = e ? w1.y : 0.f;
+        if (tF != tb[pr]) {  // F moved by one bin: the bin leaving the carried triple is complete for this walk
+          if (MINOR_UP) { rmw(tb[pr], A0[pr]); A0[pr] = A1[pr]; A1[pr] = A2[pr]; A2[pr] = 0.f; }
+          else { rmw(tb[pr] + 2, A2[pr]); A2[pr] = A1[pr]; A1[pr] = A0[pr]; A0[pr] = 0.f; }
+          tb[pr] = tF;
+        }
+        __syncwarp();  // order this pair's stores before the next read-modify-write of other lanes
+        A0[pr] = fmaf(xG, wa, fmaf(xF, w0.x, A0[pr]));
+        A1[pr] = fmaf(xG, wb, fmaf(xF, w1.x, A1[pr]));
+        A2[pr] = fmaf(xG, wc, A2[pr]);
+      }
+    }
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {
+      rmw(tb[pr], A0[pr]);
+      __syncwarp();
+      rmw(tb[pr] + 1, A1[pr]);
+      __syncwarp();
+      rmw(tb[pr] + 2, A2[pr]);
+      __syncwarp();
+    }
+
+    float* y0 = sino + ((size_t)sl * p.V + v) * (size_t)p.D1;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int t = lane + 32 * q;
+      const float val = win[t];
+      const int col = c0 + t;
+      if (val != 0.f && (unsigned)col < (unsigned)p.D1) atomicAdd(y0 + col, val);
+    }
+    __syncwarp();  // all window reads done before the next view zeroes it
+  }
+}
+
 // Small problems (BASELINE.json configs[1]: 512^2 x 360 views is ~0.1 ms of work): ONE launch for all eight
 // (major axis, minor sign, major sign) view classes instead of one launch each -- every class brings its own
 // ramp-up and tail, and four to eight of them are a third of the operator's time at this size.  A CTA looks its

@@ -362,6 +362,39 @@ def test_2d_joint_forward_matches_plane_kernel_and_oracle(torch_dev):
     assert O.rel_l2(_gpu(torch, dev, W, x), C.project_2d(x, W.view_table, W.ny)) <= TOL
 
 
+def test_2d_tile_forward_matches_register_stationary_forward_and_oracle(torch_dev):
+    """walk2d_forward_tile_kernel (128 x 64 pixel tile in shared memory, one view per warp, 64-step walks of both
+    column pairs) against walk2d_forward_joint_kernel (XCT_FLAG_NO_TILE) and the oracle.  Small problems normally take
+    the one-launch kernel, so XCT_FLAG_2D_PER_CLASS selects the per-class launches (the large-problem path): a full
+    turn (all eight view classes), ragged tiles in both axes, an anisotropic pixel, a short detector, one bin per
+    pixel, odd widths (scalar tile loads), a batch."""
+    torch, dev = torch_dev
+    rng = np.random.default_rng(45)
+    per_class = _lib.FLAG_2D_PER_CLASS
+    for nx, angles, kw in (
+        ((150, 140), np.linspace(0, 2 * np.pi, 24, endpoint=False), {}),
+        ((70, 131), np.linspace(0.01, 2 * np.pi + 0.01, 17, endpoint=False), dict(dx=(0.6, 0.7))),
+        ((64, 64), np.array([0.0, np.pi / 2, np.pi / 4, 3 * np.pi / 4, 1e-4, np.pi / 2 - 1e-4, 2.0]), {}),
+        ((96, 80), np.linspace(0, np.pi, 30, endpoint=False), dict(det_count=90)),
+        ((33, 130), np.linspace(0, np.pi, 9, endpoint=False), dict(dx=0.95)),
+        ((260, 264), np.linspace(0, np.pi, 40, endpoint=False), {}),
+    ):
+        A = sb.XRayTransform2D(nx, angles, _flags=per_class, **kw)
+        B = sb.XRayTransform2D(nx, angles, _flags=per_class | _lib.FLAG_NO_TILE, **kw)
+        assert A.analyse()["fwd_tile"] == 1 and B.analyse()["fwd_tile"] == 0 and B.plan_info()["fwd_joint"] == 1
+        x = rng.standard_normal(nx).astype(np.float32)
+        a, b = _gpu(torch, dev, A, x), _gpu(torch, dev, B, x)
+        ref = C.project_2d(x, A.view_table, A.ny)
+        assert O.rel_l2(a, b) <= 2e-6
+        for v in range(len(angles)):
+            assert O.rel_l2(a[v], ref[v]) <= TOL, v
+    A = sb.XRayTransform2D((40, 150), np.linspace(0, np.pi, 11, endpoint=False), _flags=per_class)
+    xb = rng.standard_normal((3, 40, 150)).astype(np.float32)
+    got = A.project(torch.as_tensor(xb, device=dev)).cpu().numpy()
+    for k in range(3):
+        assert O.rel_l2(got[k], C.project_2d(xb[k], A.view_table, A.ny)) <= TOL
+
+
 def test_brick_kernels_selected_and_match_thread_per_voxel_kernels(torch_dev):
     """General matrices run the brick kernels (TMA-staged adjoint window when detector rows are 16-byte aligned);
     they reproduce the thread-per-voxel family (XCT_FLAG_NO_BRICK) and the oracle, also through a z-slab with
