@@ -1598,7 +1598,30 @@ static int enqueue_host_pipelined(xct_plan* pl, const float* in_host, float* out
   }
   chunk = (chunk + 15) & ~15;  // whole slice groups of both kernels (4 slices forward, 16 adjoint)
   chunk = std::max(chunk, ((NS + 63) / 64 + 15) & ~15);  // at most 64 chunks (event table)
-  const int nchunks = ceil_div(NS, chunk);
+  // slice ranges: chunks of `chunk` slices, except that the first and the last one are halved (whole 16-slice groups):
+  // the first H2D copy and the last D2H copy are the only ones nothing overlaps, so they should be short
+  std::vector<int> bounds{0};
+  {
+    const int edge = (chunk >= 32 && NS >= 4 * chunk) ? ((chunk / 2 + 15) & ~15) : chunk;
+    int a = 0;
+    bool first = true;
+    while (a < NS) {
+      int left = NS - a;
+      const int len = first ? edge : chunk;
+      if (len >= left) {  // the end: one short chunk last (boundaries stay multiples of 16 slices)
+        if (edge < chunk && left > edge) {
+          const int head = (left - edge) & ~15;
+          if (head > 0) { a += head; bounds.push_back(a); }
+        }
+        bounds.push_back(NS);
+        break;
+      }
+      a += len;
+      bounds.push_back(a);
+      first = false;
+    }
+  }
+  const int nchunks = (int)bounds.size() - 1;
   const size_t ev_base = dir ? 2 * 64 : 0;  // each direction owns its events
   while (pl->events.size() < 4 * 64) {
     cudaEvent_t ev;
@@ -1634,7 +1657,7 @@ static int enqueue_host_pipelined(xct_plan* pl, const float* in_host, float* out
     for (int i = NS - 1; i >= 0; --i) first_from[i] = pl->h_row_lo[i] >= 0 ? std::min(first_from[i + 1], pl->h_row_lo[i]) : first_from[i + 1];
     int rows_done = 0;
     for (int k = 0; k < nchunks; ++k) {
-      const int a = k * chunk, b = std::min(NS, a + chunk);
+      const int a = bounds[k], b = bounds[k + 1];
       XCT_CUDA(cudaMemcpyAsync(vol_dev + a * slice, in_host + a * slice, (size_t)(b - a) * slice * sizeof(float),
                                cudaMemcpyHostToDevice, pl->s_in));
       XCT_CUDA(cudaEventRecord(ev(k, 0), pl->s_in));
@@ -1651,7 +1674,7 @@ static int enqueue_host_pipelined(xct_plan* pl, const float* in_host, float* out
   } else {
     int rows_up = 0;  // detector rows [0, rows_up) are on the device
     for (int k = 0; k < nchunks; ++k) {
-      const int a = k * chunk, b = std::min(NS, a + chunk);
+      const int a = bounds[k], b = bounds[k + 1];
       int need = rows_up;
       for (int i = a; i < b; ++i) need = std::max(need, pl->h_row_hi[i] + 1);
       XCT_CUDA(rows_copy(rows_up, need, true, pl->s_in));
