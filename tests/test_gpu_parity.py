@@ -395,6 +395,28 @@ def test_2d_tile_forward_matches_register_stationary_forward_and_oracle(torch_de
         assert O.rel_l2(got[k], C.project_2d(xb[k], A.view_table, A.ny)) <= TOL
 
 
+def test_pipelined_host_path_with_short_edge_chunks(torch_dev, monkeypatch):
+    """The host pipeline halves its first and last slice chunk (nothing overlaps the first H2D / the last D2H copy):
+    with 32-slice chunks on 130 and 150 slices the ranges are 16, 32, ..., 18 and 16, 32, 32, 32, 16, 22; results
+    equal the device entry points across every seam."""
+    torch, dev = torch_dev
+    monkeypatch.setenv("XCT_HOST_CHUNK_SLICES", "32")
+    rng = np.random.default_rng(23)
+    for N, D in (((130, 40, 48), (130, 72)), ((150, 36, 44), (140, 64))):
+        M = _x_mats(N, D, 7)
+        H = sb.XRayTransform3D(N, M, D)
+        x = rng.standard_normal(N).astype(np.float32)
+        y = rng.standard_normal(H.output_shape).astype(np.float32)
+        fwd_dev, adj_dev = _gpu(torch, dev, H, x), _gpu(torch, dev, H, y, adj=True)
+        out = np.full(H.output_shape, np.nan, np.float32)
+        H.project(x, out=out)
+        assert O.rel_l2(out, fwd_dev) <= 1e-6
+        np.testing.assert_array_equal(out == 0, fwd_dev == 0)
+        back = np.full(N, np.nan, np.float32)
+        H.back_project(y, out=back)
+        np.testing.assert_array_equal(back, adj_dev)
+
+
 def test_brick_kernels_selected_and_match_thread_per_voxel_kernels(torch_dev):
     """General matrices run the brick kernels (TMA-staged adjoint window when detector rows are 16-byte aligned);
     they reproduce the thread-per-voxel family (XCT_FLAG_NO_BRICK) and the oracle, also through a z-slab with
