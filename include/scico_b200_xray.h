@@ -276,6 +276,25 @@ XCT_API int xct_tv_dual_step(const xct_tv_block *blk, float *z1, const float *xb
                              float sigma, float lam, void *stream);
 /* z0 <- conj_prox_{sigma, 1/2 ||. - y||^2}(z0 + sigma ax), n elements. */
 XCT_API int xct_l2_dual_step(int64_t n, float *z0, const float *ax, const float *y, float sigma, void *stream);
+/* The same three steps with the iteration statistics of PDHG (scico/optimize/_primaldual.py:175-217:
+ * Objective = g(C x), Prml_Rsdl = ||x - x_old|| / tau, Dual_Rsdl = ||z - z_old|| / sigma) accumulated in the
+ * same pass into DEVICE doubles (added to: the caller zeroes them), so statistics cost neither copies of the old
+ * iterates nor a second forward projection:
+ *   primal: *sq_dx  += ||x_new - x_old||^2;      dual: *sq_dz1 += ||z1_new - z1_old||^2;
+ *   l2:     stat2[0] += ||z0_new - z0_old||^2;   ax_x <- (ax + alpha ax_x) / (1 + alpha) (= A x_new when ax_x held
+ *           A x_old: ax is A xbar and xbar = (1 + alpha) x_new - alpha x_old);   stat2[1] += ||ax_x - y||^2.
+ * The sinogram sums run over detector rows [row_lo, row_hi) of the (n / (rows inner), rows, inner) block (rows a
+ * z-slab shares with another slab are counted by their owner; pass inner = n, rows = 1, 0, 1 for everything).
+ * xct_tv_norm: *sum += ||D x||_{2,1} (L21Norm, l2_axis = 0, scico/functional/_norm.py:225-252). */
+XCT_API int xct_tv_primal_step_stat(const xct_tv_block *blk, float *x, float *xbar, const float *atz,
+                                    const float *z1, const float *lo_halo, float tau, float alpha,
+                                    int32_t nonneg, double *sq_dx, void *stream);
+XCT_API int xct_tv_dual_step_stat(const xct_tv_block *blk, float *z1, const float *xbar, const float *hi_halo,
+                                  float sigma, float lam, double *sq_dz1, void *stream);
+XCT_API int xct_l2_dual_step_stat(int64_t n, float *z0, const float *ax, const float *y, float sigma, float *ax_x,
+                                  float alpha, int64_t inner, int32_t rows, int32_t row_lo, int32_t row_hi,
+                                  double *stat2, void *stream);
+XCT_API int xct_tv_norm(const xct_tv_block *blk, const float *x, const float *hi_halo, double *sum, void *stream);
 /* FiniteDifference(append=0): out (3, n0, n1, n2) = D x;  out (n0, n1, n2) = D^T z1. */
 XCT_API int xct_fd_forward(const xct_tv_block *blk, const float *x, const float *hi_halo, float *out, void *stream);
 XCT_API int xct_fd_adjoint(const xct_tv_block *blk, const float *z1, const float *lo_halo, float *out, void *stream);

@@ -1884,31 +1884,74 @@ static xct::TvDims tv_dims(const xct_tv_block* b) {
 }
 static int tv_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148u * 32u); }
 
-int xct_tv_primal_step(const xct_tv_block* b, float* x, float* xbar, const float* atz, const float* z1,
-                       const float* lo_halo, float tau, float alpha, int32_t nonneg, void* stream) {
+static int tv_primal_impl(const xct_tv_block* b, float* x, float* xbar, const float* atz, const float* z1,
+                          const float* lo_halo, float tau, float alpha, int32_t nonneg, double* stat, void* stream) {
   int rc = tv_check(b, x, xbar);
   if (rc) return rc;
   if (!atz || !z1) return fail(XCT_ERR_INVALID, "null argument");
   const size_t n = (size_t)b->n0 * b->n1 * b->n2;
-  xct::tv_primal_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), x, xbar, atz, z1, lo_halo, tau, alpha, nonneg);
+  if (stat)
+    xct::tv_primal_kernel<true><<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), x, xbar, atz, z1, lo_halo, tau, alpha, nonneg, stat);
+  else
+    xct::tv_primal_kernel<false><<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), x, xbar, atz, z1, lo_halo, tau, alpha, nonneg, nullptr);
   return launch_ok("tv_primal_kernel");
 }
+int xct_tv_primal_step(const xct_tv_block* b, float* x, float* xbar, const float* atz, const float* z1,
+                       const float* lo_halo, float tau, float alpha, int32_t nonneg, void* stream) {
+  return tv_primal_impl(b, x, xbar, atz, z1, lo_halo, tau, alpha, nonneg, nullptr, stream);
+}
+int xct_tv_primal_step_stat(const xct_tv_block* b, float* x, float* xbar, const float* atz, const float* z1,
+                            const float* lo_halo, float tau, float alpha, int32_t nonneg, double* sq_dx, void* stream) {
+  if (!sq_dx) return fail(XCT_ERR_INVALID, "null statistics pointer");
+  return tv_primal_impl(b, x, xbar, atz, z1, lo_halo, tau, alpha, nonneg, sq_dx, stream);
+}
 
-int xct_tv_dual_step(const xct_tv_block* b, float* z1, const float* xbar, const float* hi_halo, float sigma,
-                     float lam, void* stream) {
+static int tv_dual_impl(const xct_tv_block* b, float* z1, const float* xbar, const float* hi_halo, float sigma,
+                        float lam, double* stat, void* stream) {
   int rc = tv_check(b, z1, xbar);
   if (rc) return rc;
   if (!(sigma > 0.f)) return fail(XCT_ERR_INVALID, "sigma must be positive");
   const size_t n = (size_t)b->n0 * b->n1 * b->n2;
-  xct::tv_dual_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), z1, xbar, hi_halo, sigma, lam);
+  if (stat)
+    xct::tv_dual_kernel<true><<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), z1, xbar, hi_halo, sigma, lam, stat);
+  else
+    xct::tv_dual_kernel<false><<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), z1, xbar, hi_halo, sigma, lam, nullptr);
   return launch_ok("tv_dual_kernel");
+}
+int xct_tv_dual_step(const xct_tv_block* b, float* z1, const float* xbar, const float* hi_halo, float sigma,
+                     float lam, void* stream) {
+  return tv_dual_impl(b, z1, xbar, hi_halo, sigma, lam, nullptr, stream);
+}
+int xct_tv_dual_step_stat(const xct_tv_block* b, float* z1, const float* xbar, const float* hi_halo, float sigma,
+                          float lam, double* sq_dz1, void* stream) {
+  if (!sq_dz1) return fail(XCT_ERR_INVALID, "null statistics pointer");
+  return tv_dual_impl(b, z1, xbar, hi_halo, sigma, lam, sq_dz1, stream);
 }
 
 int xct_l2_dual_step(int64_t n, float* z0, const float* ax, const float* y, float sigma, void* stream) {
   if (!z0 || !ax || !y || n < 1) return fail(XCT_ERR_INVALID, "null argument or empty array");
   if (!(sigma > 0.f)) return fail(XCT_ERR_INVALID, "sigma must be positive");
-  xct::l2_dual_kernel<<<tv_grid((size_t)n), 256, 0, (cudaStream_t)stream>>>((size_t)n, z0, ax, y, sigma);
+  xct::l2_dual_kernel<false><<<tv_grid((size_t)n), 256, 0, (cudaStream_t)stream>>>((size_t)n, z0, ax, y, sigma, nullptr, 0.f,
+                                                                                   xct::SinoRows{1, 1, 0, 1}, nullptr);
   return launch_ok("l2_dual_kernel");
+}
+int xct_l2_dual_step_stat(int64_t n, float* z0, const float* ax, const float* y, float sigma, float* ax_x, float alpha,
+                          int64_t inner, int32_t rows, int32_t row_lo, int32_t row_hi, double* stat2, void* stream) {
+  if (!z0 || !ax || !y || !ax_x || !stat2 || n < 1) return fail(XCT_ERR_INVALID, "null argument or empty array");
+  if (!(sigma > 0.f)) return fail(XCT_ERR_INVALID, "sigma must be positive");
+  if (!(alpha > -1.f)) return fail(XCT_ERR_INVALID, "alpha must be above -1");
+  if (inner < 1 || rows < 1 || n % (inner * rows) != 0) return fail(XCT_ERR_INVALID, "n is not a multiple of rows * inner");
+  xct::l2_dual_kernel<true><<<tv_grid((size_t)n), 256, 0, (cudaStream_t)stream>>>(
+      (size_t)n, z0, ax, y, sigma, ax_x, alpha, xct::SinoRows{(long long)inner, rows, row_lo, row_hi}, stat2);
+  return launch_ok("l2_dual_kernel");
+}
+
+int xct_tv_norm(const xct_tv_block* b, const float* x, const float* hi_halo, double* sum, void* stream) {
+  int rc = tv_check(b, x, sum);
+  if (rc) return rc;
+  const size_t n = (size_t)b->n0 * b->n1 * b->n2;
+  xct::tv_norm_kernel<<<tv_grid(n), 256, 0, (cudaStream_t)stream>>>(tv_dims(b), x, hi_halo, sum);
+  return launch_ok("tv_norm_kernel");
 }
 
 int xct_fd_forward(const xct_tv_block* b, const float* x, const float* hi_halo, float* out, void* stream) {

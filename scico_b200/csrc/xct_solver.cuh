@@ -20,20 +20,6 @@ namespace xct {
 
 enum SplitMode { kSplitAdmm = 0, kSplitLadmm = 1, kSplitPadmm = 2 };
 
-__device__ __forceinline__ void block_reduce_add(double v, double* slot) {
-  __shared__ double sh[32];
-  for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) sh[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-    v = l < nw ? sh[l] : 0.0;
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (l == 0) atomicAdd(slot, v);
-  }
-}
-
 struct Vox {
   int i, j, k;
 };

@@ -287,7 +287,9 @@ class TVPDHG(_TVSolver):
             :meth:`estimate_parameters`).  alpha: relaxation (reference default 1.0).
         nonneg: use ``f = NonNegativeIndicator`` instead of ``ZeroFunctional``.
         x0: initial volume (default zeros).  maxiter: iterations run by :meth:`solve`.
-        itstat: record objective / residual norms every iteration (host sync, extra forward).
+        itstat: record objective / residual norms every iteration like the reference's ``itstat_options`` (accumulated
+            by the iteration's own kernels; ``A x`` follows from ``A xbar`` by linearity, so no extra projection; one
+            host read per iteration).
     """
 
     _graphable = True
@@ -304,32 +306,63 @@ class TVPDHG(_TVSolver):
         self.z1 = self._grad()
         self.atz = self._vol()
         self.ax = self._sino()
-        self.x_old = None
+        if self.itstat:
+            # A x of the current iterate, kept up to date by xct_l2_dual_step_stat from A xbar (no second forward
+            # projection per iteration); five device doubles: ||dx||^2, ||dz1||^2, ||dz0||^2, ||Ax - y||^2, ||Dx||_{2,1}
+            self.ax_x = self._sino(zero=True) if x0 is None else self.A.project(self.x).clone()
+            self._stat = torch.zeros(5, dtype=torch.float64, device=self.dev)
+
+    def _sino_rows(self):
+        """(inner, rows, lo, hi) of :c:func:`xct_l2_dual_step_stat`: the detector rows of the local sinogram block
+        that count in global sums (z-slabs: the rows this rank owns; otherwise everything)."""
+        if self.sharded and hasattr(self.A, "owned_rows") and len(self.out_shape) == 3:
+            lo, hi = self.A.owned_rows
+            return self.out_shape[2], self.out_shape[1], lo - self.A.rows[0], hi - self.A.rows[0]
+        return self.y.numel(), 1, 0, 1
 
     def step(self):
-        """One PDHG iteration (``_primaldual.py:219-231``)."""
+        """One PDHG iteration (``_primaldual.py:219-231``).  With ``itstat`` the same kernels also accumulate the
+        reference's iteration statistics (``_primaldual.py:175-217``) on the device: no copies of the old iterates,
+        no extra projection, one host read of five doubles per iteration."""
         L = _lib.lib()
-        if self.itstat:
-            self.x_old = self.x.clone()
-            z0_old, z1_old = self.z0.clone(), self.z1.clone()
+        blk = ctypes.byref(self.blk)
         with torch.cuda.device(self.dev):
             st = _stream(self.dev)
+            if self.itstat:
+                self._stat.zero_()
+                sp = lambda i: self._stat.data_ptr() + 8 * i  # noqa: E731
             self.atz = self._adj(self.z0, self.atz)                       # A^T z0
             lo = self._lo_plane(self.z1)                                  # z1[0][-1] of the previous slab
-            _lib.check(L.xct_tv_primal_step(ctypes.byref(self.blk), self.x.data_ptr(), self.xbar.data_ptr(),
-                                            self.atz.data_ptr(), self.z1.data_ptr(), self._ptr(lo),
-                                            self.tau, self.alpha, int(self.nonneg), st))
+            if self.itstat:
+                _lib.check(L.xct_tv_primal_step_stat(blk, self.x.data_ptr(), self.xbar.data_ptr(), self.atz.data_ptr(),
+                                                     self.z1.data_ptr(), self._ptr(lo), self.tau, self.alpha,
+                                                     int(self.nonneg), sp(0), st))
+            else:
+                _lib.check(L.xct_tv_primal_step(blk, self.x.data_ptr(), self.xbar.data_ptr(), self.atz.data_ptr(),
+                                                self.z1.data_ptr(), self._ptr(lo), self.tau, self.alpha,
+                                                int(self.nonneg), st))
             self.ax = self._fwd(self.xbar, self.ax)                       # A xbar
             hi = self._hi_plane(self.xbar.reshape(self.vol_shape))        # xbar[n0] of the next slab
-            _lib.check(L.xct_tv_dual_step(ctypes.byref(self.blk), self.z1.data_ptr(), self.xbar.data_ptr(),
-                                          self._ptr(hi), self.sigma, self.lam, st))
-            _lib.check(L.xct_l2_dual_step(self.z0.numel(), self.z0.data_ptr(), self.ax.data_ptr(),
-                                          self.y.data_ptr(), self.sigma, st))
+            if self.itstat:
+                _lib.check(L.xct_tv_dual_step_stat(blk, self.z1.data_ptr(), self.xbar.data_ptr(), self._ptr(hi),
+                                                   self.sigma, self.lam, sp(1), st))
+                _lib.check(L.xct_l2_dual_step_stat(self.z0.numel(), self.z0.data_ptr(), self.ax.data_ptr(),
+                                                   self.y.data_ptr(), self.sigma, self.ax_x.data_ptr(), self.alpha,
+                                                   *self._sino_rows(), sp(2), st))
+                xv = self.x.reshape(self.vol_shape)
+                _lib.check(L.xct_tv_norm(blk, self.x.data_ptr(), self._ptr(self._hi_plane(xv)), sp(4), st))
+            else:
+                _lib.check(L.xct_tv_dual_step(blk, self.z1.data_ptr(), self.xbar.data_ptr(), self._ptr(hi),
+                                              self.sigma, self.lam, st))
+                _lib.check(L.xct_l2_dual_step(self.z0.numel(), self.z0.data_ptr(), self.ax.data_ptr(),
+                                              self.y.data_ptr(), self.sigma, st))
         self.itnum += 1
         if self.itstat:
-            pr = self._norm(self.x - self.x_old) / self.tau
-            du = math.sqrt(self._norm(self.z0 - z0_old) ** 2 + self._norm(self.z1 - z1_old) ** 2) / self.sigma
-            self.history.append({"iter": self.itnum, "objective": self.objective(), "prml_rsdl": pr, "dual_rsdl": du})
+            if self.world > 1:
+                dist.all_reduce(self._stat, group=self.group)
+            dx, dz1, dz0, res, tv = (float(v) for v in self._stat.cpu())
+            self.history.append({"iter": self.itnum, "objective": 0.5 * res + self.lam * tv,
+                                 "prml_rsdl": math.sqrt(dx) / self.tau, "dual_rsdl": math.sqrt(dz0 + dz1) / self.sigma})
 
     @staticmethod
     def estimate_parameters(A, ratio: float = 1.0, factor: Optional[float] = 1.01, maxiter: int = 100, seed: int = 0):

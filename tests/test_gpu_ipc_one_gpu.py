@@ -96,16 +96,44 @@ def _worker(rank, world, port, case, exchange, rendezvous="flags"):
             full = sb.XRayTransform3D(N, M, D)
             noise = rng.standard_normal((V,) + D).astype(np.float32)
             y = full(torch.as_tensor(x_gt, device=dev)) + 0.05 * torch.as_tensor(noise, device=dev)
-            ref = TVPDHG(full, y, 0.1, 0.05, 0.05, maxiter=20)
+            ref = TVPDHG(full, y, 0.1, 0.05, 0.05, maxiter=20, itstat=True)
             ref.solve()
             op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange=exchange, rendezvous=rendezvous, peer_timeout_s=5.0)
             (z0, z1), (v0, v1) = op.slab, op.views
-            S = TVPDHG(op, y[v0:v1].contiguous(), 0.1, 0.05, 0.05, maxiter=20)
+            S = TVPDHG(op, y[v0:v1].contiguous(), 0.1, 0.05, 0.05, maxiter=20, itstat=True)
             S.solve()
+            for a, b in zip(S.history, ref.history):  # fused statistics, summed over the partition
+                for key in ("objective", "prml_rsdl", "dual_rsdl"):
+                    assert abs(a[key] - b[key]) <= 2e-5 * abs(b[key]) + 1e-12, (key, a, b)
             rel = (torch.linalg.vector_norm(S.x - ref.x[z0:z1]) / torch.linalg.vector_norm(ref.x[z0:z1])).item()
             assert rel <= 1e-5, (exchange, rel)
             assert abs(S.objective() - ref.objective()) <= 1e-5 * ref.objective(), exchange
             op.close()
+        elif case == "pdhg_slab_stats":
+            # TV-PDHG with iteration statistics over z-slabs whose detector rows overlap (|M00| = 0.7: a row collects
+            # slices of two or three slabs): the statistics the iteration's kernels accumulate on every rank's OWNED
+            # rows add up to those of the unsharded solver, which in turn equal the explicitly evaluated ones
+            from scico_b200.optimize import TVPDHG
+
+            N, D, V = (12, 24, 20), (8, 32), 10  # 12 slices x 0.7 = 8.4 rows: every detector row is held by a slab
+            M = sb.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, V, endpoint=False)[:, None],
+                                              voxel_spacing=(0.7, 1.0, 1.0))
+            x_gt = np.zeros(N, np.float32)
+            x_gt[3:10, 6:16, 5:14] = 1.0
+            full = sb.XRayTransform3D(N, M, D)
+            noise = rng.standard_normal((V,) + D).astype(np.float32)
+            y = full(torch.as_tensor(x_gt, device=dev)) + 0.05 * torch.as_tensor(noise, device=dev)
+            ref = TVPDHG(full, y, 0.1, 0.05, 0.05, maxiter=15, itstat=True)
+            ref.solve()
+            op = sharded.SlabShardedXRayTransform3D(N, M, D)
+            (z0, z1), (r0, r1) = op.slab, op.rows
+            S = TVPDHG(op, y[:, r0:r1].contiguous(), 0.1, 0.05, 0.05, maxiter=15, itstat=True)
+            S.solve()
+            assert len(S.history) == 15
+            for a, b in zip(S.history, ref.history):
+                for key in ("objective", "prml_rsdl", "dual_rsdl"):
+                    assert abs(a[key] - b[key]) <= 2e-5 * abs(b[key]) + 1e-12, (key, a, b)
+            assert abs(S.history[-1]["objective"] - S.objective()) <= 1e-5 * S.objective()
         else:
             raise AssertionError(case)
         torch.cuda.synchronize()
@@ -123,6 +151,7 @@ CASES = [
     ("view3d_tilt", 2, "peer", "flags"), ("view3d_tilt", 3, "peer", "collective"), ("view3d_tilt", 3, "peer_add", "flags"),
     ("view3d_sep", 2, "peer", "flags"), ("view3d_sep", 3, "peer_add", "flags"),
     ("pdhg_view3d", 2, "peer", "flags"),
+    ("pdhg_slab_stats", 2, "nccl", "flags"), ("pdhg_slab_stats", 3, "nccl", "flags"),
 ]
 
 

@@ -147,6 +147,41 @@ def test_pdhg_itstats_and_parameter_estimate(cuda_device):
     assert O.rel_l2(S.x.cpu().numpy(), x_gt) < 0.15
 
 
+@pytest.mark.parametrize("alpha,nonneg,with_x0", [(1.0, False, False), (0.5, True, True), (0.0, False, True)])
+def test_pdhg_fused_iteration_statistics_match_explicit_ones(cuda_device, alpha, nonneg, with_x0):
+    """The statistics the iteration's own kernels accumulate (xct_*_step_stat, xct_tv_norm; A x by the recurrence
+    A x_new = (A xbar + alpha A x_old) / (1 + alpha)) equal the reference's definitions evaluated explicitly
+    (_primaldual.py:175-217): objective with its own forward projection, residuals from copies of the old iterates;
+    and the iterates are those of the solver without statistics, bit for bit."""
+    import torch
+
+    N, D, V = (8, 24, 20), (8, 32), 10
+    M = sb.matrices_from_euler_angles(N, D, "X", np.linspace(0, np.pi, V, endpoint=False)[:, None])
+    A = sb.XRayTransform3D(N, M, D)
+    rng = np.random.default_rng(5)
+    x_gt = np.zeros(N, np.float32)
+    x_gt[2:6, 6:16, 5:14] = 1.0
+    y = _t(torch, C.project_3d(x_gt, A.matrices, D) + 0.05 * rng.standard_normal((V,) + D).astype(np.float32), cuda_device)
+    x0 = _t(torch, rng.random(N).astype(np.float32), cuda_device) if with_x0 else None
+    lam, tau, sigma = 0.1, 0.05, 0.05
+    S = TVPDHG(A, y, lam, tau, sigma, alpha=alpha, nonneg=nonneg, x0=x0, maxiter=30, itstat=True)
+    P = TVPDHG(A, y, lam, tau, sigma, alpha=alpha, nonneg=nonneg, x0=x0, maxiter=30)
+    for it in range(30):
+        xo, z0o, z1o = S.x.clone(), S.z0.clone(), S.z1.clone()
+        S.step()
+        P.step()
+        h = S.history[-1]
+        assert h["iter"] == it + 1
+        obj = S.objective()
+        assert abs(h["objective"] - obj) <= 2e-6 * abs(obj)
+        pr = float((S.x - xo).double().norm()) / tau
+        du = float(torch.sqrt((S.z0 - z0o).double().norm() ** 2 + (S.z1 - z1o).double().norm() ** 2)) / sigma
+        assert abs(h["prml_rsdl"] - pr) <= 1e-9 * max(pr, 1e-30) + 1e-12
+        assert abs(h["dual_rsdl"] - du) <= 1e-9 * max(du, 1e-30) + 1e-12
+    assert torch.equal(S.x, P.x) and torch.equal(S.z0, P.z0) and torch.equal(S.z1, P.z1)
+    assert O.rel_l2(S.ax_x.cpu().numpy(), A.project(S.x).cpu().numpy()) <= 1e-6
+
+
 @pytest.mark.gpu
 def test_solve_replays_a_cuda_graph_and_matches_plain_stepping(cuda_device):
     """solve() captures one iteration in a CUDA graph when nothing in it needs the host (PDHG and the
