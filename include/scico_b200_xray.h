@@ -324,6 +324,20 @@ XCT_API int xct_grad_prox_step(const xct_tv_block *blk, const float *x, const fl
  * z0, u0, w0 updated as above with Cx = ax.  mode: XCT_SPLIT_LADMM or XCT_SPLIT_PADMM. */
 XCT_API int xct_sino_prox_step(int64_t n, const float *ax, const float *y, float *z0, float *u0, float *w0, float c,
                                float inv_nu, int32_t mode, void *stream);
+/* The two prox steps with the iteration statistics of ProximalADMM / LinearizedADMM (scico/optimize/_padmm.py:148-177,
+ * 294-345 with the default fast_dual_residual; _ladmm.py:160-200) accumulated in the same pass into three DEVICE
+ * doubles each (added to: the caller zeroes them):
+ *   stat3[0] += ||Cx - z_new||^2        (primal residual ||A x + B z||, B = -I)
+ *   stat3[1] += ||z_new - z_old||^2     (fast dual residual)
+ *   stat3[2] += g(z_new)'s sum: ||z1_new||_{2,1} (gradient block), ||z0_new - y||^2 (sinogram block)
+ * Sinogram sums run over detector rows [row_lo, row_hi) of the (n / (rows inner), rows, inner) block, see
+ * xct_l2_dual_step_stat. */
+XCT_API int xct_grad_prox_step_stat(const xct_tv_block *blk, const float *x, const float *hi_halo, float *z1, float *u1,
+                                    float *w1, float dscale, float thr, float inv_nu, int32_t mode, double *stat3,
+                                    void *stream);
+XCT_API int xct_sino_prox_step_stat(int64_t n, const float *ax, const float *y, float *z0, float *u0, float *w0, float c,
+                                    float inv_nu, int32_t mode, int64_t inner, int32_t rows, int32_t row_lo,
+                                    int32_t row_hi, double *stat3, void *stream);
 /* x <- prox_f(x - step (atq + dscale D^T w1)), f = 0 or the non-negativity indicator.
  * lo_halo: plane w1[0][-1] of the previous slab (NULL when is_first). */
 XCT_API int xct_grad_primal_step(const xct_tv_block *blk, float *x, const float *atq, const float *w1,

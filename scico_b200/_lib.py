@@ -82,6 +82,8 @@ EXPORTED_SYMBOLS = (
     "xct_tv_dual_step_stat",
     "xct_l2_dual_step_stat",
     "xct_tv_norm",
+    "xct_grad_prox_step_stat",
+    "xct_sino_prox_step_stat",
     "xct_fd_forward",
     "xct_fd_adjoint",
     "xct_grad_prox_step",
@@ -242,6 +244,10 @@ def lib() -> ctypes.CDLL:
     L.xct_l2_dual_step_stat.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, cf, c_void_p, cf, c_int64, c_int32, c_int32,
                                         c_int32, c_void_p, c_void_p]
     L.xct_tv_norm.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p]
+    L.xct_grad_prox_step_stat.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, cf, cf, cf, c_int32,
+                                          c_void_p, c_void_p]
+    L.xct_sino_prox_step_stat.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, cf, cf, c_int32, c_int64,
+                                          c_int32, c_int32, c_int32, c_void_p, c_void_p]
     L.xct_fd_forward.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p]
     L.xct_fd_adjoint.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p]
     L.xct_grad_prox_step.argtypes = [POINTER(TvBlock), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, cf, cf, cf, c_int32, c_void_p]

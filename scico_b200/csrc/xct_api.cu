@@ -1971,42 +1971,70 @@ int xct_fd_adjoint(const xct_tv_block* b, const float* z1, const float* lo_halo,
 }
 
 // ------------------------------------------------- ADMM / LADMM / PADMM kernels (xct_solver.cuh)
-int xct_grad_prox_step(const xct_tv_block* b, const float* x, const float* hi_halo, float* z1, float* u1, float* w1,
-                       float dscale, float thr, float inv_nu, int32_t mode, void* stream) {
+}  // extern "C"
+template <bool STAT>
+static int grad_prox_impl(const xct_tv_block* b, const float* x, const float* hi_halo, float* z1, float* u1, float* w1,
+                          float dscale, float thr, float inv_nu, int32_t mode, double* stat, void* stream) {
   int rc = tv_check(b, x, z1);
   if (rc) return rc;
   if (!u1 || (mode != XCT_SPLIT_ADMM && !w1)) return fail(XCT_ERR_INVALID, "null argument");
+  if (STAT && !stat) return fail(XCT_ERR_INVALID, "null statistics pointer");
   if (!(thr >= 0.f)) return fail(XCT_ERR_INVALID, "threshold must be non-negative");
   const size_t n = (size_t)b->n0 * b->n1 * b->n2;
   cudaStream_t st = (cudaStream_t)stream;
   switch (mode) {
     case XCT_SPLIT_ADMM:
-      xct::grad_prox_kernel<xct::kSplitAdmm><<<tv_grid(n), 256, 0, st>>>(tv_dims(b), x, hi_halo, z1, u1, w1, dscale, thr, inv_nu);
+      xct::grad_prox_kernel<xct::kSplitAdmm, STAT><<<tv_grid(n), 256, 0, st>>>(tv_dims(b), x, hi_halo, z1, u1, w1, dscale, thr, inv_nu, stat);
       break;
     case XCT_SPLIT_LADMM:
-      xct::grad_prox_kernel<xct::kSplitLadmm><<<tv_grid(n), 256, 0, st>>>(tv_dims(b), x, hi_halo, z1, u1, w1, dscale, thr, inv_nu);
+      xct::grad_prox_kernel<xct::kSplitLadmm, STAT><<<tv_grid(n), 256, 0, st>>>(tv_dims(b), x, hi_halo, z1, u1, w1, dscale, thr, inv_nu, stat);
       break;
     case XCT_SPLIT_PADMM:
-      xct::grad_prox_kernel<xct::kSplitPadmm><<<tv_grid(n), 256, 0, st>>>(tv_dims(b), x, hi_halo, z1, u1, w1, dscale, thr, inv_nu);
+      xct::grad_prox_kernel<xct::kSplitPadmm, STAT><<<tv_grid(n), 256, 0, st>>>(tv_dims(b), x, hi_halo, z1, u1, w1, dscale, thr, inv_nu, stat);
       break;
     default:
       return fail(XCT_ERR_INVALID, "unknown split mode");
   }
   return launch_ok("grad_prox_kernel");
 }
+extern "C" {
+int xct_grad_prox_step(const xct_tv_block* b, const float* x, const float* hi_halo, float* z1, float* u1, float* w1,
+                       float dscale, float thr, float inv_nu, int32_t mode, void* stream) {
+  return grad_prox_impl<false>(b, x, hi_halo, z1, u1, w1, dscale, thr, inv_nu, mode, nullptr, stream);
+}
+int xct_grad_prox_step_stat(const xct_tv_block* b, const float* x, const float* hi_halo, float* z1, float* u1, float* w1,
+                            float dscale, float thr, float inv_nu, int32_t mode, double* stat3, void* stream) {
+  return grad_prox_impl<true>(b, x, hi_halo, z1, u1, w1, dscale, thr, inv_nu, mode, stat3, stream);
+}
 
-int xct_sino_prox_step(int64_t n, const float* ax, const float* y, float* z0, float* u0, float* w0, float c,
-                       float inv_nu, int32_t mode, void* stream) {
+}  // extern "C"
+template <bool STAT>
+static int sino_prox_impl(int64_t n, const float* ax, const float* y, float* z0, float* u0, float* w0, float c,
+                          float inv_nu, int32_t mode, xct::SinoRows rows, double* stat, void* stream) {
   if (!ax || !y || !z0 || !u0 || !w0 || n < 1) return fail(XCT_ERR_INVALID, "null argument or empty array");
+  if (STAT && !stat) return fail(XCT_ERR_INVALID, "null statistics pointer");
+  if (rows.inner < 1 || rows.rows < 1 || n % (rows.inner * rows.rows) != 0)
+    return fail(XCT_ERR_INVALID, "n is not a multiple of rows * inner");
   if (!(c > 0.f)) return fail(XCT_ERR_INVALID, "prox parameter must be positive");
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == XCT_SPLIT_LADMM)
-    xct::sino_prox_kernel<xct::kSplitLadmm><<<tv_grid((size_t)n), 256, 0, st>>>((size_t)n, ax, y, z0, u0, w0, c, inv_nu);
+    xct::sino_prox_kernel<xct::kSplitLadmm, STAT><<<tv_grid((size_t)n), 256, 0, st>>>((size_t)n, ax, y, z0, u0, w0, c, inv_nu, rows, stat);
   else if (mode == XCT_SPLIT_PADMM)
-    xct::sino_prox_kernel<xct::kSplitPadmm><<<tv_grid((size_t)n), 256, 0, st>>>((size_t)n, ax, y, z0, u0, w0, c, inv_nu);
+    xct::sino_prox_kernel<xct::kSplitPadmm, STAT><<<tv_grid((size_t)n), 256, 0, st>>>((size_t)n, ax, y, z0, u0, w0, c, inv_nu, rows, stat);
   else
     return fail(XCT_ERR_INVALID, "unknown split mode");
   return launch_ok("sino_prox_kernel");
+}
+extern "C" {
+int xct_sino_prox_step(int64_t n, const float* ax, const float* y, float* z0, float* u0, float* w0, float c,
+                       float inv_nu, int32_t mode, void* stream) {
+  return sino_prox_impl<false>(n, ax, y, z0, u0, w0, c, inv_nu, mode, xct::SinoRows{1, 1, 0, 1}, nullptr, stream);
+}
+int xct_sino_prox_step_stat(int64_t n, const float* ax, const float* y, float* z0, float* u0, float* w0, float c,
+                            float inv_nu, int32_t mode, int64_t inner, int32_t rows, int32_t row_lo, int32_t row_hi,
+                            double* stat3, void* stream) {
+  return sino_prox_impl<true>(n, ax, y, z0, u0, w0, c, inv_nu, mode, xct::SinoRows{(long long)inner, rows, row_lo, row_hi},
+                              stat3, stream);
 }
 
 int xct_grad_primal_step(const xct_tv_block* b, float* x, const float* atq, const float* w1, const float* lo_halo,

@@ -57,11 +57,16 @@ __device__ __forceinline__ float l21_scale(float v0, float v1, float v2, float t
 //   PADMM:        z = prox_{thr ||.||_{2,1}}(z + inv_nu ((Cx - z) + u)); u = (u + Cx) - z   (_padmm.py:354-363)
 // and the array the NEXT x-step applies D^T to:
 //   LADMM: w = (Cx - z) + u (new z, u; _ladmm.py:270)     PADMM: w = 2 u_new - u_old (_padmm.py:351)
-template <int MODE>
+// STAT (iteration statistics in the same pass, _padmm.py:148-177,294-345, _ladmm.py:160-200):
+//   stat[0] += ||Cx - z_new||^2 (primal residual),  stat[1] += ||z_new - z_old||^2 (fast dual residual),
+//   stat[2] += ||z_new||_{2,1} (the gradient block's share of g(z))
+template <int MODE, bool STAT>
 __global__ void __launch_bounds__(256)
 grad_prox_kernel(TvDims d, const float* __restrict__ x, const float* __restrict__ hi_halo, float* __restrict__ z,
-                 float* __restrict__ u, float* __restrict__ w, float dscale, float thr, float inv_nu) {
+                 float* __restrict__ u, float* __restrict__ w, float dscale, float thr, float inv_nu,
+                 double* __restrict__ stat) {
   const size_t plane = (size_t)d.n1 * d.n2, n = plane * d.n0;
+  double acc_p = 0.0, acc_d = 0.0, acc_g = 0.0;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     const Vox v = unravel(d, idx);
     float c0, c1, c2;
@@ -69,8 +74,11 @@ grad_prox_kernel(TvDims d, const float* __restrict__ x, const float* __restrict_
     c0 *= dscale; c1 *= dscale; c2 *= dscale;  // exact when dscale == 1
     const float u0 = u[idx], u1 = u[idx + n], u2 = u[idx + 2 * n];
     float a0, a1, a2;
+    float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+    if (MODE == kSplitPadmm || STAT) {
+      z0 = z[idx]; z1 = z[idx + n]; z2 = z[idx + 2 * n];
+    }
     if (MODE == kSplitPadmm) {
-      const float z0 = z[idx], z1 = z[idx + n], z2 = z[idx + 2 * n];
       a0 = z0 + inv_nu * ((c0 - z0) + u0);
       a1 = z1 + inv_nu * ((c1 - z1) + u1);
       a2 = z2 + inv_nu * ((c2 - z2) + u2);
@@ -87,6 +95,20 @@ grad_prox_kernel(TvDims d, const float* __restrict__ x, const float* __restrict_
     } else if (MODE == kSplitPadmm) {
       w[idx] = 2.f * un0 - u0; w[idx + n] = 2.f * un1 - u1; w[idx + 2 * n] = 2.f * un2 - u2;
     }
+    if (STAT) {
+      const double p0 = (double)(c0 - zn0), p1 = (double)(c1 - zn1), p2 = (double)(c2 - zn2);
+      const double e0 = (double)(zn0 - z0), e1 = (double)(zn1 - z1), e2 = (double)(zn2 - z2);
+      acc_p += (p0 * p0 + p1 * p1) + p2 * p2;
+      acc_d += (e0 * e0 + e1 * e1) + e2 * e2;
+      acc_g += sqrt(((double)zn0 * zn0 + (double)zn1 * zn1) + (double)zn2 * zn2);
+    }
+  }
+  if (STAT) {
+    block_reduce_add(acc_p, stat);
+    __syncthreads();
+    block_reduce_add(acc_d, stat + 1);
+    __syncthreads();
+    block_reduce_add(acc_g, stat + 2);
   }
 }
 
@@ -94,25 +116,42 @@ grad_prox_kernel(TvDims d, const float* __restrict__ x, const float* __restrict_
 //   prox_{c g0}(v) = (c y + v) / (c + 1).
 //   LADMM: z = prox(ax + u), c = nu;  PADMM: z = prox(z + inv_nu ((ax - z) + u)), c = 1/(rho nu).
 //   u, w as in grad_prox_kernel.
-template <int MODE>
+//   STAT: stat[0] += ||ax - z_new||^2,  stat[1] += ||z_new - z_old||^2,  stat[2] += ||z_new - y||^2 (= 2 g0(z))
+//   over the detector rows `rows` counts.
+template <int MODE, bool STAT>
 __global__ void __launch_bounds__(256)
 sino_prox_kernel(size_t n, const float* __restrict__ ax, const float* __restrict__ y, float* __restrict__ z,
-                 float* __restrict__ u, float* __restrict__ w, float c, float inv_nu) {
+                 float* __restrict__ u, float* __restrict__ w, float c, float inv_nu, SinoRows rows,
+                 double* __restrict__ stat) {
   const float rc1 = 1.0f / (c + 1.0f);
+  double acc_p = 0.0, acc_d = 0.0, acc_g = 0.0;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
-    const float a = ax[idx], uo = u[idx];
-    float v;
+    const float a = ax[idx], uo = u[idx], yy = y[idx];
+    float v, zo = 0.f;
+    if (MODE == kSplitPadmm || STAT) zo = z[idx];
     if (MODE == kSplitPadmm) {
-      const float zo = z[idx];
       v = zo + inv_nu * ((a - zo) + uo);
     } else {
       v = a + uo;
     }
-    const float zn = (c * y[idx] + v) * rc1;
+    const float zn = (c * yy + v) * rc1;
     const float un = (uo + a) - zn;
     z[idx] = zn;
     u[idx] = un;
     w[idx] = (MODE == kSplitPadmm) ? 2.f * un - uo : (a - zn) + un;
+    if (STAT && rows.counted(idx)) {
+      const double pr = (double)(a - zn), dz = (double)(zn - zo), r = (double)(zn - yy);
+      acc_p += pr * pr;
+      acc_d += dz * dz;
+      acc_g += r * r;
+    }
+  }
+  if (STAT) {
+    block_reduce_add(acc_p, stat);
+    __syncthreads();
+    block_reduce_add(acc_d, stat + 1);
+    __syncthreads();
+    block_reduce_add(acc_g, stat + 2);
   }
 }
 

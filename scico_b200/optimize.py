@@ -176,6 +176,14 @@ class _TVSolver:
         res = self.A.back_project(y, out=out)
         return res if res is not None else out
 
+    def _sino_rows(self):
+        """(inner, rows, lo, hi) of :c:func:`xct_l2_dual_step_stat`: the detector rows of the local sinogram block
+        that count in global sums (z-slabs: the rows this rank owns; otherwise everything)."""
+        if self.sharded and hasattr(self.A, "owned_rows") and len(self.out_shape) == 3:
+            lo, hi = self.A.owned_rows
+            return self.out_shape[2], self.out_shape[1], lo - self.A.rows[0], hi - self.A.rows[0]
+        return self.y.numel(), 1, 0, 1
+
     #: an iteration never needs the host (no scalar read back): it can be captured in a CUDA graph
     _graphable = False
 
@@ -311,14 +319,6 @@ class TVPDHG(_TVSolver):
             # projection per iteration); five device doubles: ||dx||^2, ||dz1||^2, ||dz0||^2, ||Ax - y||^2, ||Dx||_{2,1}
             self.ax_x = self._sino(zero=True) if x0 is None else self.A.project(self.x).clone()
             self._stat = torch.zeros(5, dtype=torch.float64, device=self.dev)
-
-    def _sino_rows(self):
-        """(inner, rows, lo, hi) of :c:func:`xct_l2_dual_step_stat`: the detector rows of the local sinogram block
-        that count in global sums (z-slabs: the rows this rank owns; otherwise everything)."""
-        if self.sharded and hasattr(self.A, "owned_rows") and len(self.out_shape) == 3:
-            lo, hi = self.A.owned_rows
-            return self.out_shape[2], self.out_shape[1], lo - self.A.rows[0], hi - self.A.rows[0]
-        return self.y.numel(), 1, 0, 1
 
     def step(self):
         """One PDHG iteration (``_primaldual.py:219-231``).  With ``itstat`` the same kernels also accumulate the
@@ -512,9 +512,14 @@ class _TVSplitSolver(_TVSolver):
         self.z1, self.u1, self.w1 = (self._grad() for _ in range(3))
         self.atq, self.ax = self._vol(), self._sino()
 
+    #: dual residual as ``||z - z_old||`` (the reference's ``fast_dual_residual``, ProximalADMM's default) instead of
+    #: ``||C^T (z - z_old)||``, which costs copies of the old ``z`` and one more back projection per iteration
+    fast_dual_residual = False
+
     def _iterate(self, mode, step, dscale, thr, c, inv_nu):
         L, blk = _lib.lib(), ctypes.byref(self.blk)
-        if self.itstat:
+        slow_dual = self.itstat and not self.fast_dual_residual
+        if slow_dual:
             z_old = (self.z0.clone(), self.z1.clone())
         with torch.cuda.device(self.dev):
             st = _stream(self.dev)
@@ -524,24 +529,36 @@ class _TVSplitSolver(_TVSolver):
                                               self._ptr(lo), step, dscale, int(self.nonneg), st))
             self.ax = self._fwd(self.x, self.ax)
             hi = self._hi_plane(self.x.reshape(self.vol_shape))
-            _lib.check(L.xct_grad_prox_step(blk, self.x.data_ptr(), self._ptr(hi), self.z1.data_ptr(), self.u1.data_ptr(),
-                                            self.w1.data_ptr(), dscale, thr, inv_nu, mode, st))
-            _lib.check(L.xct_sino_prox_step(self.z0.numel(), self.ax.data_ptr(), self.y.data_ptr(), self.z0.data_ptr(),
-                                            self.u0.data_ptr(), self.w0.data_ptr(), c, inv_nu, mode, st))
+            if self.itstat:
+                # the statistics' sums come out of the two prox kernels (six device doubles, one host read)
+                if getattr(self, "_stat", None) is None:
+                    self._stat = torch.zeros(6, dtype=torch.float64, device=self.dev)
+                self._stat.zero_()
+                sp = self._stat.data_ptr()
+                _lib.check(L.xct_grad_prox_step_stat(blk, self.x.data_ptr(), self._ptr(hi), self.z1.data_ptr(),
+                                                     self.u1.data_ptr(), self.w1.data_ptr(), dscale, thr, inv_nu, mode, sp, st))
+                _lib.check(L.xct_sino_prox_step_stat(self.z0.numel(), self.ax.data_ptr(), self.y.data_ptr(), self.z0.data_ptr(),
+                                                     self.u0.data_ptr(), self.w0.data_ptr(), c, inv_nu, mode,
+                                                     *self._sino_rows(), sp + 24, st))
+            else:
+                _lib.check(L.xct_grad_prox_step(blk, self.x.data_ptr(), self._ptr(hi), self.z1.data_ptr(), self.u1.data_ptr(),
+                                                self.w1.data_ptr(), dscale, thr, inv_nu, mode, st))
+                _lib.check(L.xct_sino_prox_step(self.z0.numel(), self.ax.data_ptr(), self.y.data_ptr(), self.z0.data_ptr(),
+                                                self.u0.data_ptr(), self.w0.data_ptr(), c, inv_nu, mode, st))
         self.itnum += 1
         if self.itstat:
-            self._stats(z_old, dscale)
-
-    def _stats(self, z_old, dscale):
-        D = self._fd()
-        xv = self.x.reshape(self.vol_shape)
-        pr = math.sqrt(self._norm(self.ax - self.z0) ** 2
-                       + self._norm(dscale * D(xv, self._hi_plane(xv)) - self.z1) ** 2)
-        dz0, dz1 = self.z0 - z_old[0], self.z1 - z_old[1]
-        du = self._norm(self.A.back_project(dz0).reshape(self.vol_shape) + dscale * D.adj(dz1, self._lo_plane(dz1)))
-        r = self._owned(self.z0 - self.y)
-        obj = 0.5 * self._sum(r.double() ** 2) + (self.lam / dscale) * self._l21(self.z1)  # f(x) + g(z)
-        self.history.append({"iter": self.itnum, "objective": obj, "prml_rsdl": pr, "dual_rsdl": du})
+            if self.world > 1:
+                dist.all_reduce(self._stat, group=self.group)
+            pr1, dz1, g1, pr0, dz0, res = (float(v) for v in self._stat.cpu())
+            if slow_dual:
+                e0, e1 = self.z0 - z_old[0], self.z1 - z_old[1]
+                D = self._fd()
+                du = self._norm(self.A.back_project(e0).reshape(self.vol_shape) + dscale * D.adj(e1, self._lo_plane(e1)))
+            else:
+                du = math.sqrt(dz0 + dz1)
+            # f(x) + g(z) (_padmm.py:148-177, _ladmm.py:130-158), ||A x + B z|| with B = -I, dual residual
+            self.history.append({"iter": self.itnum, "objective": 0.5 * res + (self.lam / dscale) * g1,
+                                 "prml_rsdl": math.sqrt(pr0 + pr1), "dual_rsdl": du})
 
     @property
     def z(self):
@@ -587,10 +604,11 @@ class TVProximalADMM(_TVSplitSolver):
     is given (``_padmm.py:106-118``)."""
 
     def __init__(self, A, y, lam: float, rho: float, mu: float, nu: float, alpha: float = 1.0, x0=None,
-                 nonneg: bool = False, maxiter: int = 100, itstat: bool = False):
+                 nonneg: bool = False, maxiter: int = 100, itstat: bool = False, fast_dual_residual: bool = True):
         self._setup(A, y, x0)
         self.lam, self.rho, self.mu, self.nu, self.alpha = float(lam), float(rho), float(mu), float(nu), float(alpha)
         self.nonneg, self.maxiter, self.itstat = bool(nonneg), int(maxiter), bool(itstat)
+        self.fast_dual_residual = bool(fast_dual_residual)  # the reference's default (_padmm.py:70,330-345)
         self._alloc()
 
     def step(self):

@@ -182,9 +182,14 @@ class SlabShardedXRayTransform3D:
         halos = self.halo_rows()
         if not halos or self.world_size == 1:
             return y
+        # NCCL moves device memory directly; gloo (the CPU / one-GPU test rendezvous) cannot send device pointers
+        # (writev: "Bad address"), so the rows are staged through host memory there
+        staged = y.is_cuda and dist.get_backend(self.group) == "gloo"
         ops, bufs = [], []
         for other, lo, hi in halos:
             send = y[:, lo - self.rows[0]:hi - self.rows[0], :].contiguous()
+            if staged:
+                send = send.cpu()
             recv = torch.empty_like(send)
             peer = other if self.group is None else dist.get_global_rank(self.group, other)
             ops += [dist.P2POp(dist.isend, send, peer, self.group), dist.P2POp(dist.irecv, recv, peer, self.group)]
@@ -192,7 +197,7 @@ class SlabShardedXRayTransform3D:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         for lo, hi, recv in bufs:
-            y[:, lo - self.rows[0]:hi - self.rows[0], :] += recv
+            y[:, lo - self.rows[0]:hi - self.rows[0], :] += recv.to(y.device) if staged else recv
         return y
 
     def project(self, x_local, out=None):

@@ -418,6 +418,51 @@ def test_padmm_iterations_match_oracle(cuda_device, dim, alpha):
     assert len(S.history) == iters and all(np.isfinite(h["objective"]) for h in S.history)
 
 
+@pytest.mark.parametrize("solver,dim,fast", [("padmm", 3, True), ("padmm", 3, False), ("padmm", 2, True), ("ladmm", 3, False)])
+def test_split_solver_fused_iteration_statistics_match_explicit_ones(cuda_device, solver, dim, fast):
+    """Objective f(x) + g(z), primal residual ||A x + B z|| and dual residual (fast: ||z - z_old||, the reference's
+    ProximalADMM default; otherwise ||C^T (z - z_old)||) as accumulated by the prox kernels (xct_*_prox_step_stat)
+    against the same quantities evaluated with torch from the iterates (_padmm.py:148-177,294-345, _ladmm.py:130-213);
+    the iterates are those of a run without statistics (up to the last bit: the two instantiations of a kernel need not
+    contract the same products into FMAs)."""
+    import torch
+
+    from scico_b200.optimize import FiniteDifference
+
+    N, A, Ao, ATo, x_gt, y = _problem_2d() if dim == 2 else _problem_3d()
+    yt = _t(torch, y, cuda_device)
+    lam, iters = 0.1, 12
+    if solver == "padmm":
+        alpha = 4.0
+        mu, nu = TVProximalADMM.estimate_parameters(A, alpha=alpha, factor=1.01, maxiter=40)
+        mk = lambda st: TVProximalADMM(A, yt, lam, 0.05, mu, nu, alpha=alpha, maxiter=iters, itstat=st,  # noqa: E731
+                                       fast_dual_residual=fast)
+    else:
+        alpha = 1.0
+        mu, nu = TVLinearizedADMM.estimate_parameters(A, nu=1.0, maxiter=40)
+        mk = lambda st: TVLinearizedADMM(A, yt, lam, mu, nu, maxiter=iters, itstat=st)  # noqa: E731
+    S, P = mk(True), mk(False)
+    D = FiniteDifference(S.vol_shape)
+    dn = lambda t: float(t.double().norm())  # noqa: E731
+    for _ in range(iters):
+        z0o, z1o = S.z0.clone(), S.z1.clone()
+        S.step()
+        P.step()
+        h = S.history[-1]
+        xv = S.x.reshape(S.vol_shape)
+        pr = np.hypot(dn(A.project(S.x) - S.z0), dn(alpha * D(xv) - S.z1))
+        obj = 0.5 * dn(S.z0 - yt) ** 2 + (lam / alpha) * float(torch.sqrt((S.z1.double() ** 2).sum(0)).sum())
+        if fast:
+            du = np.hypot(dn(S.z0 - z0o), dn(S.z1 - z1o))
+        else:
+            du = dn(A.back_project(S.z0 - z0o).reshape(S.vol_shape) + alpha * D.adj(S.z1 - z1o))
+        assert abs(h["objective"] - obj) <= 1e-6 * abs(obj) + 1e-12
+        assert abs(h["prml_rsdl"] - pr) <= 1e-5 * pr + 1e-9
+        assert abs(h["dual_rsdl"] - du) <= 1e-5 * du + 1e-9
+    for a, b in ((S.x, P.x), (S.z0, P.z0), (S.z1, P.z1), (S.u0, P.u0)):
+        assert O.rel_l2(a.cpu().numpy(), b.cpu().numpy()) <= 1e-6
+
+
 def test_padmm_estimate_matches_oracle_power_iteration(cuda_device):
     N, A, Ao, ATo, x_gt, y = _problem_3d()
     alpha = 7.0
