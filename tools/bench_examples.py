@@ -1,0 +1,139 @@
+"""The reference's published example runs, re-timed on this framework with the same shapes.
+
+  * examples/scripts/ct_3d_tv_padmm.py (notebook cell 7, RTX 2080 Ti): 64 x 256 x 128 tangle phantom, 10 views,
+    ProximalADMM, 1000 iterations with iteration statistics: 26.6 s (first iteration 1.65 s).
+  * examples/scripts/ct_projector_comparison_3d.py (notebook cell 15): 129 x 130 x 131 block phantom, 3 views tilted 74
+    degrees ("XY"), 128 x 129 detector: average forward 1.88e-3 s, average back projection 1.11e-3 s (first calls
+    0.499 / 0.565 s with JIT).
+  * examples/scripts/ct_projector_comparison_2d.py (notebook cell 15): 512^2, 500 views, 369 bins: average forward
+    3.59e-2 s (the published back-projection time blocks on the wrong array).
+
+Wall-clock seconds around a device synchronisation, like the reference's Timer + block_until_ready.  Prints one JSON
+object.  Usage: python tools/bench_examples.py > gpurun_out/examples.json"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+
+    import _ct3d_example as E
+    import scico_b200 as sb
+    from scico_b200.optimize import TVProximalADMM
+
+    dev = "cuda:0"
+    sync = lambda: torch.cuda.synchronize()  # noqa: E731
+    out = {}
+
+    # --- ct_3d_tv_padmm
+    t0 = time.perf_counter()
+    N, M, D = E.geometry()
+    A = sb.XRayTransform3D(N, M, D)
+    x_gt = E.tangle_phantom()
+    y = A(torch.as_tensor(x_gt, device=dev))
+    sync()
+    t1 = time.perf_counter()
+    mu, nu = TVProximalADMM.estimate_parameters(A, alpha=E.ALPHA)
+    sync()
+    t2 = time.perf_counter()
+    S = TVProximalADMM(A, y, E.LAM, E.RHO, mu, nu, alpha=E.ALPHA, maxiter=E.MAXITER, itstat=True)
+    S.step()
+    sync()
+    t3 = time.perf_counter()
+    for _ in range(E.MAXITER - 1):
+        S.step()
+    sync()
+    t4 = time.perf_counter()
+    x = S.x.cpu().numpy()
+    S2 = TVProximalADMM(A, y, E.LAM, E.RHO, mu, nu, alpha=E.ALPHA, maxiter=E.MAXITER)
+    S2.step()
+    sync()
+    t5 = time.perf_counter()
+    for _ in range(E.MAXITER - 1):
+        S2.step()
+    sync()
+    t6 = time.perf_counter()
+    out["ct_3d_tv_padmm"] = {
+        "shape": "64 x 256 x 128 volume, 10 views, 64 x 256 detector, ProximalADMM, 1000 iterations",
+        "reference_published_s": 26.6, "reference_first_iteration_s": 1.65, "reference_hw": "RTX 2080 Ti (notebook cell 7)",
+        "solve_s_itstats_on": (t3 - t2) + (t4 - t3), "first_iteration_s": t3 - t2, "iters_per_s_itstats_on": (E.MAXITER - 1) / (t4 - t3),
+        "solve_s_itstats_off": t6 - t4 - 0.0, "iters_per_s_itstats_off": (E.MAXITER - 1) / (t6 - t5),
+        "setup_s_operator_and_sinogram": t1 - t0, "estimate_parameters_s": t2 - t1,
+        "snr_db": float(E.snr_db(x_gt, x)), "reference_snr_db": 14.36, "mae": E.mae(x_gt, x), "reference_mae": 0.048,
+        "final_objective": S.history[-1]["objective"], "reference_final_objective": 3.546e5}
+
+    # --- ct_projector_comparison_3d
+    n = 128
+    in_shape, det = (n + 1, n + 2, n + 3), (n, n + 1)
+    ang = np.stack(np.broadcast_arrays(90.0 - 16.0, np.linspace(0, 180, 3, endpoint=False)), axis=-1)
+    t0 = time.perf_counter()
+    H = sb.XRayTransform3D(in_shape, sb.matrices_from_euler_angles(in_shape, det, "XY", ang, degrees=True), det)
+    t1 = time.perf_counter()
+    xb = torch.zeros(in_shape, device=dev)
+    xb[20:100, 30:90, 25:110] = 1.0
+    sync()
+    t2 = time.perf_counter()
+    yb = H(xb)
+    sync()
+    t3 = time.perf_counter()
+    for _ in range(3):
+        yb = H(xb)
+        sync()
+    t4 = time.perf_counter()
+    xb2 = H.T(yb)
+    sync()
+    t5 = time.perf_counter()
+    xb2 = H.T(yb)  # a second untimed call: the first two launches of a kernel family carry one-off module loads (13 ms)
+    sync()
+    t5b = time.perf_counter()
+    for _ in range(3):
+        xb2 = H.T(yb)
+        sync()
+    t6 = time.perf_counter()
+    out["ct_projector_comparison_3d"] = {
+        "shape": "129 x 130 x 131 volume, 3 views (XY tilt 74 deg), 128 x 129 detector",
+        "reference_published": {"init_s": 1.42e-4, "first_fwd_s": 0.499, "first_back_s": 0.565, "avg_fwd_s": 1.88e-3, "avg_back_s": 1.11e-3},
+        "init_s": t1 - t0, "first_fwd_s": t3 - t2, "avg_fwd_s": (t4 - t3) / 3, "first_back_s": t5 - t4, "second_back_s": t5b - t5, "avg_back_s": (t6 - t5b) / 3}
+
+    # --- ct_projector_comparison_2d
+    n, nv = 512, 500
+    angles = np.linspace(0, np.pi, nv, endpoint=False)
+    det_count = int(n * 1.02 / np.sqrt(2.0))
+    t0 = time.perf_counter()
+    H2 = sb.XRayTransform2D((n, n), angles, det_count=det_count)
+    t1 = time.perf_counter()
+    x2 = torch.rand((n, n), device=dev)
+    sync()
+    t2 = time.perf_counter()
+    y2 = H2(x2)
+    sync()
+    t3 = time.perf_counter()
+    for _ in range(3):
+        y2 = H2(x2)
+        sync()
+    t4 = time.perf_counter()
+    b2 = H2.T(y2)
+    sync()
+    t5 = time.perf_counter()
+    for _ in range(3):
+        b2 = H2.T(y2)
+        sync()
+    t6 = time.perf_counter()
+    out["ct_projector_comparison_2d"] = {
+        "shape": f"512 x 512 image, 500 views, {det_count} bins",
+        "reference_published": {"init_s": 0.346, "first_fwd_s": 0.432, "avg_fwd_s": 3.59e-2, "first_back_s": 0.304,
+                                "avg_back_s": "5.93e-4 (invalid: blocks on the wrong array)"},
+        "init_s": t1 - t0, "first_fwd_s": t3 - t2, "avg_fwd_s": (t4 - t3) / 3, "first_back_s": t5 - t4, "avg_back_s": (t6 - t5) / 3}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
