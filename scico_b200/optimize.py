@@ -107,7 +107,8 @@ class _TVSolver:
                 raise ValueError(f"x0 must have shape {in_shape}")
             self.x = x0.to(device=self.dev, dtype=torch.float32).clone().contiguous()
         self.itnum = 0
-        self.history = []
+        self._history = []
+        self._stat_buf, self._stat_n, self._stat_pending = None, 0, []
 
     def _vol(self):
         return torch.empty(self.in_shape, dtype=torch.float32, device=self.dev)
@@ -183,6 +184,41 @@ class _TVSolver:
             lo, hi = self.A.owned_rows
             return self.out_shape[2], self.out_shape[1], lo - self.A.rows[0], hi - self.A.rows[0]
         return self.y.numel(), 1, 0, 1
+
+    # -- iteration statistics: device rows, read back on demand ------------------------------------
+    _STAT_ROWS = 256
+
+    @property
+    def history(self):
+        """List of per-iteration statistics (``iter``, ``objective``, ``prml_rsdl``, ``dual_rsdl``).  The sums behind
+        them are accumulated on the device by the iteration's own kernels into one row per iteration; the rows are
+        read back here (one copy for all pending iterations), so an iteration with statistics never waits for the
+        host -- reading ``history`` inside a callback costs one synchronisation, as any display of the values would."""
+        self._flush_stats()
+        return self._history
+
+    def _stat_row(self, width, to_entry):
+        """Device pointer of a zeroed row of ``width`` doubles for this iteration's sums; ``to_entry(row values)``
+        turns the row into the history entry when it is read back."""
+        if self._stat_buf is None:
+            self._stat_buf = torch.zeros((self._STAT_ROWS, width), dtype=torch.float64, device=self.dev)
+        if self._stat_n == self._STAT_ROWS:
+            self._flush_stats()
+        row = self._stat_buf[self._stat_n]
+        self._stat_n += 1
+        self._stat_pending.append((self.itnum + 1, to_entry))
+        return row
+
+    def _flush_stats(self):
+        if not self._stat_pending:
+            return
+        rows = self._stat_buf[: self._stat_n].cpu().tolist()  # stream-ordered after the kernels that wrote them
+        for (it, to_entry), vals in zip(self._stat_pending, rows):
+            entry = {"iter": it}
+            entry.update(to_entry(vals))
+            self._history.append(entry)
+        self._stat_buf[: self._stat_n].zero_()
+        self._stat_n, self._stat_pending = 0, []
 
     #: an iteration never needs the host (no scalar read back): it can be captured in a CUDA graph
     _graphable = False
@@ -318,19 +354,21 @@ class TVPDHG(_TVSolver):
             # A x of the current iterate, kept up to date by xct_l2_dual_step_stat from A xbar (no second forward
             # projection per iteration); five device doubles: ||dx||^2, ||dz1||^2, ||dz0||^2, ||Ax - y||^2, ||Dx||_{2,1}
             self.ax_x = self._sino(zero=True) if x0 is None else self.A.project(self.x).clone()
-            self._stat = torch.zeros(5, dtype=torch.float64, device=self.dev)
 
     def step(self):
         """One PDHG iteration (``_primaldual.py:219-231``).  With ``itstat`` the same kernels also accumulate the
         reference's iteration statistics (``_primaldual.py:175-217``) on the device: no copies of the old iterates,
-        no extra projection, one host read of five doubles per iteration."""
+        no extra projection, no host synchronisation (the sums are read back when ``history`` is looked at)."""
         L = _lib.lib()
         blk = ctypes.byref(self.blk)
         with torch.cuda.device(self.dev):
             st = _stream(self.dev)
             if self.itstat:
-                self._stat.zero_()
-                sp = lambda i: self._stat.data_ptr() + 8 * i  # noqa: E731
+                tau, sigma, lam = self.tau, self.sigma, self.lam
+                row = self._stat_row(5, lambda v: {  # ||dx||^2, ||dz1||^2, ||dz0||^2, ||Ax - y||^2, ||Dx||_{2,1}
+                    "objective": 0.5 * v[3] + lam * v[4], "prml_rsdl": math.sqrt(v[0]) / tau,
+                    "dual_rsdl": math.sqrt(v[2] + v[1]) / sigma})
+                sp = lambda i: row.data_ptr() + 8 * i  # noqa: E731
             self.atz = self._adj(self.z0, self.atz)                       # A^T z0
             lo = self._lo_plane(self.z1)                                  # z1[0][-1] of the previous slab
             if self.itstat:
@@ -356,13 +394,9 @@ class TVPDHG(_TVSolver):
                                               self.sigma, self.lam, st))
                 _lib.check(L.xct_l2_dual_step(self.z0.numel(), self.z0.data_ptr(), self.ax.data_ptr(),
                                               self.y.data_ptr(), self.sigma, st))
+            if self.itstat and self.world > 1:
+                dist.all_reduce(row, group=self.group)
         self.itnum += 1
-        if self.itstat:
-            if self.world > 1:
-                dist.all_reduce(self._stat, group=self.group)
-            dx, dz1, dz0, res, tv = (float(v) for v in self._stat.cpu())
-            self.history.append({"iter": self.itnum, "objective": 0.5 * res + self.lam * tv,
-                                 "prml_rsdl": math.sqrt(dx) / self.tau, "dual_rsdl": math.sqrt(dz0 + dz1) / self.sigma})
 
     @staticmethod
     def estimate_parameters(A, ratio: float = 1.0, factor: Optional[float] = 1.01, maxiter: int = 100, seed: int = 0):
@@ -530,11 +564,16 @@ class _TVSplitSolver(_TVSolver):
             self.ax = self._fwd(self.x, self.ax)
             hi = self._hi_plane(self.x.reshape(self.vol_shape))
             if self.itstat:
-                # the statistics' sums come out of the two prox kernels (six device doubles, one host read)
-                if getattr(self, "_stat", None) is None:
-                    self._stat = torch.zeros(6, dtype=torch.float64, device=self.dev)
-                self._stat.zero_()
-                sp = self._stat.data_ptr()
+                # the statistics' sums come out of the two prox kernels: (||Cx - z||^2, ||dz||^2, g(z) sum) of the
+                # gradient block, then of the sinogram block; read back when `history` is looked at
+                lam_g = self.lam / dscale
+                if slow_dual:
+                    row = self._stat_row(7, lambda v: {"objective": 0.5 * v[5] + lam_g * v[2],
+                                                       "prml_rsdl": math.sqrt(v[3] + v[0]), "dual_rsdl": math.sqrt(v[6])})
+                else:
+                    row = self._stat_row(7, lambda v: {"objective": 0.5 * v[5] + lam_g * v[2],
+                                                       "prml_rsdl": math.sqrt(v[3] + v[0]), "dual_rsdl": math.sqrt(v[4] + v[1])})
+                sp = row.data_ptr()
                 _lib.check(L.xct_grad_prox_step_stat(blk, self.x.data_ptr(), self._ptr(hi), self.z1.data_ptr(),
                                                      self.u1.data_ptr(), self.w1.data_ptr(), dscale, thr, inv_nu, mode, sp, st))
                 _lib.check(L.xct_sino_prox_step_stat(self.z0.numel(), self.ax.data_ptr(), self.y.data_ptr(), self.z0.data_ptr(),
@@ -545,20 +584,14 @@ class _TVSplitSolver(_TVSolver):
                                                 self.w1.data_ptr(), dscale, thr, inv_nu, mode, st))
                 _lib.check(L.xct_sino_prox_step(self.z0.numel(), self.ax.data_ptr(), self.y.data_ptr(), self.z0.data_ptr(),
                                                 self.u0.data_ptr(), self.w0.data_ptr(), c, inv_nu, mode, st))
+            if self.itstat:
+                if slow_dual:  # ||C^T (z - z_old)||^2 (this rank's voxels) into the row's last slot
+                    e0, e1 = self.z0 - z_old[0], self.z1 - z_old[1]
+                    ct = self.A.back_project(e0).reshape(self.vol_shape) + dscale * self._fd().adj(e1, self._lo_plane(e1))
+                    row[6] = (ct.double() ** 2).sum()
+                if self.world > 1:
+                    dist.all_reduce(row, group=self.group)
         self.itnum += 1
-        if self.itstat:
-            if self.world > 1:
-                dist.all_reduce(self._stat, group=self.group)
-            pr1, dz1, g1, pr0, dz0, res = (float(v) for v in self._stat.cpu())
-            if slow_dual:
-                e0, e1 = self.z0 - z_old[0], self.z1 - z_old[1]
-                D = self._fd()
-                du = self._norm(self.A.back_project(e0).reshape(self.vol_shape) + dscale * D.adj(e1, self._lo_plane(e1)))
-            else:
-                du = math.sqrt(dz0 + dz1)
-            # f(x) + g(z) (_padmm.py:148-177, _ladmm.py:130-158), ||A x + B z|| with B = -I, dual residual
-            self.history.append({"iter": self.itnum, "objective": 0.5 * res + (self.lam / dscale) * g1,
-                                 "prml_rsdl": math.sqrt(pr0 + pr1), "dual_rsdl": du})
 
     @property
     def z(self):

@@ -52,7 +52,11 @@ def main():
         S.step()
     sync()
     t4 = time.perf_counter()
+    hist = S.history  # the statistics' read-back belongs to the solve
+    sync()
+    t4 = time.perf_counter()
     x = S.x.cpu().numpy()
+    t4b = time.perf_counter()
     S2 = TVProximalADMM(A, y, E.LAM, E.RHO, mu, nu, alpha=E.ALPHA, maxiter=E.MAXITER)
     S2.step()
     sync()
@@ -65,10 +69,10 @@ def main():
         "shape": "64 x 256 x 128 volume, 10 views, 64 x 256 detector, ProximalADMM, 1000 iterations",
         "reference_published_s": 26.6, "reference_first_iteration_s": 1.65, "reference_hw": "RTX 2080 Ti (notebook cell 7)",
         "solve_s_itstats_on": (t3 - t2) + (t4 - t3), "first_iteration_s": t3 - t2, "iters_per_s_itstats_on": (E.MAXITER - 1) / (t4 - t3),
-        "solve_s_itstats_off": t6 - t4 - 0.0, "iters_per_s_itstats_off": (E.MAXITER - 1) / (t6 - t5),
+        "solve_s_itstats_off": t6 - t4b, "iters_per_s_itstats_off": (E.MAXITER - 1) / (t6 - t5),
         "setup_s_operator_and_sinogram": t1 - t0, "estimate_parameters_s": t2 - t1,
         "snr_db": float(E.snr_db(x_gt, x)), "reference_snr_db": 14.36, "mae": E.mae(x_gt, x), "reference_mae": 0.048,
-        "final_objective": S.history[-1]["objective"], "reference_final_objective": 3.546e5}
+        "final_objective": hist[-1]["objective"], "reference_final_objective": 3.546e5}
 
     # --- ct_projector_comparison_3d
     n = 128
