@@ -21,9 +21,13 @@ Restates, in float32 and in the reference's operation order:
 * ``ProximalADMM.step`` for ``A = VerticalStack((C, alpha*D))``, ``B = -I``
   (``examples/scripts/ct_3d_tv_padmm.py:96-120``): ``scico/optimize/_padmm.py:349-363``.
 
-Pinning: these functions have no golden vectors in the reference's tests beyond generic operator
+Pinning: the reference's tests hold no golden vectors for these functions beyond generic operator
 identities (``scico/test/linop/test_diff.py``, ``scico/test/functional/test_norm.py`` check the adjoint
-identity and prox optimality); ``tests/test_tv_oracle.py`` checks the same identities here.
+identity and prox optimality); ``tests/test_tv_oracle.py`` checks the same identities here, the reference's
+own ``cg`` / ``L21Norm.prox`` files executed over the NumPy ``jax`` stand-in give identical iterates, and
+``padmm_tv_step`` together with the C projector pair reproduces the iteration-statistics table the reference
+itself printed (real JAX / XLA) in ``data/notebooks/ct_3d_tv_padmm.ipynb``
+(``tests/test_reference_notebook.py``, fixture ``tests/golden/nb_ct_3d_tv_padmm.npz``).
 """
 from __future__ import annotations
 
