@@ -8,17 +8,24 @@ ALPHA, LAM, RHO, MAXITER = 1e2, 2e0, 5e-3, 1000
 
 
 def tangle_phantom(nx=NX, ny=NY, nz=NZ):
-    xs = 1.0 * np.linspace(-1.0, 1.0, nx, dtype=np.float32)
-    ys = 1.0 * np.linspace(-1.0, 1.0, ny, dtype=np.float32)
-    zs = 1.0 * np.linspace(-1.0, 1.0, nz, dtype=np.float32)
-    xx, yy, zz = np.meshgrid(ys, zs, xs, copy=True)  # (nz, ny, nx)
-    xx, yy, zz = 3.0 * xx, 3.0 * yy, 3.0 * zz
-    v = (xx * xx * xx * xx - 5.0 * xx * xx + yy * yy * yy * yy - 5.0 * yy * yy + zz * zz * zz * zz - 5.0 * zz * zz
-         + 11.8) * 0.2 + 0.5
-    v[v <= 2.0] = 2.0 - v[v <= 2.0]
-    v[v > 2.0] = 0.0
-    v[v < 0.0] = 0.0
-    return v
+    """(nz, ny, nx) float32 tanglecube phantom: p = 2 - t where 0 <= t <= 2, else 0, with
+    t = 0.2 (x^4 - 5 x^2 + y^4 - 5 y^2 + z^4 - 5 z^2 + 11.8) + 0.5 on [-3, 3]^3; float32 throughout and summed in the
+    reference's order (first the axis of length ny, then nz, then nx: its meshgrid naming), so the values are the
+    reference's bit for bit."""
+    def quartic(n):
+        t = np.float32(3.0) * np.linspace(-1.0, 1.0, n, dtype=np.float32)
+        return t * t * t * t, np.float32(5.0) * t * t
+
+    (qy, sy), (qz, sz), (qx, sx) = quartic(ny), quartic(nz), quartic(nx)
+    acc = np.broadcast_to(qy[None, :, None], (nz, ny, nx)) - sy[None, :, None]
+    acc = acc + qz[:, None, None]
+    acc = acc - sz[:, None, None]
+    acc = acc + qx[None, None, :]
+    acc = acc - sx[None, None, :]
+    t = (acc + np.float32(11.8)) * np.float32(0.2) + np.float32(0.5)
+    p = np.float32(2.0) - t
+    # the reference flips t <= 2 to 2 - t FIRST and then zeroes everything above 2: t < 0 (p > 2) ends up 0 as well
+    return np.where((t <= 2.0) & (p <= 2.0), p, np.float32(0.0)).astype(np.float32)
 
 
 def geometry():

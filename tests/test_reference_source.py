@@ -82,3 +82,33 @@ def test_tv_oracle_pieces_equal_the_reference_source():
         assert info["num_iter"] == io["num_iter"]
         np.testing.assert_array_equal(np.asarray(xr), xo)
         assert abs(float(info["rel_res"]) - io["rel_res"]) <= 1e-6 * max(io["rel_res"], 1e-30)
+
+
+@needs_reference
+def test_example_phantom_and_notebook_numbers_come_from_the_reference():
+    """The tangle phantom of the notebook-pin tests equals ``scico/examples.py::create_tangle_phantom`` (the function is
+    taken out of the reference file with ``ast`` and executed as it stands: plain NumPy, no jax in it) bit for bit, and
+    ``nb_ct_3d_tv_padmm.npz`` regenerates from the reference's notebook."""
+    import ast
+
+    import _ct3d_example as E
+
+    path = "/root/reference/scico/examples.py"
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "create_tangle_phantom")
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    for shape in ((128, 256, 64), (7, 5, 9)):
+        np.testing.assert_array_equal(E.tangle_phantom(*shape), ns["create_tangle_phantom"](*shape))
+
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_notebook_golden", os.path.join(HERE, "golden", "make_notebook_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    kept = np.load(os.path.join(HERE, "golden", "nb_ct_3d_tv_padmm.npz"))
+    keep = {k: kept[k].copy() for k in ("objective", "prml_rsdl", "dual_rsdl", "snr_db", "mae")}
+    mod.main()  # rewrites the fixture in place from the notebook
+    again = np.load(os.path.join(HERE, "golden", "nb_ct_3d_tv_padmm.npz"))
+    for k, v in keep.items():
+        np.testing.assert_array_equal(again[k], v, err_msg=k)
