@@ -129,3 +129,90 @@ def test_c3_4096sq_2048views_2d(cuda_device):
     # mass conservation: default det_count covers the diagonal, nothing falls off
     ones = A(torch.ones((n, n), device=cuda_device))
     assert torch.allclose(ones.sum(dim=1), torch.full((V,), float(n * n), device=cuda_device), rtol=1e-5)
+
+
+def test_more_than_2_to_the_31_elements_per_array(cuda_device):
+    """Volume and sinogram of 2112 x 1024 x 1024 = 2.21e9 elements each (8.9 GB; a B200 holds arrays far beyond the
+    range of 32-bit element offsets): adjoint identity, and the oracle on the LAST slices / rows / views, whose element
+    offsets lie above 2^31 (byte offsets above 2^33)."""
+    import torch
+
+    n0, n, V = 2112, 1024, 1024
+    N, D = (n0, n, n), (n0, n)
+    assert n0 * n * n > 2**31 and V * n0 * n > 2**31
+    M = _x_mats(N, D, V)
+    A = sb.XRayTransform3D(N, M, D)
+    assert A.plan_info()["path_name"] == "3d_sep"
+    g = torch.Generator(device=cuda_device).manual_seed(7)
+    x = torch.randn(N, device=cuda_device, generator=g)
+    y = torch.randn(A.output_shape, device=cuda_device, generator=g)
+    Ax = A(x)
+    ATy = A.adj(y)
+    ns, ref = _dots(torch, Ax, y, x, ATy)
+    assert ns < TOL and ref < 1e-4, (ns, ref)
+    # forward: complete views (the first and the last ones) of the first and the last 4-slice slab
+    vs = [0, 300, V - 2, V - 1]
+    for z0 in (0, n0 - 4):
+        z1 = z0 + 4
+        want_f = C.project_3d(x[z0:z1].cpu().numpy(), A.matrices[vs], D, slice_offset=z0, fused=True)[:, z0:z1]
+        got_f = Ax[vs][:, z0:z1].cpu().numpy()
+        assert max(O.rel_l2(got_f[i], want_f[i]) for i in range(len(vs))) <= TOL, z0
+    del Ax, x
+    # back projection: voxels of the last 64 slices (and a few of the first ones) against the oracle
+    rng = np.random.default_rng(2)
+    hi = np.stack([rng.integers(n0 - 64, n0, 1024), rng.integers(0, n, 1024), rng.integers(0, n, 1024)], 1)
+    lo = np.stack([rng.integers(0, 8, 64), rng.integers(0, n, 64), rng.integers(0, n, 64)], 1)
+    pts = np.concatenate([hi, lo, [[n0 - 1, n - 1, n - 1]]]).astype(np.int32)
+    want = C.back_project_3d_points(y.cpu().numpy(), A.matrices, pts)
+    got = ATy[pts[:, 0], pts[:, 1], pts[:, 2]].cpu().numpy()
+    assert O.rel_l2(got, want) <= TOL
+
+
+def test_more_than_2_to_the_31_voxels_general_matrices(cuda_device):
+    """The brick kernels (tilted geometry: general 2 x 4 matrices) on a 1312^3 volume (2.26e9 voxels, 9.0 GB): adjoint
+    identity, and the back projection against the oracle at voxels whose element offsets lie above 2^31."""
+    import torch
+
+    n, V = 1312, 6
+    N, D = (n, n, n), (1856, 1856)
+    assert n**3 > 2**31
+    ang = np.stack([np.linspace(0, np.pi, V, endpoint=False), np.full(V, np.deg2rad(74.0))], 1)
+    A = sb.XRayTransform3D(N, sb.matrices_from_euler_angles(N, D, "XY", ang), D)
+    assert A.plan_info()["path_name"] == "3d_general"
+    g = torch.Generator(device=cuda_device).manual_seed(8)
+    x = torch.randn(N, device=cuda_device, generator=g)
+    y = torch.randn(A.output_shape, device=cuda_device, generator=g)
+    Ax, ATy = A(x), A.adj(y)
+    ns, ref = _dots(torch, Ax, y, x, ATy)
+    assert ns < TOL and ref < 1e-4, (ns, ref)
+    rng = np.random.default_rng(3)
+    hi = np.stack([rng.integers(n - 32, n, 2048), rng.integers(0, n, 2048), rng.integers(0, n, 2048)], 1)
+    lo = np.stack([rng.integers(0, n, 512), rng.integers(0, n, 512), rng.integers(0, n, 512)], 1)
+    pts = np.concatenate([hi, lo, [[n - 1, n - 1, n - 1], [0, 0, 0]]]).astype(np.int32)
+    want = C.back_project_3d_points(y.cpu().numpy(), A.matrices, pts)
+    got = ATy[pts[:, 0], pts[:, 1], pts[:, 2]].cpu().numpy()
+    assert O.rel_l2(got, want) <= TOL
+
+
+def test_more_than_2_to_the_31_pixels_2d(cuda_device):
+    """2D image of 47104^2 = 2.22e9 pixels (8.9 GB), two views: adjoint identity, both views against the oracle (forward)
+    and the first / last image rows of the oracle's back projection (pixel offsets above 2^31)."""
+    import torch
+
+    n = 47104
+    assert n * n > 2**31
+    angles = np.array([0.3, 1.9])
+    A = sb.XRayTransform2D((n, n), angles)
+    g = torch.Generator(device=cuda_device).manual_seed(9)
+    x = torch.randn((n, n), device=cuda_device, generator=g)
+    y = torch.randn(A.output_shape, device=cuda_device, generator=g)
+    Ax, ATy = A(x), A.adj(y)
+    ns, ref = _dots(torch, Ax, y, x, ATy)
+    assert ns < TOL, (ns, ref)
+    T = A.view_table
+    want = C.project_2d(x.cpu().numpy(), T, A.ny, fused=True)
+    assert O.rel_l2(Ax.cpu().numpy(), want) <= TOL
+    del x, want
+    want_a = C.back_project_2d(y.cpu().numpy(), T, (n, n))
+    for sl in (slice(0, 64), slice(n - 64, n)):
+        assert O.rel_l2(ATy[sl].cpu().numpy(), want_a[sl]) <= TOL, sl
