@@ -13,7 +13,7 @@ from oracle import xray_c as C
 from oracle import xray_np as O
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+FILES = sorted(f for f in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(f).startswith("nb_"))  # nb_*: notebook tables
 
 
 def test_fixture_inventory():

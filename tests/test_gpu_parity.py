@@ -20,7 +20,7 @@ from oracle import xray_np as O
 
 TOL = 1e-5
 HERE = os.path.dirname(os.path.abspath(__file__))
-GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+GOLDEN = sorted(f for f in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(f).startswith("nb_"))  # nb_*: notebook tables
 
 
 @pytest.fixture(scope="module")
