@@ -45,6 +45,7 @@ constexpr int kWarps = 8;
 constexpr int kAdjWin = 64;
 constexpr int kAdj3S = 4, kAdj3TA = 16;
 constexpr int kAdj2S = 1, kAdj2TA = 32;
+constexpr int kAdj2bS = 4, kAdj2bTA = 16;  // 2D image batches (>= 3 images): coordinates and weights of a (view, pixel) serve 4 images
 // forward
 constexpr int kFwdWin = 96;
 constexpr int kFwd3S = 2, kFwd3TN = 16;
@@ -1447,7 +1448,12 @@ int xct_adjoint(const xct_plan* pl, const float* in, float* out, int32_t batch, 
     xct::gen3d_adjoint_kernel<false><<<general_grid(in_elems(pl)), 256, 0, st>>>(gen3_params(pl), in, out, xct::OutRoute{});
     return launch_ok("gen3d_adjoint_kernel");
   }
-  if (pl->adj_plane) return launch_plane_adjoint<xct::Geom2, false, kAdj2S, kAdj2TA>(pl, batch, in, out, st);
+  if (pl->adj_plane) {
+    // a batch shares the geometry: four images per thread amortise the coordinate / weight arithmetic that bounds the
+    // single-image kernel (same taps in the same order per image: bit-identical to image-by-image calls)
+    if (batch >= 3) return launch_plane_adjoint<xct::Geom2, false, kAdj2bS, kAdj2bTA>(pl, batch, in, out, st);
+    return launch_plane_adjoint<xct::Geom2, false, kAdj2S, kAdj2TA>(pl, batch, in, out, st);
+  }
   xct::gen2d_adjoint_kernel<false><<<general_grid(in_elems(pl) * batch), 256, 0, st>>>(gen2_params(pl, batch), in, out, xct::OutRoute{});
   return launch_ok("gen2d_adjoint_kernel");
 }

@@ -678,6 +678,23 @@ def test_2d_batch(torch_dev):
         A(torch.as_tensor(xb, device=dev))  # __call__ enforces the exact input_shape
 
 
+def test_2d_batch_adjoint_four_images_per_thread_is_bit_identical_to_single_images(torch_dev):
+    """Batches of three and more images take plane_adjoint_kernel<Geom2, S = 4>: one coordinate / weight evaluation per
+    (view, pixel) for four images.  Same taps in the same order per image, so the result equals image-by-image calls
+    bit for bit; ragged batch (6 = 4 + 2), anisotropic pixels, a short detector (out-of-range bins)."""
+    torch, dev = torch_dev
+    rng = np.random.default_rng(21)
+    for nx, V, kw, nb in (((70, 90), 33, {}, 6), ((130, 65), 48, dict(dx=(0.6, 0.45), det_count=61), 5), ((33, 200), 20, {}, 3)):
+        A = sb.XRayTransform2D(nx, np.linspace(0, 2 * np.pi, V, endpoint=False), **kw)
+        yb = torch.as_tensor(rng.standard_normal((nb,) + A.output_shape).astype(np.float32), device=dev)
+        got = A.back_project(yb)
+        for b in range(nb):
+            one = A.back_project(yb[b].contiguous())
+            d = (got[b] - one).double()
+            assert float(torch.linalg.vector_norm(d) / torch.linalg.vector_norm(one.double())) <= 1e-6, (nx, b)
+        assert O.rel_l2(got[nb - 1].cpu().numpy(), C.back_project_2d(yb[nb - 1].cpu().numpy(), A.view_table, nx)) <= TOL
+
+
 def test_mass_conservation(torch_dev):
     """Per voxel the 2 (2D) / 4 (3D) weights sum to 1: each view's projection sums to sum(x)
     when nothing falls off the detector (SURVEY.md section 8a invariants)."""
