@@ -445,6 +445,7 @@ class TVADMM(_TVSolver):
         self.cg_info = {"num_iter": 0, "rel_res": 0.0}
         self.cg_iters_total = 0
         self.cg_trace, self.cg_tol_sq = [], 0.0
+        self.ax_x = None
 
     def _allreduce(self, i):
         if self.world > 1:
@@ -466,6 +467,13 @@ class TVADMM(_TVSolver):
         _lib.check(L.xct_admm_rhs(blk, self.aty.data_ptr(), self.z1.data_ptr(), self.u1.data_ptr(), self._ptr(zu_lo),
                                   self.rho, self.rhs.data_ptr(), sp(5), st))
         self.ax = self._fwd(self.x, self.ax)
+        if self.itstat:
+            # A x for the objective of the iteration statistics: anchored here on the exact A x_k, then carried
+            # through the CG updates x += alpha p with the A p every CG iteration computes anyway
+            # (A x += alpha A p) -- no forward projection of its own
+            if self.ax_x is None:
+                self.ax_x = torch.empty_like(self.ax)
+            self.ax_x.copy_(self.ax)
         self.atq = self._adj(self.ax, self.atq)
         lo, hi = self._halos(self.x)
         _lib.check(L.xct_cg_init(blk, self.x.data_ptr(), self._ptr(lo), self._ptr(hi), self.atq.data_ptr(),
@@ -493,6 +501,8 @@ class TVADMM(_TVSolver):
             self._allreduce(pq)
             _lib.check(L.xct_cg_update_xr(n, self.x.data_ptr(), self.r.data_ptr(), self.p.data_ptr(), self.q.data_ptr(),
                                           sp(cur), sp(pq), sp(nxt), sp(pq_nxt), st))
+            if self.itstat:
+                self.ax_x.addcmul_(self.ax, (sc[cur] / sc[pq]).to(torch.float32))  # alpha of this CG iteration, on the device
             self._allreduce(nxt)
             _lib.check(L.xct_cg_update_p(n, self.p.data_ptr(), self.r.data_ptr(), sp(cur), sp(nxt), st))
             num = float(f32(sc[nxt].item()))
@@ -519,7 +529,7 @@ class TVADMM(_TVSolver):
             pr = math.sqrt(self.rho) * self._norm(D(xv, self._hi_plane(xv)) - self.z1)  # _admm.py:253-277
             dz = self.z1 - z_old
             du = self.rho * self._norm(D.adj(dz, self._lo_plane(dz)))                     # _admm.py:279-295
-            r = self._owned(self.A.project(self.x) - self.y)
+            r = self._owned(self.ax_x - self.y)                                           # ax_x = A x, see _xstep
             obj = 0.5 * self._sum(r.double() ** 2) + self.lam * self._l21(self.z1)        # f(x) + g(z), _admm.py:215-251
             self.history.append({"iter": self.itnum, "objective": obj, "prml_rsdl": pr, "dual_rsdl": du,
                                  "cg_iters": self.cg_info["num_iter"], "cg_rel_res": self.cg_info["rel_res"]})

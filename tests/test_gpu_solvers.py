@@ -257,7 +257,14 @@ def test_admm_with_tolerance_stop_converges_like_the_oracle(cuda_device):
     for _ in range(iters):
         x, z, u, info = T.admm_tv_step(x, z, u, Ao, ATo, y, lam, rho, cg_tol=1e-4, cg_maxiter=25)
         its.append(info["num_iter"])
-    S.solve()
+    def check_objective(solver):
+        # the statistics' objective uses A x carried through the CG updates (A x += alpha A p): equal to the objective
+        # evaluated with a forward projection of its own
+        zt = solver.z1.double()
+        explicit = 0.5 * float(((A.project(solver.x) - solver.y).double() ** 2).sum()) + lam * float(torch.sqrt((zt ** 2).sum(0)).sum())
+        assert abs(solver.history[-1]["objective"] - explicit) <= 1e-5 * explicit
+
+    S.solve(callback=check_objective)
     assert abs(S.cg_iters_total - sum(its)) <= iters
     assert O.rel_l2(S.x.cpu().numpy(), x) <= 5e-3  # one CG iteration apart moves x by a few 1e-3 (seen: 2.05e-3)
     h = S.history
