@@ -87,6 +87,7 @@ constexpr int kWFwdS = 4, kWFwdTN = 8;     // walk forward tile: 64 (major) x 8 
 // views a warp walks together over the tile (1 or 2): the voxel loads of a step are shared.  Measured at C5
 // (ms per application; one view x 12 warps: 305.4 -> 301.1 with the two columns' coordinates in packed fp32):
 // two views x 12 warps 295.8, two views x 10 warps 291.3; 8 slices x two views x 12 warps (1 CTA per SM) 296.3;
+// THREE views x 8 warps (127 registers, 2 CTAs per SM) 290.6 against 291.2 in the same run, x 7 warps 306.1: no gain;
 // shared-memory data pipe 89 % -> 71 % busy, issue slots 78 % -> 80 % (profiles/ncu_r02_walk.md)
 #define XCT_TILE_NVW 2
 #endif

@@ -1040,7 +1040,7 @@ template <class G, int S, int TN, int WIN, bool MAJOR_B, bool MINOR_UP, bool MAJ
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 walk_forward_tile_kernel(Walk2Params wp, const float* __restrict__ in, float* __restrict__ sino) {
   static_assert(WIN % 32 == 0 && WIN <= 128 && (S == 4 || S == 8), "float4 window slots, flushed 4 bins per lane in one pass");
-  static_assert(NVW == 1 || NVW == 2, "one or two views per warp pass");
+  static_assert(NVW >= 1 && NVW <= 3, "one to three views per warp pass");
   using Vec = float4;
   // S slices = NV planes of 4: the tile and the windows are arrays of float4 per plane, so every shared access
   // stays a conflict-free LDS.128 / STS.128 over 512 contiguous bytes; the coordinates, bins and weights of a
