@@ -134,7 +134,7 @@ def _worker(rank, world, port, case, exchange, rendezvous="flags"):
                 for key in ("objective", "prml_rsdl", "dual_rsdl"):
                     assert abs(a[key] - b[key]) <= 2e-5 * abs(b[key]) + 1e-12, (key, a, b)
             assert abs(S.history[-1]["objective"] - S.objective()) <= 1e-5 * S.objective()
-        elif case == "padmm_notebook_slabs":
+        elif case in ("padmm_notebook_slabs", "padmm_notebook_views"):
             # the reference's published ct_3d_tv_padmm run (tests/golden/nb_ct_3d_tv_padmm.npz: the iteration statistics
             # its ProximalADMM printed with real JAX / XLA, see tests/test_gpu_reference_notebook.py) reproduced by the
             # z-slab PARTITION: every rank holds its slices of the 64 x 256 x 128 volume and its detector rows, the
@@ -152,10 +152,18 @@ def _worker(rank, world, port, case, exchange, rendezvous="flags"):
             x_gt = E.tangle_phantom()
             full = sb.XRayTransform3D(N, M, D)
             y = full(torch.as_tensor(x_gt, device=dev))
-            op = sharded.SlabShardedXRayTransform3D(N, M, D)
-            (z0, z1), (r0, r1) = op.slab, op.rows
+            if case == "padmm_notebook_views":
+                # ... and by the VIEW-BLOCK partition: sinogram state in view blocks, volume state in z-slabs, every one
+                # of the 1000 back projections exchanging its rows through the kernel's routed epilogue (peer memory)
+                op = sharded.ViewShardedXRayTransform3D(N, M, D, exchange=exchange, rendezvous=rendezvous, peer_timeout_s=20.0)
+                v0, v1 = op.views
+                y_loc = y[v0:v1].contiguous()
+            else:
+                op = sharded.SlabShardedXRayTransform3D(N, M, D)
+                r0, r1 = op.rows
+                y_loc = y[:, r0:r1].contiguous()
             mu, nu = TVProximalADMM.estimate_parameters(op, alpha=E.ALPHA)
-            S = TVProximalADMM(op, y[:, r0:r1].contiguous(), E.LAM, E.RHO, mu, nu, alpha=E.ALPHA, maxiter=E.MAXITER, itstat=True)
+            S = TVProximalADMM(op, y_loc, E.LAM, E.RHO, mu, nu, alpha=E.ALPHA, maxiter=E.MAXITER, itstat=True)
             S.solve()
             h = S.history
             assert len(h) == E.MAXITER
@@ -166,6 +174,9 @@ def _worker(rank, world, port, case, exchange, rendezvous="flags"):
             dist.all_gather(parts, S.x.cpu())
             x_rec = torch.cat(parts).numpy()
             assert abs(E.snr_db(x_gt, x_rec) - float(g["snr_db"])) <= 0.02 and abs(E.mae(x_gt, x_rec) - float(g["mae"])) <= 1e-3
+            if case == "padmm_notebook_views":
+                assert not op.peer.mem.timed_out()
+                op.close()
         else:
             raise AssertionError(case)
         torch.cuda.synchronize()
@@ -184,7 +195,7 @@ CASES = [
     ("view3d_sep", 2, "peer", "flags"), ("view3d_sep", 3, "peer_add", "flags"),
     ("pdhg_view3d", 2, "peer", "flags"),
     ("pdhg_slab_stats", 2, "nccl", "flags"), ("pdhg_slab_stats", 3, "nccl", "flags"),
-    ("padmm_notebook_slabs", 2, "nccl", "flags"),
+    ("padmm_notebook_slabs", 2, "nccl", "flags"), ("padmm_notebook_views", 2, "peer", "flags"),
 ]
 
 
