@@ -9,7 +9,8 @@ fused iteration statistics -- and has to reproduce the reference's table.
 
 The one input that cannot be replayed is the random start vector of the reference's power iteration (`mu`, a JAX PRNG
 stream): 100 iterations from another start give `||A||^2` to a few 1e-4, which moves the statistics in the fourth
-digit; the tolerances (1e-3 on the objective, 5e-3 on the residuals, all 1000 rows) say so."""
+digit; the tolerances (1e-3 on the objective, 5e-3 on the residuals, all 1000 rows) say so.  They are sharp: a `mu`
+1 % off moves the dual residual of iteration 3 by 3.3 % and the objective of iteration 7 by 0.2 %."""
 import os
 
 import numpy as np
