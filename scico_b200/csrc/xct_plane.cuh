@@ -135,10 +135,18 @@ plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __res
   for (int v = v_begin; v < v_end; ++v) {
     float* zb = zs + ((v - v_begin) & 1) * (S * WIN);
     const int c0 = c0_next;
+    if constexpr (S == 4) {
+      // four slices: the window is [bin][slice], one float4 per bin, so that a tap of all four slices is ONE LDS.128
+      // (a quarter-warp's 8 lanes sit on <= 8 consecutive bins: conflict-free) instead of four LDS.32
 #pragma unroll
-    for (int s = 0; s < S; ++s)
+      for (int q = 0; q < Q; ++q)
+        reinterpret_cast<float4*>(zb)[lane + 32 * q] = make_float4(pre[0][q], pre[1][q], pre[2][q], pre[3][q]);
+    } else {
 #pragma unroll
-      for (int q = 0; q < Q; ++q) zb[s * WIN + lane + 32 * q] = pre[s][q];
+      for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int q = 0; q < Q; ++q) zb[s * WIN + lane + 32 * q] = pre[s][q];
+    }
     __syncwarp();
     if (v + 1 < v_end) fetch(v + 1, c0_next);
 
@@ -172,10 +180,18 @@ plane_adjoint_kernel(PlaneParams p, const float* __restrict__ sino, float* __res
         G::bins(vr, u, c, w0, w1);
         int t = c - c0;
         t = min(max(t, 0), WIN - 2);  // never taken for validated plans; keeps smem access in range
-        const float* z = zb + t;
+        if constexpr (S == 4) {
+          const float4 lo = reinterpret_cast<const float4*>(zb)[t], hi = reinterpret_cast<const float4*>(zb)[t + 1];
+          acc[n][0] = fmaf(hi.x, w1, fmaf(lo.x, w0, acc[n][0]));
+          acc[n][1] = fmaf(hi.y, w1, fmaf(lo.y, w0, acc[n][1]));
+          acc[n][2] = fmaf(hi.z, w1, fmaf(lo.z, w0, acc[n][2]));
+          acc[n][3] = fmaf(hi.w, w1, fmaf(lo.w, w0, acc[n][3]));
+        } else {
+          const float* z = zb + t;
 #pragma unroll
-        for (int s = 0; s < S; ++s)
-          acc[n][s] = fmaf(z[s * WIN + 1], w1, fmaf(z[s * WIN], w0, acc[n][s]));
+          for (int s = 0; s < S; ++s)
+            acc[n][s] = fmaf(z[s * WIN + 1], w1, fmaf(z[s * WIN], w0, acc[n][s]));
+        }
       }
     }
   }
