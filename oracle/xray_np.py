@@ -6,7 +6,7 @@ This file is the *oracle*: a CPU restatement of the algorithm in the reference's
 CUDA path.  Nothing under ``scico_b200/`` may import it.
 
 Pinning status.  JAX is not installable in this image, so the reference cannot run on
-its own array library.  Two pins instead:
+its own array library.  Three pins instead:
 
 1. The reference's OWN SOURCE FILES (``_xray2d.py``, ``_xray3d.py``, loaded unmodified from
    /root/reference) are executed over a NumPy stand-in for the few ``jax`` entry points
@@ -23,7 +23,13 @@ its own array library.  Two pins instead:
 * ``scico/test/linop/xray/test_xray_2d.py:88-102`` FBP PSNR > 28 dB (4 cases),
 * ``scico/test/linop/xray/astra/test_astra_3d.py:200-222`` geometry known answer.
 
-What is NOT pinned (and cannot be here): what only XLA decides -- its fp32 ``cos``/``sin``,
+3. Output of the REAL reference (JAX / XLA on a GPU): the iteration-statistics table its ProximalADMM
+   printed in the executed notebook ``data/notebooks/ct_3d_tv_padmm.ipynb`` (objective and residuals of
+   1000 iterations, 4 significant digits; ``tests/golden/nb_ct_3d_tv_padmm.npz``).  The C port of this
+   oracle plus ``oracle/tv_np.py`` rebuild that example and print the same numbers
+   (``tests/test_reference_notebook.py``) -- the 3D projector pair inside a full solve.
+
+What is NOT pinned bit for bit (and cannot be here): what only XLA decides -- its fp32 ``cos``/``sin``,
 FMA contraction and scatter order.  The oracle (like the stand-in) *defines* those as strict
 IEEE fp32, no contraction, NumPy float32 ``cos``/``sin``.
 
